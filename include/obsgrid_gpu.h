@@ -1,0 +1,245 @@
+/*
+ * obsgrid_gpu.h -- C ABI of libobsgrid_gpu.so, the B200 (sm_100a) implementation of
+ * OBSGRID's objective-analysis hot path.
+ *
+ * The Fortran driver of wrf-model/OBSGRID keeps everything above this boundary
+ * (namelist, little_r ingest, linked-list obs store, netCDF I/O).  The entry points
+ * below replace, one for one, the flat-array procedures the reference's stage
+ * drivers call (all file:line citations are relative to the reference tree):
+ *
+ *   og_innovation  <- inline loops station_loop_1fg / station_loop_5fg,
+ *                     src/proc_oa.F90:517-554 and :750-778
+ *   og_cressman    <- SUBROUTINE cressman, src/oa_module.F90:25-218
+ *                     (dist_uu_vv_rh :229-574, dist_not_uu_vv_rh :577-627,
+ *                      smooth_5 :928-1006, smoother_desmoother :875-923)
+ *   og_oa_slab     <- the multi_scan loop of one (level, variable) slab,
+ *                     src/proc_oa.F90:491-825 (radius scaling :663-707, clean_rh :803)
+ *   og_error_max   <- SUBROUTINE error_max,   src/qc1_module.F90:9-300
+ *   og_buddy_check <- SUBROUTINE buddy_check, src/qc2_module.F90:9-388
+ *   og_qc_slab     <- the error_max + buddy_check pair of one slab, fused,
+ *                     src/proc_qc.F90:371-392
+ *   og_local_time  <- SUBROUTINE local, src/qc0_module.F90:236-309
+ *   og_qc_time / og_oa_time <- the level x variable loops of proc_qc
+ *                     (src/proc_qc.F90:243-408 + qc_consistency, qc0_module.F90:313-434)
+ *                     and proc_oa (src/proc_oa.F90:356-849) over one analysis time,
+ *                     fed from a flat SoA observation table instead of per-slab
+ *                     proc_ob_access calls (src/proc_ob_access.F90:146-403).
+ *
+ * Conventions
+ *   - plain C: pointers, ints, floats.  No torch / C++ types cross this boundary.
+ *   - every array argument is HOST memory owned by the caller; the library stages it
+ *     through its own pinned buffers and never keeps a pointer after the call returns.
+ *     (The og_dev_* entry points at the bottom take DEVICE pointers; they exist for
+ *     benchmarks and for callers that already keep the data resident.)
+ *   - 2-D slabs are (iew,jns), x fastest, exactly as Fortran passes `gridded(iew,jns)`:
+ *     gridded(i,j) == g[(j-1)*iew + (i-1)].  3-D first-guess fields of the per-time
+ *     API are (jns,iew,kbu), y fastest (src/first_guess.inc).
+ *   - xob/yob are the reference's 1-based REAL(4) dot-grid coordinates.
+ *   - Fortran LOGICALs are passed as int 0/1; CHARACTER(8) variable names as og_var codes.
+ *   - all functions return OG_OK (0) or a negative og_status; they never abort/STOP.
+ *     og_last_error() returns a message for the last failure on the calling thread.
+ *   - there is NO CPU fallback: og_init fails with OG_ERR_NO_DEVICE without an
+ *     sm_100 GPU.
+ *   - callers are single threaded per og_ctx (like the reference); calls block.
+ */
+#ifndef OBSGRID_GPU_H
+#define OBSGRID_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OG_ABI_VERSION 1
+
+typedef enum og_status {
+    OG_OK = 0,
+    OG_ERR_NO_DEVICE = -1,   /* no sm_100 device / CUDA runtime failure at init        */
+    OG_ERR_INVALID = -2,     /* bad argument (null pointer, n<0, unknown variable ...)   */
+    OG_ERR_CUDA = -3,        /* a CUDA call or kernel failed; see og_last_error()        */
+    OG_ERR_ALLOC = -4,       /* host or device allocation failed                         */
+    OG_ERR_RADIUS = -5,      /* surface scan-1 radius below 4.5 cells: the reference     */
+                             /* STOPs here (src/proc_oa.F90:694-703)                     */
+    OG_ERR_NOCONV = -6       /* buddy difmax fix-point did not converge (cannot happen   */
+                             /* for a finite slab; defensive)                            */
+} og_status;
+
+/* Variable codes.  OA uses 1..6 (src/proc_oa.F90:204-205), QC uses 1..7
+ * (src/proc_qc.F90:264-320); code 6 is PSFC in the OA loop and PMSLPSFC in QC. */
+enum {
+    OG_VAR_UU = 1, OG_VAR_VV = 2, OG_VAR_TT = 3, OG_VAR_RH = 4, OG_VAR_PMSL = 5,
+    OG_VAR_PSFC = 6, OG_VAR_PMSLPSFC = 6, OG_VAR_DEWPOINT = 7
+};
+
+/* QC flag bits (src/missing.inc:21-43). */
+#define OG_NO_BUDDIES        (1 << 14)
+#define OG_FAILS_ERROR_MAX   (1 << 16)
+#define OG_FAILS_BUDDY_CHECK (1 << 17)
+#define OG_OUTSIDE_OF_DOMAIN (1 << 18)
+#define OG_MISSING_R         (-888888.0f)   /* src/missing.inc:14 */
+#define OG_MISSING_I         (-888888)
+#define OG_MAX_SCAN 10                       /* src/proc_oa.F90:105 */
+
+typedef struct og_ctx og_ctx;
+
+/* ---- context -------------------------------------------------------------------- */
+int  og_abi_version(void);
+/* device: CUDA ordinal.  Fails (OG_ERR_NO_DEVICE) unless the device is compute 10.x. */
+int  og_init(og_ctx** ctx, int device);
+int  og_finalize(og_ctx* ctx);
+const char* og_last_error(void);
+/* Counters accumulated since og_init / og_reset_stats: the library's own kernel launches,
+ * Cressman contributing updates (pairs with d2 < R2, oa_module.F90:553/616), Cressman
+ * candidate pairs examined, buddy pair tests examined, obs buddy-checked. */
+typedef struct og_stats {
+    int64_t kernel_launches;
+    int64_t cressman_updates;
+    int64_t cressman_candidates;
+    int64_t buddy_pair_tests;
+    int64_t buddy_obs;
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int64_t buddy_fixpoint_iters;
+} og_stats;
+int  og_get_stats(og_ctx* ctx, og_stats* out);
+int  og_reset_stats(og_ctx* ctx);
+/* When nonzero the Cressman kernels also count updates/candidates (one extra integer
+ * reduction per block); off by default so the timed path does no bookkeeping. */
+int  og_set_counting(og_ctx* ctx, int on);
+
+/* ---- per-slab drop-ins (host arrays, blocking) ----------------------------------- */
+
+/* proc_oa.F90:517-554 / :750-778.  diff = obs_value/scale - aob (or obs_value/scale when
+ * use_first_guess==0); fg_value (nullable) receives aob as in :530. */
+int og_innovation(og_ctx* ctx, const float* gridded, int iew, int jns,
+                  const float* xob, const float* yob, const float* obs_value, int n,
+                  float scale, int use_first_guess, float* diff, float* fg_value);
+
+/* oa_module.F90:25-32.  `diff` is the reference's `obs` dummy (innovations); obs_value and
+ * lat_center are unused by the reference and therefore not passed.  radius_influence is
+ * the already NINT()ed integer radius in cells; dxd_km the grid distance in km
+ * (driver.F90:265).  gridded is updated in place. */
+int og_cressman(og_ctx* ctx, const float* diff, const float* xob, const float* yob, int n,
+                float* gridded, int iew, int jns, int crsdot, int var,
+                int radius_influence, float dxd_km,
+                const float* u_banana, const float* v_banana, float pressure_hpa,
+                int passes, int smooth_type, int use_first_guess,
+                const float* fg_value, int scale_cressman_rh_decreases);
+
+/* One (level, variable) slab of proc_oa: innovations, every Cressman scan with the
+ * surface radius scaling, the re-interpolated innovations between scans and the final
+ * RH clamp.  radius_influence[OG_MAX_SCAN] ends at the first negative entry.
+ * scale is 100 for PMSL else 1 (proc_oa.F90:208).  n_scans_done (nullable) returns the
+ * number of scans executed. */
+int og_oa_slab(og_ctx* ctx, float* gridded, int iew, int jns, int var, float pressure_hpa,
+               const float* obs_value, const float* xob, const float* yob, int n,
+               float scale, const int* radius_influence, float radius_influence_sfc_mult,
+               float dxd_km, const float* u_banana, const float* v_banana,
+               int passes, int smooth_type, int use_first_guess,
+               int scale_cressman_rh_decreases, int* n_scans_done);
+
+/* qc0_module.F90:236-267: local_time = mod(int(hh + lon/15) [+24 if <0], 24) * 100.
+ * time_hhmm is what proc_qc passes (time/100, proc_qc.F90:344). */
+int og_local_time(og_ctx* ctx, int time_hhmm, const float* lonob, int n, int* local_time);
+
+/* qc1_module.F90:9-15.  station_id / ship_report / index only feed prints in the
+ * reference and stay on the Fortran side.  Diagnostics (nullable): aob, err, thr. */
+int og_error_max(og_ctx* ctx, const float* obs, const float* xob, const float* yob,
+                 const float* station_elevation, int* qc_flag, int n,
+                 const float* gridded, int iew, int jns, int var, float max_difference,
+                 float pressure_hpa, const int* local_time,
+                 float* aob, float* err, float* thr);
+
+/* qc2_module.F90:9-14.  Diagnostics (nullable): aob, err, difmax (after the x1.2
+ * two-buddy relaxation, :327), buddy_num_final. */
+int og_buddy_check(og_ctx* ctx, const float* obs, int n, const float* xob, const float* yob,
+                   int* qc_flag, const float* station_elevation,
+                   const float* gridded, int iew, int jns, int var, float pressure_hpa,
+                   float dx_km, float buddy_weight, float buddy_difference,
+                   float* aob, float* err, float* difmax, int* buddy_num_final);
+
+/* error_max followed by buddy_check on one slab in one upload (proc_qc.F90:371-392). */
+int og_qc_slab(og_ctx* ctx, int do_error_max, int do_buddy, const float* gridded, int iew,
+               int jns, int var, float pressure_hpa, const float* obs, const float* xob,
+               const float* yob, const float* station_elevation, const int* local_time,
+               int n, float max_error, float max_buddy, float buddy_weight, float dx_km,
+               int* qc_flag);
+
+/* ---- per-time batched API -------------------------------------------------------- */
+
+typedef struct og_qc_params {       /* namelist &record4 (src/namelist.nml) */
+    int   qc_test_error_max, qc_test_buddy;
+    float max_error_t, max_error_uv, max_error_rh, max_error_dewpoint, max_error_p;
+    float max_buddy_t, max_buddy_uv, max_buddy_rh, max_buddy_dewpoint, max_buddy_p;
+    float buddy_weight;             /* driver.F90:456 passes the literal 1. */
+    int   time_hhmmss;              /* current_time_6 */
+    int   qc_dewpoint;              /* run variable 7 (always on in the reference) */
+} og_qc_params;
+
+typedef struct og_oa_params {       /* namelist &record7/8/9 */
+    int   radius_influence[OG_MAX_SCAN];
+    float radius_influence_sfc_mult;
+    int   use_first_guess;
+    int   scale_cressman_rh_decreases;
+    int   smooth_type;
+    int   smooth_sfc_wind, smooth_sfc_temp, smooth_sfc_rh, smooth_sfc_slp;
+    int   smooth_upper_wind, smooth_upper_temp, smooth_upper_rh;
+    int   surface_only;             /* fdda_loop > 1: only kp == 1 (proc_oa.F90:365) */
+    int   clamp_fg_rh;              /* apply mixing_ratio's in-place RH clamp to [1,100]
+                                       (final_analysis_module.F90:1055) before the loop */
+} og_oa_params;
+
+/* One analysis time.  Observation table: nrep reports in the reference's report order;
+ * per level k (0-based, k==0 is the 1001 hPa surface pseudo-level) and report r the
+ * value at [k*nrep + r], OG_MISSING_R when the report has no such level/variable.
+ * QC flags are in/out.  PMSL exists only at k==0: ob_slp / qc_slp are [nrep]. */
+typedef struct og_time_desc {
+    int   iew, jns, kbu;
+    float dx_km;
+    const float* pressure;          /* [kbu] hPa, pressure[0] == 1001 */
+    float *t, *u, *v, *rh;          /* (jns,iew,kbu) y fastest; in (QC) / in-out (OA) */
+    float *slp;                     /* (jns,iew) hPa */
+    int   nrep;
+    const float *xob, *yob;         /* [nrep] */
+    const float *lon, *elev;        /* [nrep] (QC only) */
+    const float *ob_u, *ob_v, *ob_t, *ob_rh;   /* [kbu*nrep] */
+    const float *ob_slp;            /* [nrep] Pa */
+    int *qc_u, *qc_v, *qc_t, *qc_rh;           /* [kbu*nrep] */
+    int *qc_slp;                    /* [nrep] */
+} og_time_desc;
+
+/* proc_qc level x variable loop + qc_consistency.  Flags are updated in place. */
+int og_qc_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p);
+/* proc_oa level x variable loop.  Fields are updated in place.  Observations whose flag is
+ * >= min(fails_error_max, fails_buddy_check) are not used (proc_oa.F90:462).
+ * k_begin/k_end select a half-open level range [k_begin,k_end) -- the unit by which the
+ * multi-GPU driver shards a time across ranks; pass 0,kbu for all. */
+int og_oa_time(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
+               int k_begin, int k_end);
+int og_qc_time_levels(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p,
+                      int k_begin, int k_end, int run_consistency);
+
+/* ---- resident (device-pointer) API ---------------------------------------------- */
+/* Same semantics as og_qc_time / og_oa_time but every pointer inside `d` is a DEVICE
+ * pointer on the context's device and nothing is copied; used to time the kernels with
+ * inputs already in HBM.  `pressure` stays a host pointer. */
+int og_dev_qc_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p,
+                   int k_begin, int k_end, int run_consistency);
+int og_dev_oa_time(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
+                   int k_begin, int k_end);
+/* Stream all library work is issued on (a cudaStream_t), for event timing by the caller. */
+void* og_stream(og_ctx* ctx);
+int   og_sync(og_ctx* ctx);
+/* Kernel-only timing of the last og_*_time call, measured with CUDA events on the
+ * library's stream: total ms inside Cressman scan kernels and inside buddy kernels. */
+int   og_last_kernel_ms(og_ctx* ctx, float* cressman_ms, float* buddy_ms);
+/* Micro-benchmark: sustained FP32 lane-instructions/s of dependent-chain FADD/FMUL
+ * (no FMA contraction) on this device -- the denominator of the FP32 roofline. */
+int   og_fp32_peak(og_ctx* ctx, double* lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBSGRID_GPU_H */

@@ -1,0 +1,99 @@
+/*
+ * og_oracle.h -- CPU oracle for the OBSGRID objective-analysis hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library, and only as the checker / the CPU baseline.  libobsgrid_gpu.so never
+ * links or calls it.
+ *
+ * PARITY UNPINNED: the reference (wrf-model/OBSGRID) ships no tests, golden vectors or
+ * fixtures, and is Fortran 90 + netCDF, neither of which exists in the build container
+ * (no gfortran/ifort/nvfortran/flang, no netcdf.inc), so oracle/_ref cannot be built.
+ * This file is a line-by-line FP32 restatement of the reference loops; it is pinned only
+ * by the hand-derived known-answer tests in tests/test_oracle_kat.py.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile) so that every
+ * operation is one IEEE-754 binary32 operation in source order, as gfortran -O emits on
+ * x86-64 (arch/configure.defaults:44-46: no fast-math, no FMA contraction).
+ */
+#ifndef OG_ORACLE_H
+#define OG_ORACLE_H
+
+#include <stdint.h>
+#include "../include/obsgrid_gpu.h"   /* shared plain-C structs/constants only */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ogo_stats {
+    int64_t cressman_updates;      /* executions of oa_module.F90:566-568 / :618-620 */
+    int64_t cressman_candidates;   /* inner-loop iterations (window sweep)           */
+    int64_t buddy_pair_tests;      /* executions of qc2_module.F90:233-236           */
+    int64_t n_circle, n_ellipse, n_banana;
+} ogo_stats;
+
+void ogo_reset_stats(void);
+void ogo_get_stats(ogo_stats* out);
+
+void ogo_innovation(const float* gridded, int iew, int jns, const float* xob,
+                    const float* yob, const float* obs_value, int n, float scale,
+                    int use_first_guess, float* diff, float* fg_value);
+
+void ogo_cressman(const float* diff, const float* xob, const float* yob, int n,
+                  float* gridded, int iew, int jns, int crsdot, int var,
+                  int radius_influence, float dxd_km, const float* u_banana,
+                  const float* v_banana, float pressure_hpa, int passes, int smooth_type,
+                  int use_first_guess, const float* fg_value,
+                  int scale_cressman_rh_decreases);
+
+int ogo_oa_slab(float* gridded, int iew, int jns, int var, float pressure_hpa,
+                const float* obs_value, const float* xob, const float* yob, int n,
+                float scale, const int* radius_influence, float radius_influence_sfc_mult,
+                float dxd_km, const float* u_banana, const float* v_banana, int passes,
+                int smooth_type, int use_first_guess, int scale_cressman_rh_decreases,
+                int* n_scans_done);
+
+void ogo_smooth_5(float* field, int iew, int jns, int passes, int crsdot);
+void ogo_smoother_desmoother(float* slab, int imx, int jmx, int passes, int crsdot);
+void ogo_clean_rh(float* rh, int iew, int jns, float rh_min, float rh_max);
+
+void ogo_modify_qc_flag(int* qc_flag, int n, const float* err, const float* thr, int test);
+void ogo_add_to_qc_flag(int* qc_flag, int to_add);
+void ogo_local_time(int time_hhmm, const float* lonob, int n, int* local_time);
+
+void ogo_error_max(const float* obs, const float* xob, const float* yob,
+                   const float* station_elevation, int* qc_flag, int n,
+                   const float* gridded, int iew, int jns, int var, float max_difference,
+                   float pressure_hpa, const int* local_time,
+                   float* aob, float* err, float* thr);
+
+void ogo_buddy_check(const float* obs, int n, const float* xob, const float* yob,
+                     int* qc_flag, const float* station_elevation, const float* gridded,
+                     int iew, int jns, int var, float pressure_hpa, float dx_km,
+                     float buddy_weight, float buddy_difference,
+                     float* aob, float* err, float* difmax, int* buddy_num_final);
+
+/* DEWPOINT first-guess field of proc_qc.F90:315-319 and dewpoint ob of
+ * ob_access_module.F90:476-486 (same formula). */
+float ogo_dewpoint(float t, float rh);
+
+/* proc_qc / proc_oa level x variable loops over the flat observation table. */
+int ogo_qc_time(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
+                int run_consistency);
+int ogo_oa_time(const og_time_desc* d, const og_oa_params* p, int k_begin, int k_end);
+/* Same as ogo_oa_time but slabs are distributed over `threads` pthreads (slabs of one
+ * level are independent) -- the "all host cores" CPU baseline. */
+int ogo_oa_time_mt(const og_time_desc* d, const og_oa_params* p, int k_begin, int k_end,
+                   int threads);
+int ogo_qc_time_mt(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
+                   int run_consistency, int threads);
+
+/* GET_FG_T_AT_POINT (get_fg_at_point_module.F90:7-116) with (x,y) already projected. */
+float ogo_fg_t_at_point(const float* t3d, const float* h3d, int jns, int iew, int kbu,
+                        float x_location, float y_location, float height_msl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
