@@ -108,6 +108,14 @@ int  og_reset_stats(og_ctx* ctx);
 /* When nonzero the Cressman kernels also count updates/candidates (one extra integer
  * reduction per block); off by default so the timed path does no bookkeeping. */
 int  og_set_counting(og_ctx* ctx, int on);
+/* When nonzero, CUDA event pairs are recorded around the Cressman scan kernels and the buddy
+ * all-pairs kernel (no host synchronisation); og_last_kernel_ms() resolves them. */
+int  og_set_timing(og_ctx* ctx, int on);
+/* Pinned host memory for callers that want asynchronous, full-rate PCIe copies of the arrays
+ * they hand to the library (Fortran: c_f_pointer on the result).  Optional: any host pointer
+ * is accepted everywhere. */
+int  og_host_alloc(void** ptr, size_t bytes);
+int  og_host_free(void* ptr);
 
 /* ---- per-slab drop-ins (host arrays, blocking) ----------------------------------- */
 
@@ -176,6 +184,9 @@ typedef struct og_qc_params {       /* namelist &record4 (src/namelist.nml) */
     float buddy_weight;             /* driver.F90:456 passes the literal 1. */
     int   time_hhmmss;              /* current_time_6 */
     int   qc_dewpoint;              /* run variable 7 (always on in the reference) */
+    int   var_mask;                 /* 0 = every variable; else bit (v-1) enables variable v.
+                                       Lets the multi-GPU driver shard one level by variable;
+                                       keep RH (4) and DEWPOINT (7) on the same rank.          */
 } og_qc_params;
 
 typedef struct og_oa_params {       /* namelist &record7/8/9 */
@@ -189,6 +200,7 @@ typedef struct og_oa_params {       /* namelist &record7/8/9 */
     int   surface_only;             /* fdda_loop > 1: only kp == 1 (proc_oa.F90:365) */
     int   clamp_fg_rh;              /* apply mixing_ratio's in-place RH clamp to [1,100]
                                        (final_analysis_module.F90:1055) before the loop */
+    int   var_mask;                 /* 0 = every variable; else bit (v-1) enables variable v */
 } og_oa_params;
 
 /* One analysis time.  Observation table: nrep reports in the reference's report order;
@@ -232,12 +244,16 @@ int og_dev_oa_time(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
 /* Stream all library work is issued on (a cudaStream_t), for event timing by the caller. */
 void* og_stream(og_ctx* ctx);
 int   og_sync(og_ctx* ctx);
-/* Kernel-only timing of the last og_*_time call, measured with CUDA events on the
- * library's stream: total ms inside Cressman scan kernels and inside buddy kernels. */
+/* Kernel-only time accumulated since the last call (og_set_timing must be on), measured with
+ * CUDA events on the library's stream: ms inside the Cressman scan kernels and inside the
+ * buddy all-pairs kernel.  Synchronises the stream. */
 int   og_last_kernel_ms(og_ctx* ctx, float* cressman_ms, float* buddy_ms);
 /* Micro-benchmark: sustained FP32 lane-instructions/s of dependent-chain FADD/FMUL
  * (no FMA contraction) on this device -- the denominator of the FP32 roofline. */
 int   og_fp32_peak(og_ctx* ctx, double* lane_ops_per_s);
+/* Self test: compares the kernels' FCHK-less exact division with __fdiv_rn on n random
+ * Cressman weight operand pairs (R in 1..rmax); *mismatches must come back 0. */
+int   og_selftest_div(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches);
 
 #ifdef __cplusplus
 }

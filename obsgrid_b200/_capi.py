@@ -44,7 +44,7 @@ class OgQcParams(C.Structure):
                 ("max_buddy_rh", C.c_float), ("max_buddy_dewpoint", C.c_float),
                 ("max_buddy_p", C.c_float),
                 ("buddy_weight", C.c_float), ("time_hhmmss", C.c_int),
-                ("qc_dewpoint", C.c_int)]
+                ("qc_dewpoint", C.c_int), ("var_mask", C.c_int)]
 
 
 class OgOaParams(C.Structure):
@@ -56,7 +56,7 @@ class OgOaParams(C.Structure):
                 ("smooth_sfc_rh", C.c_int), ("smooth_sfc_slp", C.c_int),
                 ("smooth_upper_wind", C.c_int), ("smooth_upper_temp", C.c_int),
                 ("smooth_upper_rh", C.c_int),
-                ("surface_only", C.c_int), ("clamp_fg_rh", C.c_int)]
+                ("surface_only", C.c_int), ("clamp_fg_rh", C.c_int), ("var_mask", C.c_int)]
 
 
 class OgTimeDesc(C.Structure):
@@ -83,6 +83,10 @@ SIGNATURES = {
     "og_get_stats": (C.c_int, [_vp, C.POINTER(OgStats)]),
     "og_reset_stats": (C.c_int, [_vp]),
     "og_set_counting": (C.c_int, [_vp, C.c_int]),
+    "og_set_timing": (C.c_int, [_vp, C.c_int]),
+    "og_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "og_host_free": (C.c_int, [_vp]),
+    "og_selftest_div": (C.c_int, [_vp, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_longlong)]),
     "og_innovation": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_float,
                                 C.c_int, _vp, _vp]),
     "og_cressman": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int,

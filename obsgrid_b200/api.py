@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI.
+
+Function names, argument meaning and error behaviour follow the reference procedures
+(`cressman` oa_module.F90:25, `error_max` qc1_module.F90:9, `buddy_check` qc2_module.F90:9,
+`local` qc0_module.F90:236, `proc_qc` / `proc_oa` level x variable loops); 2-D slabs are
+numpy arrays of shape (jns, iew) in C order, i.e. the memory of Fortran's gridded(iew,jns).
+Everything runs on the GPU through libobsgrid_gpu.so; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import OG_MAX_SCAN, OgStats, check, f32, i32, ptr
+
+
+class Context:
+    """An og_ctx: one CUDA device + stream.  Raises OgError without an sm_100 GPU."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _capi.lib()
+        h = C.c_void_p()
+        check(self._lib.og_init(C.byref(h), device), "og_init")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.og_finalize(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- bookkeeping -------------------------------------------------------------------
+    def stats(self) -> dict:
+        s = OgStats()
+        check(self._lib.og_get_stats(self._h, C.byref(s)), "og_get_stats")
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def reset_stats(self):
+        check(self._lib.og_reset_stats(self._h), "og_reset_stats")
+
+    def set_counting(self, on: bool):
+        check(self._lib.og_set_counting(self._h, int(on)), "og_set_counting")
+
+    def set_timing(self, on: bool):
+        check(self._lib.og_set_timing(self._h, int(on)), "og_set_timing")
+
+    def kernel_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        check(self._lib.og_last_kernel_ms(self._h, C.byref(a), C.byref(b)), "og_last_kernel_ms")
+        return a.value, b.value
+
+    def sync(self):
+        check(self._lib.og_sync(self._h), "og_sync")
+
+    def stream(self) -> int:
+        return int(self._lib.og_stream(self._h) or 0)
+
+    def fp32_peak(self) -> float:
+        v = C.c_double(0)
+        check(self._lib.og_fp32_peak(self._h, C.byref(v)), "og_fp32_peak")
+        return v.value
+
+    def selftest_div(self, n=1 << 22, seed=1234, rmax=100) -> int:
+        bad = C.c_longlong(-1)
+        check(self._lib.og_selftest_div(self._h, n, seed, rmax, C.byref(bad)), "og_selftest_div")
+        return bad.value
+
+    # ---- per-slab drop-ins ---------------------------------------------------------------
+    def innovation(self, gridded, xob, yob, obs_value, scale=1.0, use_first_guess=True):
+        g = f32(gridded); jns, iew = g.shape
+        xob, yob, obs_value = f32(xob), f32(yob), f32(obs_value)
+        n = xob.size
+        diff = np.zeros(n, np.float32); fg = np.full(n, -9999999.0, np.float32)
+        check(self._lib.og_innovation(self._h, ptr(g), iew, jns, ptr(xob), ptr(yob),
+                                      ptr(obs_value), n, scale, int(use_first_guess), ptr(diff),
+                                      ptr(fg)), "og_innovation")
+        return diff, fg
+
+    def cressman(self, diff, xob, yob, gridded, var, radius, dxd_km, u_banana=None,
+                 v_banana=None, pressure=1001.0, passes=0, smooth_type=1, use_first_guess=True,
+                 fg_value=None, scale_rh=False, crsdot=1):
+        g = f32(gridded).copy(); jns, iew = g.shape
+        diff, xob, yob = f32(diff), f32(xob), f32(yob)
+        ub = f32(u_banana) if u_banana is not None else None
+        vb = f32(v_banana) if v_banana is not None else None
+        fg = f32(fg_value) if fg_value is not None else None
+        check(self._lib.og_cressman(self._h, ptr(diff), ptr(xob), ptr(yob), diff.size, ptr(g), iew,
+                                    jns, crsdot, var, int(radius), dxd_km, ptr(ub), ptr(vb),
+                                    pressure, passes, smooth_type, int(use_first_guess), ptr(fg),
+                                    int(scale_rh)), "og_cressman")
+        return g
+
+    def oa_slab(self, gridded, var, pressure, obs_value, xob, yob, radii, dxd_km, u_banana=None,
+                v_banana=None, scale=1.0, sfc_mult=1.0, passes=0, smooth_type=1,
+                use_first_guess=True, scale_rh=False):
+        g = f32(gridded).copy(); jns, iew = g.shape
+        obs_value, xob, yob = f32(obs_value), f32(xob), f32(yob)
+        ub = f32(u_banana) if u_banana is not None else None
+        vb = f32(v_banana) if v_banana is not None else None
+        rad = np.full(OG_MAX_SCAN, -1, np.int32); rad[:len(radii)] = radii
+        ns = C.c_int(0)
+        rc = self._lib.og_oa_slab(self._h, ptr(g), iew, jns, var, pressure, ptr(obs_value), ptr(xob),
+                                  ptr(yob), xob.size, scale, ptr(rad), sfc_mult, dxd_km, ptr(ub),
+                                  ptr(vb), passes, smooth_type, int(use_first_guess),
+                                  int(scale_rh), C.byref(ns))
+        if rc not in (0, -5):
+            check(rc, "og_oa_slab")
+        return g, rc, ns.value
+
+    def local_time(self, time_hhmm, lonob):
+        lon = f32(lonob); out = np.zeros(lon.size, np.int32)
+        check(self._lib.og_local_time(self._h, int(time_hhmm), ptr(lon), lon.size, ptr(out)),
+              "og_local_time")
+        return out
+
+    def error_max(self, obs, xob, yob, elev, qc_flag, gridded, var, max_difference, pressure,
+                  local_t):
+        g = f32(gridded); jns, iew = g.shape
+        obs, xob, yob, elev = f32(obs), f32(xob), f32(yob), f32(elev)
+        qc = i32(qc_flag).copy(); lt = i32(local_t); n = obs.size
+        aob = np.zeros(n, np.float32); err = np.zeros(n, np.float32); thr = np.zeros(n, np.float32)
+        check(self._lib.og_error_max(self._h, ptr(obs), ptr(xob), ptr(yob), ptr(elev), ptr(qc), n,
+                                     ptr(g), iew, jns, var, max_difference, pressure, ptr(lt),
+                                     ptr(aob), ptr(err), ptr(thr)), "og_error_max")
+        return qc, aob, err, thr
+
+    def buddy_check(self, obs, xob, yob, qc_flag, elev, gridded, var, pressure, dx_km,
+                    buddy_weight, buddy_difference):
+        g = f32(gridded); jns, iew = g.shape
+        obs, xob, yob, elev = f32(obs), f32(xob), f32(yob), f32(elev)
+        qc = i32(qc_flag).copy(); n = obs.size
+        aob = np.zeros(n, np.float32); err = np.zeros(n, np.float32); dm = np.zeros(n, np.float32)
+        bnf = np.zeros(n, np.int32)
+        check(self._lib.og_buddy_check(self._h, ptr(obs), n, ptr(xob), ptr(yob), ptr(qc), ptr(elev),
+                                       ptr(g), iew, jns, var, pressure, dx_km, buddy_weight,
+                                       buddy_difference, ptr(aob), ptr(err), ptr(dm), ptr(bnf)),
+              "og_buddy_check")
+        return qc, aob, err, dm, bnf
+
+    def qc_slab(self, gridded, var, pressure, obs, xob, yob, elev, local_t, qc_flag, max_error,
+                max_buddy, buddy_weight, dx_km, do_error_max=True, do_buddy=True):
+        g = f32(gridded); jns, iew = g.shape
+        obs, xob, yob, elev = f32(obs), f32(xob), f32(yob), f32(elev)
+        qc = i32(qc_flag).copy(); lt = i32(local_t)
+        check(self._lib.og_qc_slab(self._h, int(do_error_max), int(do_buddy), ptr(g), iew, jns, var,
+                                   pressure, ptr(obs), ptr(xob), ptr(yob), ptr(elev), ptr(lt),
+                                   obs.size, max_error, max_buddy, buddy_weight, dx_km, ptr(qc)),
+              "og_qc_slab")
+        return qc
+
+    # ---- per-time drivers (synth.TimeCase; arrays updated in place) ------------------------
+    def proc_qc(self, case, k_begin=0, k_end=None, run_consistency=True):
+        d = case.desc()
+        k_end = case.kbu if k_end is None else k_end
+        check(self._lib.og_qc_time_levels(self._h, C.byref(d), C.byref(case.qc_params), k_begin,
+                                          k_end, int(run_consistency)), "og_qc_time_levels")
+
+    def proc_oa(self, case, k_begin=0, k_end=None):
+        d = case.desc()
+        k_end = case.kbu if k_end is None else k_end
+        rc = self._lib.og_oa_time(self._h, C.byref(d), C.byref(case.oa_params), k_begin, k_end)
+        if rc not in (0, -5):
+            check(rc, "og_oa_time")
+        return rc
+
+    # resident variants: `desc` holds device pointers (see bench.py)
+    def dev_proc_qc(self, desc, qc_params, k_begin, k_end, run_consistency=True):
+        check(self._lib.og_dev_qc_time(self._h, C.byref(desc), C.byref(qc_params), k_begin, k_end,
+                                       int(run_consistency)), "og_dev_qc_time")
+
+    def dev_proc_oa(self, desc, oa_params, k_begin, k_end):
+        rc = self._lib.og_dev_oa_time(self._h, C.byref(desc), C.byref(oa_params), k_begin, k_end)
+        if rc not in (0, -5):
+            check(rc, "og_dev_oa_time")
+        return rc

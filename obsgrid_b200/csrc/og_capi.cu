@@ -1,0 +1,911 @@
+// og_capi.cu -- the extern "C" surface of libobsgrid_gpu.so (include/obsgrid_gpu.h):
+// context, the per-slab drop-ins for the reference's three call sites, and the per-time
+// batched drivers that mirror the level x variable loops of proc_qc / proc_oa.
+#include "og_ctx.h"
+#include "og_device.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+using namespace og;
+
+// =========================================================================================
+// context
+// =========================================================================================
+extern "C" int og_abi_version(void) { return OG_ABI_VERSION; }
+extern "C" const char* og_last_error(void) { return og::last_error(); }
+
+extern "C" int og_init(og_ctx** out, int device)
+{
+    if (!out) { set_error("og_init: null ctx pointer"); return OG_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("og_init: no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+        return OG_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { set_error("og_init: device %d of %d", device, ndev); return OG_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        set_error("og_init: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return OG_ERR_NO_DEVICE;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("og_init: cudaSetDevice failed"); return OG_ERR_NO_DEVICE; }
+    og_ctx* c = new (std::nothrow) og_ctx();
+    if (!c) return OG_ERR_ALLOC;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
+        cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&c->d_flag, 64 * sizeof(int)) != cudaSuccess ||
+        cudaMallocHost(&c->h_pinned_small, 4096) != cudaSuccess) {
+        set_error("og_init: resource creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return OG_ERR_CUDA;
+    }
+    cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
+    *out = c;
+    return OG_OK;
+}
+
+extern "C" int og_finalize(og_ctx* c)
+{
+    if (!c) return OG_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
+    for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    cudaFree(c->d_counters); cudaFree(c->d_flag); cudaFreeHost(c->h_pinned_small);
+    cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return OG_OK;
+}
+
+static int fetch_counters(og_ctx* c)
+{
+    unsigned long long h[2];
+    OG_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    c->stats.cressman_updates = (int64_t)h[0];
+    c->stats.cressman_candidates = (int64_t)h[1];
+    return OG_OK;
+}
+
+extern "C" int og_get_stats(og_ctx* c, og_stats* out)
+{
+    if (!c || !out) return OG_ERR_INVALID;
+    OG_TRY(fetch_counters(c));
+    *out = c->stats;
+    return OG_OK;
+}
+extern "C" int og_reset_stats(og_ctx* c)
+{
+    if (!c) return OG_ERR_INVALID;
+    c->stats = og_stats{};
+    OG_CUDA(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    return OG_OK;
+}
+extern "C" int og_set_counting(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->counting = on; return OG_OK; }
+extern "C" int og_set_timing(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->time_kernels = on != 0; c->timers_used = 0; return OG_OK; }
+extern "C" void* og_stream(og_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int og_sync(og_ctx* c) { if (!c) return OG_ERR_INVALID; OG_CUDA(cudaStreamSynchronize(c->stream)); return OG_OK; }
+
+extern "C" int og_last_kernel_ms(og_ctx* c, float* cressman_ms, float* buddy_ms)
+{
+    if (!c) return OG_ERR_INVALID;
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    float acc[2] = {0.f, 0.f};
+    for (size_t i = 0; i < c->timers_used; ++i) {
+        float ms = 0.f;
+        OG_CUDA(cudaEventElapsedTime(&ms, c->timers[i].a, c->timers[i].b));
+        acc[c->timers[i].kind & 1] += ms;
+    }
+    c->timers_used = 0;
+    if (cressman_ms) *cressman_ms = acc[0];
+    if (buddy_ms) *buddy_ms = acc[1];
+    return OG_OK;
+}
+extern "C" int og_fp32_peak(og_ctx* c, double* v) { if (!c || !v) return OG_ERR_INVALID; return fp32_peak(c, v); }
+extern "C" int og_selftest_div(og_ctx* c, int n, unsigned seed, int rmax, long long* bad)
+{
+    if (!c || !bad || n <= 0 || rmax <= 0) return OG_ERR_INVALID;
+    return div_selftest(c, n, seed, rmax, bad);
+}
+extern "C" int og_host_alloc(void** p, size_t bytes)
+{
+    if (!p) return OG_ERR_INVALID;
+    if (cudaMallocHost(p, bytes ? bytes : 1) != cudaSuccess) { set_error("og_host_alloc(%zu) failed", bytes); return OG_ERR_ALLOC; }
+    return OG_OK;
+}
+extern "C" int og_host_free(void* p) { if (p) cudaFreeHost(p); return OG_OK; }
+
+// =========================================================================================
+// helpers
+// =========================================================================================
+#define REQUIRE(cond, msg)                                                                \
+    do { if (!(cond)) { set_error("%s: %s", __func__, msg); return OG_ERR_INVALID; } } while (0)
+
+template <class T>
+static int upload(og_ctx* c, const char* name, const T* host, size_t count, T** dev)
+{
+    OG_TRY(c->reserve_t(name, std::max<size_t>(count, 1), dev));
+    if (count) {
+        OG_CUDA(cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (int64_t)(count * sizeof(T));
+    }
+    return OG_OK;
+}
+template <class T>
+static int download(og_ctx* c, T* host, const T* dev, size_t count)
+{
+    if (count && host) {
+        OG_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (int64_t)(count * sizeof(T));
+    }
+    return OG_OK;
+}
+
+static inline int h_nint(float x) { return (int)lroundf(x); }
+
+// Radii actually used by the multi_scan loop of one slab (proc_oa.F90:641-707).
+// Returns OG_ERR_RADIUS when the reference would STOP (surface scan 1 below 4.5 cells).
+static int scan_radii(const int* radius_influence, float sfc_mult, float pressure, int* out,
+                      int* nscan)
+{
+    int rc = OG_OK, n = 0;
+    for (int num_scan = 1; num_scan <= OG_MAX_SCAN; ++num_scan) {
+        if (radius_influence[num_scan - 1] < 0) break;
+        const bool is_sfc = fabsf(pressure - 1001.0f) < 0.0001f;
+        volatile float sf = is_sfc ? sfc_mult : 1.00f;
+        volatile float r_scaled = (float)radius_influence[num_scan - 1] * sf;
+        volatile float r_scan1 = (float)radius_influence[0] * sf;
+        if (sfc_mult < 0.99999f && is_sfc) {
+            if (r_scan1 > 100.0f) { volatile float q = 100.0f / r_scan1; r_scaled = r_scaled * q; }
+            if (r_scaled < 4.5f) { if (num_scan == 1) rc = OG_ERR_RADIUS; break; }
+        }
+        out[n++] = h_nint(r_scaled);
+    }
+    *nscan = n;
+    return rc;
+}
+
+// =========================================================================================
+// per-slab drop-ins (host arrays, blocking)
+// =========================================================================================
+extern "C" int og_innovation(og_ctx* c, const float* gridded, int iew, int jns, const float* xob,
+                             const float* yob, const float* obs_value, int n, float scale,
+                             int use_first_guess, float* diff, float* fg_value)
+{
+    REQUIRE(c && gridded && diff && n >= 0 && iew > 2 && jns > 2, "bad argument");
+    if (n == 0) return OG_OK;
+    REQUIRE(xob && yob && obs_value, "null observation array");
+    float *d_g, *d_x, *d_y, *d_v, *d_d, *d_f;
+    OG_TRY(upload(c, "io.g", gridded, (size_t)iew * jns, &d_g));
+    OG_TRY(upload(c, "io.x", xob, (size_t)n, &d_x));
+    OG_TRY(upload(c, "io.y", yob, (size_t)n, &d_y));
+    OG_TRY(upload(c, "io.v", obs_value, (size_t)n, &d_v));
+    OG_TRY(c->reserve_t("io.diff", (size_t)n, &d_d));
+    OG_TRY(c->reserve_t("io.fg", (size_t)n, &d_f));
+    OG_TRY(innovation_device(c, d_g, iew, jns, d_x, d_y, d_v, n, scale, use_first_guess, d_d,
+                             fg_value ? d_f : nullptr));
+    OG_TRY(download(c, diff, d_d, (size_t)n));
+    if (fg_value && use_first_guess) OG_TRY(download(c, fg_value, d_f, (size_t)n));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
+static bool aniso(int var) { return var == OG_VAR_UU || var == OG_VAR_VV || var == OG_VAR_RH; }
+
+extern "C" int og_cressman(og_ctx* c, const float* diff, const float* xob, const float* yob, int n,
+                           float* gridded, int iew, int jns, int crsdot, int var,
+                           int radius_influence, float dxd_km, const float* u_banana,
+                           const float* v_banana, float pressure_hpa, int passes, int smooth_type,
+                           int use_first_guess, const float* fg_value,
+                           int scale_cressman_rh_decreases)
+{
+    REQUIRE(c && gridded && n >= 0 && iew > 2 && jns > 2, "bad argument");
+    REQUIRE(var >= OG_VAR_UU && var <= OG_VAR_PSFC, "unknown variable code");
+    REQUIRE(radius_influence >= 0 && radius_influence < 8000, "radius out of range");
+    REQUIRE(crsdot == 0 || crsdot == 1, "crsdot must be 0 or 1");
+    REQUIRE(n == 0 || (diff && xob && yob), "null observation array");
+    REQUIRE(!aniso(var) || (u_banana && v_banana), "UU/VV/RH need u_banana and v_banana");
+    const size_t npts = (size_t)iew * jns;
+    float *d_g, *d_ub = nullptr, *d_vb = nullptr, *d_x, *d_y, *d_d, *d_f;
+    OG_TRY(upload(c, "io.g", gridded, npts, &d_g));
+    if (aniso(var)) {
+        OG_TRY(upload(c, "io.ub", u_banana, npts, &d_ub));
+        OG_TRY(upload(c, "io.vb", v_banana, npts, &d_vb));
+    }
+    OG_TRY(upload(c, "io.x", xob, (size_t)n, &d_x));
+    OG_TRY(upload(c, "io.y", yob, (size_t)n, &d_y));
+    OG_TRY(upload(c, "io.diff", diff, (size_t)n, &d_d));
+    if (fg_value) OG_TRY(upload(c, "io.fg", fg_value, (size_t)n, &d_f));
+    else { OG_TRY(c->reserve_t("io.fg", (size_t)std::max(n, 1), &d_f)); OG_CUDA(cudaMemsetAsync(d_f, 0, sizeof(float) * (size_t)std::max(n, 1), c->stream)); }
+
+    OaBatch b;
+    b.iew = iew; b.jns = jns; b.crsdot = crsdot; b.dxd = dxd_km;
+    b.use_first_guess = use_first_guess; b.scale_rh = scale_cressman_rh_decreases;
+    b.smooth_type = smooth_type;
+    OaSlabHost s;
+    s.g = d_g; s.ub = d_ub; s.vb = d_vb; s.n = n; s.ob_off = 0; s.var = var;
+    s.pressure = pressure_hpa; s.scale = 1.f; s.passes = passes; s.nscan = 1;
+    s.radius[0] = radius_influence;
+    b.slabs.push_back(s);
+    b.total_obs = n; b.xob = d_x; b.yob = d_y; b.val = nullptr; b.diff = d_d; b.fg = d_f;
+    b.given_diff = true; b.clean_rh = false;
+    OG_TRY(oa_run_batch(c, b));
+    OG_TRY(download(c, gridded, d_g, npts));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
+extern "C" int og_oa_slab(og_ctx* c, float* gridded, int iew, int jns, int var, float pressure_hpa,
+                          const float* obs_value, const float* xob, const float* yob, int n,
+                          float scale, const int* radius_influence,
+                          float radius_influence_sfc_mult, float dxd_km, const float* u_banana,
+                          const float* v_banana, int passes, int smooth_type,
+                          int use_first_guess, int scale_cressman_rh_decreases, int* n_scans_done)
+{
+    REQUIRE(c && gridded && radius_influence && n >= 0 && iew > 2 && jns > 2, "bad argument");
+    REQUIRE(var >= OG_VAR_UU && var <= OG_VAR_PSFC, "unknown variable code");
+    REQUIRE(n == 0 || (obs_value && xob && yob), "null observation array");
+    REQUIRE(!aniso(var) || (u_banana && v_banana), "UU/VV/RH need u_banana and v_banana");
+    const size_t npts = (size_t)iew * jns;
+    OaBatch b;
+    OaSlabHost s;
+    int rrc = scan_radii(radius_influence, radius_influence_sfc_mult, pressure_hpa, s.radius, &s.nscan);
+    float *d_g, *d_ub = nullptr, *d_vb = nullptr, *d_x, *d_y, *d_v;
+    OG_TRY(upload(c, "io.g", gridded, npts, &d_g));
+    if (aniso(var)) {
+        OG_TRY(upload(c, "io.ub", u_banana, npts, &d_ub));
+        OG_TRY(upload(c, "io.vb", v_banana, npts, &d_vb));
+    }
+    OG_TRY(upload(c, "io.x", xob, (size_t)n, &d_x));
+    OG_TRY(upload(c, "io.y", yob, (size_t)n, &d_y));
+    OG_TRY(upload(c, "io.v", obs_value, (size_t)n, &d_v));
+    b.iew = iew; b.jns = jns; b.crsdot = 1; b.dxd = dxd_km;
+    b.use_first_guess = use_first_guess; b.scale_rh = scale_cressman_rh_decreases;
+    b.smooth_type = smooth_type;
+    s.g = d_g; s.ub = d_ub; s.vb = d_vb; s.n = n; s.ob_off = 0; s.var = var;
+    s.pressure = pressure_hpa; s.scale = scale; s.passes = passes;
+    b.slabs.push_back(s);
+    b.total_obs = n; b.xob = d_x; b.yob = d_y; b.val = d_v;
+    b.given_diff = false; b.clean_rh = true;
+    OG_TRY(oa_run_batch(c, b));
+    OG_TRY(download(c, gridded, d_g, npts));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_scans_done) *n_scans_done = s.nscan;
+    if (rrc != OG_OK) set_error("surface scan-1 radius below 4.5 cells (proc_oa.F90:694-703)");
+    return rrc;
+}
+
+extern "C" int og_local_time(og_ctx* c, int time_hhmm, const float* lonob, int n, int* local_time)
+{
+    REQUIRE(c && n >= 0 && (n == 0 || (lonob && local_time)), "bad argument");
+    if (n == 0) return OG_OK;
+    float* d_l; int* d_o;
+    OG_TRY(upload(c, "io.lon", lonob, (size_t)n, &d_l));
+    OG_TRY(c->reserve_t("io.lt", (size_t)n, &d_o));
+    OG_TRY(local_time_device(c, time_hhmm, d_l, n, d_o));
+    OG_TRY(download(c, local_time, d_o, (size_t)n));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
+// shared body of og_error_max / og_buddy_check / og_qc_slab
+static int qc_slab_common(og_ctx* c, int do_emax, int do_buddy, const float* gridded, int iew,
+                          int jns, int var, float pressure, const float* obs, const float* xob,
+                          const float* yob, const float* elev, const int* local_time, int n,
+                          float max_error, float max_buddy, float buddy_weight, float dx_km,
+                          int* qc_flag, float* aob, float* err_max, float* thr_max,
+                          float* err_buddy, float* difmax, int* bnf)
+{
+    REQUIRE(c && gridded && n >= 0 && iew > 2 && jns > 2, "bad argument");
+    REQUIRE(var >= OG_VAR_UU && var <= OG_VAR_DEWPOINT, "unknown variable code");
+    if (n == 0) return OG_OK;
+    REQUIRE(obs && xob && yob && qc_flag, "null observation array");
+    REQUIRE(var != OG_VAR_PMSLPSFC || elev, "PMSLPSFC needs station_elevation");
+    REQUIRE(!(do_emax && var == OG_VAR_TT && pressure > 1000.1f) || local_time, "surface TT needs local_time");
+    const size_t nn = (size_t)n;
+    float *d_g, *d_o, *d_x, *d_y, *d_e = nullptr; int *d_lt = nullptr, *d_q;
+    OG_TRY(upload(c, "io.g", gridded, (size_t)iew * jns, &d_g));
+    OG_TRY(upload(c, "io.v", obs, nn, &d_o));
+    OG_TRY(upload(c, "io.x", xob, nn, &d_x));
+    OG_TRY(upload(c, "io.y", yob, nn, &d_y));
+    if (elev) OG_TRY(upload(c, "io.elev", elev, nn, &d_e));
+    else { OG_TRY(c->reserve_t("io.elev", nn, &d_e)); OG_CUDA(cudaMemsetAsync(d_e, 0, nn * 4, c->stream)); }
+    if (local_time) OG_TRY(upload(c, "io.lt", local_time, nn, &d_lt));
+    else { OG_TRY(c->reserve_t("io.lt", nn, &d_lt)); OG_CUDA(cudaMemsetAsync(d_lt, 0, nn * 4, c->stream)); }
+    OG_TRY(upload(c, "io.qc", qc_flag, nn, &d_q));
+    QcBatch b;
+    b.iew = iew; b.jns = jns; b.dx_km = dx_km; b.buddy_weight = buddy_weight;
+    b.do_error_max = do_emax; b.do_buddy = do_buddy;
+    QcSlabHost s;
+    s.g = d_g; s.n = n; s.ob_off = 0; s.var = var; s.pressure = pressure;
+    s.max_error = max_error; s.max_buddy = max_buddy;
+    b.slabs.push_back(s);
+    b.total_obs = n; b.xob = d_x; b.yob = d_y; b.val = d_o; b.elev = d_e; b.local_time = d_lt;
+    b.qc = d_q;
+    if (aob) OG_TRY(c->reserve_t("io.d_aob", nn, &b.aob));
+    if (err_max) OG_TRY(c->reserve_t("io.d_em", nn, &b.err_max));
+    if (thr_max) OG_TRY(c->reserve_t("io.d_tm", nn, &b.thr_max));
+    if (err_buddy) OG_TRY(c->reserve_t("io.d_eb", nn, &b.err_buddy));
+    if (difmax) OG_TRY(c->reserve_t("io.d_dm", nn, &b.difmax));
+    if (bnf) OG_TRY(c->reserve_t("io.d_bnf", nn, &b.buddy_num_final));
+    OG_TRY(qc_run_batch(c, b));
+    OG_TRY(download(c, qc_flag, d_q, nn));
+    OG_TRY(download(c, aob, b.aob, nn));
+    OG_TRY(download(c, err_max, b.err_max, nn));
+    OG_TRY(download(c, thr_max, b.thr_max, nn));
+    OG_TRY(download(c, err_buddy, b.err_buddy, nn));
+    OG_TRY(download(c, difmax, b.difmax, nn));
+    OG_TRY(download(c, bnf, b.buddy_num_final, nn));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
+extern "C" int og_error_max(og_ctx* c, const float* obs, const float* xob, const float* yob,
+                            const float* station_elevation, int* qc_flag, int n,
+                            const float* gridded, int iew, int jns, int var, float max_difference,
+                            float pressure_hpa, const int* local_time, float* aob, float* err,
+                            float* thr)
+{
+    return qc_slab_common(c, 1, 0, gridded, iew, jns, var, pressure_hpa, obs, xob, yob,
+                          station_elevation, local_time, n, max_difference, 0.f, 1.f, 1.f, qc_flag,
+                          aob, err, thr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int og_buddy_check(og_ctx* c, const float* obs, int n, const float* xob, const float* yob,
+                              int* qc_flag, const float* station_elevation, const float* gridded,
+                              int iew, int jns, int var, float pressure_hpa, float dx_km,
+                              float buddy_weight, float buddy_difference, float* aob, float* err,
+                              float* difmax, int* buddy_num_final)
+{
+    return qc_slab_common(c, 0, 1, gridded, iew, jns, var, pressure_hpa, obs, xob, yob,
+                          station_elevation, nullptr, n, 0.f, buddy_difference, buddy_weight, dx_km,
+                          qc_flag, aob, nullptr, nullptr, err, difmax, buddy_num_final);
+}
+
+extern "C" int og_qc_slab(og_ctx* c, int do_error_max, int do_buddy, const float* gridded, int iew,
+                          int jns, int var, float pressure_hpa, const float* obs, const float* xob,
+                          const float* yob, const float* station_elevation, const int* local_time,
+                          int n, float max_error, float max_buddy, float buddy_weight, float dx_km,
+                          int* qc_flag)
+{
+    return qc_slab_common(c, do_error_max, do_buddy, gridded, iew, jns, var, pressure_hpa, obs, xob,
+                          yob, station_elevation, local_time, n, max_error, max_buddy, buddy_weight,
+                          dx_km, qc_flag, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// =========================================================================================
+// per-time drivers
+// =========================================================================================
+namespace {
+
+// One slab's selection rule ('get' / 'use' of proc_ob_access.F90:146-355 over the flat table)
+struct SelSlab {
+    const float* ob;     // value row of the level ([nrep])
+    const int* qc;       // flag row
+    const float* ob_t;   // DEWPOINT only: temperature row
+    const int* qc_t;
+    int kind;            // 0 plain variable, 1 DEWPOINT (ob = rh row)
+    int qc_max;
+    int ob_off;          // output offset (filled after the count pass)
+};
+
+struct SelDev {
+    const SelSlab* slabs;
+    int nrep, nchunk, iew, jns;
+    const float* xob; const float* yob;
+    const float* elev; const int* lt_rep;   // nullable (OA)
+    int* chunk_cnt;      // [nslab][nchunk] -> exclusive offsets after the scan
+    int* slab_n;         // [nslab]
+    float* ox; float* oy; float* oval; float* oelev; int* olt; int* oqc; int* oidx;
+};
+
+constexpr int SEL_THREADS = 256;
+
+__device__ __forceinline__ bool not_missing(float r) { return fabsf(fsub(r, OG_MISSING_R)) > 1.f; }
+
+// ob_access_module.F90:476-486 / proc_qc.F90:315-319.  LOG is evaluated in double and rounded
+// once (glibc's logf is not reproducible bit-for-bit on the device).
+__device__ __forceinline__ float dewpoint_dev(float t, float rh)
+{
+    const float Rv_over_L = fdiv(1.f, 5418.12f);
+    const float very_small_rh = 0.0001f;
+    float arg = (rh < very_small_rh) ? fdiv(very_small_rh, 100.f) : fdiv(rh, 100.f);
+    float lg = (float)log((double)arg);
+    return fdiv(1.f, fsub(fdiv(1.f, t), fmul(Rv_over_L, lg)));
+}
+
+__device__ __forceinline__ bool sel_pred(const SelDev& A, const SelSlab& S, int r)
+{
+    if (r >= A.nrep) return false;
+    bool ok = not_missing(S.ob[r]) && (S.qc[r] < S.qc_max);
+    if (S.kind == 1) ok = ok && not_missing(S.ob_t[r]) && (S.qc_t[r] < S.qc_max);
+    const float x = A.xob[r], y = A.yob[r];   // proc_ob_access.F90:231-234
+    ok = ok && (x >= 2.f) && (x <= (float)(A.iew - 1)) && (y >= 2.f) && (y <= (float)(A.jns - 1));
+    return ok;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) sel_count_kernel(SelDev A)
+{
+    const SelSlab& S = A.slabs[blockIdx.y];
+    const int r = blockIdx.x * SEL_THREADS + threadIdx.x;
+    const int c = __syncthreads_count(sel_pred(A, S, r) ? 1 : 0);
+    if (threadIdx.x == 0) A.chunk_cnt[(size_t)blockIdx.y * A.nchunk + blockIdx.x] = c;
+}
+
+// per slab: exclusive scan of its chunk counts; total -> slab_n
+__global__ void __launch_bounds__(1024) sel_scan_kernel(SelDev A)
+{
+    int* cnt = A.chunk_cnt + (size_t)blockIdx.x * A.nchunk;
+    const int n = A.nchunk;
+    __shared__ int s_sum[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(b + per, n);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += cnt[i];
+    s_sum[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = (threadIdx.x >= o) ? s_sum[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = s_sum[threadIdx.x] - s;
+    for (int i = b; i < e; ++i) { int v = cnt[i]; cnt[i] = run; run += v; }
+    if (threadIdx.x == 1023) A.slab_n[blockIdx.x] = s_sum[1023];
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) sel_scatter_kernel(SelDev A)
+{
+    const SelSlab& S = A.slabs[blockIdx.y];
+    const int r = blockIdx.x * SEL_THREADS + threadIdx.x;
+    const bool p = sel_pred(A, S, r);
+    __shared__ int s_w[SEL_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, p);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    if (!p) return;
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += s_w[w];
+    const int pos = S.ob_off + A.chunk_cnt[(size_t)blockIdx.y * A.nchunk + blockIdx.x] + woff +
+                    __popc(m & ((1u << lane) - 1u));
+    A.ox[pos] = A.xob[r];
+    A.oy[pos] = A.yob[r];
+    A.oval[pos] = (S.kind == 1) ? dewpoint_dev(S.ob_t[r], S.ob[r]) : S.ob[r];
+    if (A.oqc) A.oqc[pos] = S.qc[r];
+    if (A.oidx) A.oidx[pos] = r;
+    if (A.oelev) A.oelev[pos] = A.elev[r];
+    if (A.olt) A.olt[pos] = A.lt_rep[r];
+}
+
+// 'put' (proc_ob_access.F90:381-403): flags back into the table rows
+struct PutSlab { int* qc; int ob_off; int n; };
+__global__ void put_kernel(const PutSlab* slabs, const int* oqc, const int* oidx)
+{
+    const PutSlab S = slabs[blockIdx.y];
+    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= S.n) return;
+    S.qc[oidx[S.ob_off + li]] = oqc[S.ob_off + li];
+}
+
+// qc_consistency (qc0_module.F90:371-404) on the table rows of the levels in range;
+// contains_2n(q, 2**n) == bit test for 0 <= q < 2**19 (tests/test_oracle_kat.py).
+__global__ void consistency_kernel(int* qc_u, int* qc_v, const int* qc_t, int* qc_rh, size_t n)
+{
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int u = qc_u[q], v = qc_v[q];
+    if (u > v) qc_v[q] = u;
+    if (v > u) qc_u[q] = v;
+    const int t = qc_t[q];
+    int rh = qc_rh[q];
+    const int rh0 = rh;
+    if ((t & OG_FAILS_ERROR_MAX) && !(rh0 & OG_FAILS_ERROR_MAX)) rh = qc_add_flag(rh, OG_FAILS_ERROR_MAX);
+    if ((t & OG_FAILS_BUDDY_CHECK) && !(rh0 & OG_FAILS_BUDDY_CHECK)) rh = qc_add_flag(rh, OG_FAILS_BUDDY_CHECK);
+    qc_rh[q] = rh;
+}
+
+__global__ void scale_kernel(const float* __restrict__ a, float* __restrict__ o, size_t n, float f)
+{
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) o[q] = fmul(a[q], f);
+}
+__global__ void dewfield_kernel(const float* __restrict__ t, const float* __restrict__ rh,
+                                float* __restrict__ o, size_t n)
+{
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) o[q] = dewpoint_dev(t[q], rh[q]);
+}
+// mixing_ratio's in-place clamp of the first-guess RH (final_analysis_module.F90:1055) on the
+// x-fastest copy: rh(1:jns-1, 1:iew-1, :) = MIN(MAX(rh, 1.), 100.)
+__global__ void clamp_fg_rh_kernel(float* rh, int iew, int jns, int nlev)
+{
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t per = (size_t)iew * jns;
+    if (q >= per * nlev) return;
+    int i = (int)((q % per) % iew), j = (int)((q % per) / iew);
+    if (i < iew - 1 && j < jns - 1) rh[q] = fminf(fmaxf(rh[q], 1.f), 100.f);
+}
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// Device-resident view of one time (every pointer a device pointer, reference layouts).
+struct TimeDev {
+    int iew, jns, kbu, nrep;
+    float dx_km;
+    const float* pressure;   // host
+    float *t, *u, *v, *rh, *slp;
+    const float *xob, *yob, *lon, *elev;
+    const float *ob_u, *ob_v, *ob_t, *ob_rh, *ob_slp;
+    int *qc_u, *qc_v, *qc_t, *qc_rh, *qc_slp;
+};
+
+// Run the three selection kernels for `sel` and return per-slab counts / offsets on the host.
+int run_selection(og_ctx* c, const TimeDev& T, std::vector<SelSlab>& sel, bool qc_outputs,
+                  const int* lt_rep, SelDev& A, std::vector<int>& n_out, int& total)
+{
+    const int ns = (int)sel.size();
+    const int nchunk = (T.nrep + SEL_THREADS - 1) / SEL_THREADS;
+    A = SelDev{};
+    A.nrep = T.nrep; A.nchunk = nchunk; A.iew = T.iew; A.jns = T.jns;
+    A.xob = T.xob; A.yob = T.yob; A.elev = qc_outputs ? T.elev : nullptr; A.lt_rep = lt_rep;
+    SelSlab* d_sel;
+    OG_TRY(c->reserve_t("sel.slabs", (size_t)ns, &d_sel));
+    OG_TRY(c->reserve_t("sel.chunk", (size_t)ns * std::max(nchunk, 1), &A.chunk_cnt));
+    OG_TRY(c->reserve_t("sel.n", (size_t)ns, &A.slab_n));
+    A.slabs = d_sel;
+    n_out.assign(ns, 0);
+    total = 0;
+    if (T.nrep == 0) return OG_OK;
+    OG_CUDA(cudaMemcpyAsync(d_sel, sel.data(), sizeof(SelSlab) * ns, cudaMemcpyHostToDevice, c->stream));
+    dim3 g(nchunk, ns);
+    sel_count_kernel<<<g, SEL_THREADS, 0, c->stream>>>(A);
+    sel_scan_kernel<<<ns, 1024, 0, c->stream>>>(A);
+    c->count_launch(2);
+    OG_CUDA(cudaMemcpyAsync(n_out.data(), A.slab_n, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < ns; ++s) { sel[s].ob_off = total; total += n_out[s]; }
+    OG_CUDA(cudaMemcpyAsync(d_sel, sel.data(), sizeof(SelSlab) * ns, cudaMemcpyHostToDevice, c->stream));
+    const size_t tot = (size_t)std::max(total, 1);
+    OG_TRY(c->reserve_t("sel.x", tot, &A.ox));
+    OG_TRY(c->reserve_t("sel.y", tot, &A.oy));
+    OG_TRY(c->reserve_t("sel.val", tot, &A.oval));
+    if (qc_outputs) {
+        OG_TRY(c->reserve_t("sel.elev", tot, &A.oelev));
+        OG_TRY(c->reserve_t("sel.lt", tot, &A.olt));
+        OG_TRY(c->reserve_t("sel.qc", tot, &A.oqc));
+        OG_TRY(c->reserve_t("sel.idx", tot, &A.oidx));
+    }
+    sel_scatter_kernel<<<g, SEL_THREADS, 0, c->stream>>>(A);
+    c->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+// ---- OA over the levels [k0,k1) of a device-resident time -------------------------------
+int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int k1)
+{
+    const int iew = T.iew, jns = T.jns, nlev = k1 - k0;
+    const size_t per = (size_t)iew * jns;
+    if (nlev <= 0) return OG_OK;
+    // x-fastest working copies (yx2xy of get_background_for_oa, oa_module.F90:634-676)
+    float *w_t, *w_u, *w_v, *w_rh, *w_slp, *b_u, *b_v;
+    OG_TRY(c->reserve_t("oa.w_t", per * nlev, &w_t));
+    OG_TRY(c->reserve_t("oa.w_u", per * nlev, &w_u));
+    OG_TRY(c->reserve_t("oa.w_v", per * nlev, &w_v));
+    OG_TRY(c->reserve_t("oa.w_rh", per * nlev, &w_rh));
+    OG_TRY(c->reserve_t("oa.w_slp", per, &w_slp));
+    OG_TRY(c->reserve_t("oa.b_u", per * nlev, &b_u));
+    OG_TRY(c->reserve_t("oa.b_v", per * nlev, &b_v));
+    const size_t lo = per * (size_t)k0;
+    OG_TRY(transpose_levels(c, T.t + lo, w_t, jns, iew, nlev));
+    OG_TRY(transpose_levels(c, T.u + lo, w_u, jns, iew, nlev));
+    OG_TRY(transpose_levels(c, T.v + lo, w_v, jns, iew, nlev));
+    OG_TRY(transpose_levels(c, T.rh + lo, w_rh, jns, iew, nlev));
+    const bool has_sfc = (k0 == 0);
+    if (has_sfc) OG_TRY(transpose_levels(c, T.slp, w_slp, jns, iew, 1));
+    if (p->clamp_fg_rh) {
+        clamp_fg_rh_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_rh, iew, jns, nlev);
+        c->count_launch();
+    }
+    // pre-analysis winds of each level for the banana scheme (proc_oa.F90:376-386)
+    OG_CUDA(cudaMemcpyAsync(b_u, w_u, per * nlev * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    OG_CUDA(cudaMemcpyAsync(b_v, w_v, per * nlev * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+
+    // slabs in the reference's loop order: level, then UU VV TT RH PMSL
+    const int qc_max = std::min(OG_FAILS_ERROR_MAX, OG_FAILS_BUDDY_CHECK); // proc_oa.F90:462
+    std::vector<SelSlab> sel;
+    OaBatch b;
+    b.iew = iew; b.jns = jns; b.crsdot = 1; b.dxd = T.dx_km;
+    b.use_first_guess = p->use_first_guess; b.scale_rh = p->scale_cressman_rh_decreases;
+    b.smooth_type = p->smooth_type; b.given_diff = false; b.clean_rh = true;
+    int rc_radius = OG_OK;
+    for (int k = k0; k < k1; ++k) {
+        if (p->surface_only && k > 0) break; // proc_oa.F90:365
+        const size_t row = (size_t)k * T.nrep, lev = per * (size_t)(k - k0);
+        for (int ivar = 1; ivar <= 5; ++ivar) {
+            if (ivar == 5 && k > 0) continue;
+            if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
+            OaSlabHost s;
+            SelSlab q{};
+            q.kind = 0; q.qc_max = qc_max;
+            switch (ivar) {
+            case 1: s.g = w_u + lev; q.ob = T.ob_u + row; q.qc = T.qc_u + row; break;
+            case 2: s.g = w_v + lev; q.ob = T.ob_v + row; q.qc = T.qc_v + row; break;
+            case 3: s.g = w_t + lev; q.ob = T.ob_t + row; q.qc = T.qc_t + row; break;
+            case 4: s.g = w_rh + lev; q.ob = T.ob_rh + row; q.qc = T.qc_rh + row; break;
+            default: s.g = w_slp; q.ob = T.ob_slp; q.qc = T.qc_slp; break;
+            }
+            s.ub = b_u + lev; s.vb = b_v + lev;
+            s.var = ivar; s.pressure = T.pressure[k]; s.scale = (ivar == 5) ? 100.f : 1.f;
+            const int psfc[5] = {p->smooth_sfc_wind, p->smooth_sfc_wind, p->smooth_sfc_temp, p->smooth_sfc_rh, p->smooth_sfc_slp};
+            const int pup[5] = {p->smooth_upper_wind, p->smooth_upper_wind, p->smooth_upper_temp, p->smooth_upper_rh, 0};
+            s.passes = (k == 0) ? psfc[ivar - 1] : pup[ivar - 1];
+            int r = scan_radii(p->radius_influence, p->radius_influence_sfc_mult, s.pressure, s.radius, &s.nscan);
+            if (r != OG_OK) rc_radius = r;
+            b.slabs.push_back(s);
+            sel.push_back(q);
+        }
+    }
+    SelDev SA;
+    std::vector<int> ncount;
+    int total = 0;
+    OG_TRY(run_selection(c, T, sel, false, nullptr, SA, ncount, total));
+    for (size_t s = 0; s < b.slabs.size(); ++s) { b.slabs[s].n = ncount[s]; b.slabs[s].ob_off = sel[s].ob_off; }
+    b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval;
+    OG_TRY(oa_run_batch(c, b));
+    // put_background_from_oa (oa_module.F90:828-870): back to the (jns,iew,k) layout
+    OG_TRY(transpose_levels(c, w_t, T.t + lo, iew, jns, nlev));
+    OG_TRY(transpose_levels(c, w_u, T.u + lo, iew, jns, nlev));
+    OG_TRY(transpose_levels(c, w_v, T.v + lo, iew, jns, nlev));
+    OG_TRY(transpose_levels(c, w_rh, T.rh + lo, iew, jns, nlev));
+    if (has_sfc) OG_TRY(transpose_levels(c, w_slp, T.slp, iew, jns, 1));
+    if (rc_radius != OG_OK) set_error("surface scan-1 radius below 4.5 cells (proc_oa.F90:694-703)");
+    return rc_radius;
+}
+
+// ---- QC over the levels [k0,k1) of a device-resident time --------------------------------
+int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int k1,
+                 int run_consistency)
+{
+    const int iew = T.iew, jns = T.jns, nlev = k1 - k0;
+    const size_t per = (size_t)iew * jns;
+    if (nlev <= 0) return OG_OK;
+    float *w_t, *w_u, *w_v, *w_rh, *w_slp, *w_dew;
+    OG_TRY(c->reserve_t("qc.w_t", per * nlev, &w_t));
+    OG_TRY(c->reserve_t("qc.w_u", per * nlev, &w_u));
+    OG_TRY(c->reserve_t("qc.w_v", per * nlev, &w_v));
+    OG_TRY(c->reserve_t("qc.w_rh", per * nlev, &w_rh));
+    OG_TRY(c->reserve_t("qc.w_slp", per, &w_slp));
+    const size_t lo = per * (size_t)k0;
+    OG_TRY(transpose_levels(c, T.t + lo, w_t, jns, iew, nlev));
+    OG_TRY(transpose_levels(c, T.u + lo, w_u, jns, iew, nlev));
+    OG_TRY(transpose_levels(c, T.v + lo, w_v, jns, iew, nlev));
+    OG_TRY(transpose_levels(c, T.rh + lo, w_rh, jns, iew, nlev));
+    const bool has_sfc = (k0 == 0);
+    if (has_sfc) {
+        OG_TRY(transpose_levels(c, T.slp, w_slp, jns, iew, 1));
+        scale_kernel<<<nblk(per), 256, 0, c->stream>>>(w_slp, w_slp, per, 100.f); // proc_qc.F90:296
+        c->count_launch();
+    }
+    int* lt_rep;
+    OG_TRY(c->reserve_t("qc.lt_rep", (size_t)std::max(T.nrep, 1), &lt_rep));
+    OG_TRY(local_time_device(c, p->time_hhmmss / 100, T.lon, T.nrep, lt_rep)); // proc_qc.F90:344
+
+    for (int phase = 0; phase < 2; ++phase) { // 0: UU VV TT RH PMSL, 1: DEWPOINT (reads RH flags)
+        if (phase == 1) {
+            if (!p->qc_dewpoint) break;
+            OG_TRY(c->reserve_t("qc.w_dew", per * nlev, &w_dew));
+            dewfield_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_t, w_rh, w_dew, per * nlev);
+            c->count_launch();
+        }
+        std::vector<SelSlab> sel;
+        QcBatch b;
+        b.iew = iew; b.jns = jns; b.dx_km = T.dx_km; b.buddy_weight = p->buddy_weight;
+        b.do_error_max = p->qc_test_error_max; b.do_buddy = p->qc_test_buddy;
+        std::vector<PutSlab> puts;
+        for (int k = k0; k < k1; ++k) {
+            const size_t row = (size_t)k * T.nrep, lev = per * (size_t)(k - k0);
+            const float pk = T.pressure[k];
+            for (int ivar = 1; ivar <= 7; ++ivar) {
+                if ((phase == 0) == (ivar == 7)) continue;
+                if (ivar == 6) continue;                      // qc_psfc = .FALSE.
+                if (k > 0 && ivar == 5) continue;             // proc_qc.F90:255
+                if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
+                QcSlabHost s; SelSlab q{}; PutSlab pt{};
+                q.kind = 0; q.qc_max = 1 << 20;               // proc_qc.F90:329
+                s.var = ivar; s.pressure = pk;
+                switch (ivar) {
+                case 1: s.g = w_u + lev; q.ob = T.ob_u + row; q.qc = T.qc_u + row; pt.qc = T.qc_u + row;
+                        s.max_error = p->max_error_uv; s.max_buddy = p->max_buddy_uv; break;
+                case 2: s.g = w_v + lev; q.ob = T.ob_v + row; q.qc = T.qc_v + row; pt.qc = T.qc_v + row;
+                        s.max_error = p->max_error_uv; s.max_buddy = p->max_buddy_uv; break;
+                case 3: s.g = w_t + lev; q.ob = T.ob_t + row; q.qc = T.qc_t + row; pt.qc = T.qc_t + row;
+                        s.max_error = p->max_error_t; s.max_buddy = p->max_buddy_t; break;
+                case 4: s.g = w_rh + lev; q.ob = T.ob_rh + row; q.qc = T.qc_rh + row; pt.qc = T.qc_rh + row;
+                        if (pk == 300.f) s.max_error = p->max_error_rh * 2.f;        // proc_qc.F90:282-288
+                        else if (pk < 300.f) s.max_error = p->max_error_rh * 3.f;
+                        else s.max_error = p->max_error_rh;
+                        s.max_buddy = p->max_buddy_rh; break;
+                case 5: s.g = w_slp; q.ob = T.ob_slp; q.qc = T.qc_slp; pt.qc = T.qc_slp;
+                        s.max_error = p->max_error_p; s.max_buddy = p->max_buddy_p; break;
+                default: s.g = w_dew + lev; q.kind = 1; q.ob = T.ob_rh + row; q.qc = T.qc_rh + row;
+                        q.ob_t = T.ob_t + row; q.qc_t = T.qc_t + row; pt.qc = T.qc_rh + row;
+                        s.max_error = p->max_error_dewpoint; s.max_buddy = p->max_buddy_dewpoint; break;
+                }
+                b.slabs.push_back(s); sel.push_back(q); puts.push_back(pt);
+            }
+        }
+        if (b.slabs.empty()) continue;
+        SelDev SA;
+        std::vector<int> ncount;
+        int total = 0, max_n = 0;
+        OG_TRY(run_selection(c, T, sel, true, lt_rep, SA, ncount, total));
+        for (size_t s = 0; s < b.slabs.size(); ++s) {
+            b.slabs[s].n = ncount[s]; b.slabs[s].ob_off = sel[s].ob_off;
+            puts[s].n = ncount[s]; puts[s].ob_off = sel[s].ob_off;
+            max_n = std::max(max_n, ncount[s]);
+        }
+        b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval; b.elev = SA.oelev;
+        b.local_time = SA.olt; b.qc = SA.oqc;
+        OG_TRY(qc_run_batch(c, b));
+        if (max_n > 0) {
+            PutSlab* d_put;
+            OG_TRY(c->reserve_t("qc.put", puts.size(), &d_put));
+            OG_CUDA(cudaMemcpyAsync(d_put, puts.data(), sizeof(PutSlab) * puts.size(), cudaMemcpyHostToDevice, c->stream));
+            dim3 g(nblk((size_t)max_n), (unsigned)puts.size());
+            put_kernel<<<g, 256, 0, c->stream>>>(d_put, SA.oqc, SA.oidx);
+            c->count_launch();
+            // `puts` is consumed by the copy engine before it goes out of scope
+            OG_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
+    if (run_consistency && T.nrep > 0) {
+        const size_t n = (size_t)nlev * T.nrep, off = (size_t)k0 * T.nrep;
+        consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(T.qc_u + off, T.qc_v + off, T.qc_t + off, T.qc_rh + off, n);
+        c->count_launch();
+    }
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+int check_desc(const og_time_desc* d, int k0, int k1, bool qc)
+{
+    if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
+    if (d->iew < 4 || d->jns < 4 || d->kbu < 1 || d->nrep < 0) { set_error("bad dimensions in og_time_desc"); return OG_ERR_INVALID; }
+    if (k0 < 0 || k1 > d->kbu || k0 > k1) { set_error("bad level range [%d,%d) of %d", k0, k1, d->kbu); return OG_ERR_INVALID; }
+    if (!d->pressure || !d->t || !d->u || !d->v || !d->rh || !d->slp) { set_error("null field pointer in og_time_desc"); return OG_ERR_INVALID; }
+    if (d->nrep > 0 && (!d->xob || !d->yob || !d->ob_u || !d->ob_v || !d->ob_t || !d->ob_rh || !d->ob_slp ||
+                        !d->qc_u || !d->qc_v || !d->qc_t || !d->qc_rh || !d->qc_slp)) { set_error("null observation pointer in og_time_desc"); return OG_ERR_INVALID; }
+    if (qc && d->nrep > 0 && (!d->lon || !d->elev)) { set_error("QC needs lon and elev"); return OG_ERR_INVALID; }
+    return OG_OK;
+}
+
+TimeDev view_of(const og_time_desc* d)
+{
+    TimeDev T{};
+    T.iew = d->iew; T.jns = d->jns; T.kbu = d->kbu; T.nrep = d->nrep; T.dx_km = d->dx_km;
+    T.pressure = d->pressure;
+    T.t = d->t; T.u = d->u; T.v = d->v; T.rh = d->rh; T.slp = d->slp;
+    T.xob = d->xob; T.yob = d->yob; T.lon = d->lon; T.elev = d->elev;
+    T.ob_u = d->ob_u; T.ob_v = d->ob_v; T.ob_t = d->ob_t; T.ob_rh = d->ob_rh; T.ob_slp = d->ob_slp;
+    T.qc_u = d->qc_u; T.qc_v = d->qc_v; T.qc_t = d->qc_t; T.qc_rh = d->qc_rh; T.qc_slp = d->qc_slp;
+    return T;
+}
+
+// Host -> device mirror of the level range [k0,k1) of a time.  Device arrays keep the full
+// [kbu] extent so that row offsets match; only the rows in range are copied.
+int mirror_in(og_ctx* c, const og_time_desc* d, int k0, int k1, bool qc, TimeDev& T)
+{
+    T = view_of(d);
+    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
+    auto up_lev = [&](const char* name, const float* h, float** dev) -> int {
+        OG_TRY(c->reserve_t(name, per * d->kbu, dev));
+        OG_CUDA(cudaMemcpyAsync(*dev + per * k0, h + per * k0, per * nlev * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (int64_t)(per * nlev * sizeof(float));
+        return OG_OK;
+    };
+    OG_TRY(up_lev("m.t", d->t, &T.t));
+    OG_TRY(up_lev("m.u", d->u, &T.u));
+    OG_TRY(up_lev("m.v", d->v, &T.v));
+    OG_TRY(up_lev("m.rh", d->rh, &T.rh));
+    OG_TRY(upload(c, "m.slp", d->slp, k0 == 0 ? per : 0, &T.slp));
+    float* f; int* q;
+    OG_TRY(upload(c, "m.x", d->xob, nrep, &f)); T.xob = f;
+    OG_TRY(upload(c, "m.y", d->yob, nrep, &f)); T.yob = f;
+    if (qc) {
+        OG_TRY(upload(c, "m.lon", d->lon, nrep, &f)); T.lon = f;
+        OG_TRY(upload(c, "m.elev", d->elev, nrep, &f)); T.elev = f;
+    }
+    auto up_row = [&](const char* name, const void* h, void** dev) -> int {
+        OG_TRY(c->reserve(name, std::max<size_t>(nrep * d->kbu, 1) * 4, dev));
+        if (nrep * nlev) {
+            OG_CUDA(cudaMemcpyAsync((char*)*dev + nrep * k0 * 4, (const char*)h + nrep * k0 * 4, nrep * nlev * 4, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += (int64_t)(nrep * nlev * 4);
+        }
+        return OG_OK;
+    };
+    void* v;
+    OG_TRY(up_row("m.ob_u", d->ob_u, &v)); T.ob_u = (const float*)v;
+    OG_TRY(up_row("m.ob_v", d->ob_v, &v)); T.ob_v = (const float*)v;
+    OG_TRY(up_row("m.ob_t", d->ob_t, &v)); T.ob_t = (const float*)v;
+    OG_TRY(up_row("m.ob_rh", d->ob_rh, &v)); T.ob_rh = (const float*)v;
+    OG_TRY(up_row("m.qc_u", d->qc_u, &v)); T.qc_u = (int*)v;
+    OG_TRY(up_row("m.qc_v", d->qc_v, &v)); T.qc_v = (int*)v;
+    OG_TRY(up_row("m.qc_t", d->qc_t, &v)); T.qc_t = (int*)v;
+    OG_TRY(up_row("m.qc_rh", d->qc_rh, &v)); T.qc_rh = (int*)v;
+    OG_TRY(upload(c, "m.ob_slp", d->ob_slp, k0 == 0 ? nrep : 0, &f)); T.ob_slp = f;
+    OG_TRY(upload(c, "m.qc_slp", d->qc_slp, k0 == 0 ? nrep : 0, &q)); T.qc_slp = q;
+    return OG_OK;
+}
+
+} // namespace
+
+extern "C" int og_dev_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* p, int k0, int k1)
+{
+    REQUIRE(c && p, "null argument");
+    OG_TRY(check_desc(d, k0, k1, false));
+    return oa_time_core(c, view_of(d), p, k0, k1);
+}
+
+extern "C" int og_dev_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p, int k0,
+                              int k1, int run_consistency)
+{
+    REQUIRE(c && p, "null argument");
+    OG_TRY(check_desc(d, k0, k1, true));
+    return qc_time_core(c, view_of(d), p, k0, k1, run_consistency);
+}
+
+extern "C" int og_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* p, int k0, int k1)
+{
+    REQUIRE(c && p, "null argument");
+    OG_TRY(check_desc(d, k0, k1, false));
+    if (k1 == k0) return OG_OK;
+    TimeDev T;
+    OG_TRY(mirror_in(c, d, k0, k1, false, T));
+    int rc = oa_time_core(c, T, p, k0, k1);
+    if (rc != OG_OK && rc != OG_ERR_RADIUS) return rc;
+    const size_t per = (size_t)d->iew * d->jns, nlev = (size_t)(k1 - k0), lo = per * k0;
+    OG_TRY(download(c, d->t + lo, T.t + lo, per * nlev));
+    OG_TRY(download(c, d->u + lo, T.u + lo, per * nlev));
+    OG_TRY(download(c, d->v + lo, T.v + lo, per * nlev));
+    OG_TRY(download(c, d->rh + lo, T.rh + lo, per * nlev));
+    if (k0 == 0) OG_TRY(download(c, d->slp, T.slp, per));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return rc;
+}
+
+extern "C" int og_qc_time_levels(og_ctx* c, const og_time_desc* d, const og_qc_params* p, int k0,
+                                 int k1, int run_consistency)
+{
+    REQUIRE(c && p, "null argument");
+    OG_TRY(check_desc(d, k0, k1, true));
+    if (k1 == k0) return OG_OK;
+    TimeDev T;
+    OG_TRY(mirror_in(c, d, k0, k1, true, T));
+    OG_TRY(qc_time_core(c, T, p, k0, k1, run_consistency));
+    const size_t nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0), lo = nrep * k0;
+    OG_TRY(download(c, d->qc_u + lo, T.qc_u + lo, nrep * nlev));
+    OG_TRY(download(c, d->qc_v + lo, T.qc_v + lo, nrep * nlev));
+    OG_TRY(download(c, d->qc_t + lo, T.qc_t + lo, nrep * nlev));
+    OG_TRY(download(c, d->qc_rh + lo, T.qc_rh + lo, nrep * nlev));
+    if (k0 == 0) OG_TRY(download(c, d->qc_slp, T.qc_slp, nrep));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
+extern "C" int og_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p)
+{
+    if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
+    return og_qc_time_levels(c, d, p, 0, d->kbu, 1);
+}

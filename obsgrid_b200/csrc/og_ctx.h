@@ -1,0 +1,152 @@
+// og_ctx.h -- host-side context of libobsgrid_gpu.so: device, stream, grow-only buffers,
+// counters and error reporting.  Internal; the public surface is include/obsgrid_gpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/obsgrid_gpu.h"
+
+namespace og {
+
+void set_error(const char* fmt, ...);
+
+#define OG_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            og::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                   \
+                          cudaGetErrorString(e__));                                       \
+            return OG_ERR_CUDA;                                                           \
+        }                                                                                 \
+    } while (0)
+
+#define OG_TRY(call)                                                                      \
+    do {                                                                                  \
+        int rc__ = (call);                                                                \
+        if (rc__ != OG_OK) return rc__;                                                   \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace og
+
+struct og_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    og_stats stats{};
+    int counting = 0;
+    unsigned long long* d_counters = nullptr;   // [0] updates, [1] candidates
+    int* d_flag = nullptr;                      // small device scratch (changed flags)
+    int* h_pinned_small = nullptr;              // pinned host scratch (>= 4 KiB)
+    std::map<std::string, og::DevBuf> bufs;     // named grow-only device buffers
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // kernel timing: event pairs recorded around the Cressman scan / buddy kernels when
+    // time_kernels is on; resolved lazily by og_last_kernel_ms (no sync on the hot path)
+    struct Timer { cudaEvent_t a, b; int kind; };
+    std::vector<Timer> timers;
+    size_t timers_used = 0;
+    bool time_kernels = false;
+    int timer_begin(int kind);   // records the start event; returns slot or -1
+    void timer_end(int slot);
+
+    // grow-only named device buffer; contents are NOT preserved on growth
+    int reserve(const char* name, size_t bytes, void** out);
+    template <class T> int reserve_t(const char* name, size_t count, T** out)
+    {
+        void* p = nullptr;
+        int rc = reserve(name, count * sizeof(T), &p);
+        *out = static_cast<T*>(p);
+        return rc;
+    }
+    void count_launch(int n = 1) { stats.kernel_launches += n; }
+};
+
+namespace og {
+
+// ---- OA (og_oa.cu) -------------------------------------------------------------------
+struct OaSlabHost {             // one (level, variable) slab of a batch, host description
+    float* g = nullptr;         // device: field to analyse, (iew,jns) x fastest, in/out
+    const float* ub = nullptr;  // device: pre-analysis u of the level (banana scheme)
+    const float* vb = nullptr;
+    int n = 0;                  // obs in the slab (known on host)
+    int ob_off = 0;             // first ob of the slab in the batch-wide ob arrays
+    int var = 0;
+    float pressure = 0.f;
+    float scale = 1.f;
+    int passes = 0;
+    int nscan = 0;
+    int radius[OG_MAX_SCAN] = {0};
+};
+
+struct OaBatch {
+    int iew = 0, jns = 0, crsdot = 1;
+    float dxd = 0.f;
+    int use_first_guess = 1, scale_rh = 0, smooth_type = 1;
+    std::vector<OaSlabHost> slabs;
+    int total_obs = 0;
+    // device, batch-wide, length total_obs
+    const float* xob = nullptr;
+    const float* yob = nullptr;
+    const float* val = nullptr;     // obs_value (innovations are derived), or
+    float* diff = nullptr;          // innovations (given when given_diff, else scratch)
+    float* fg = nullptr;            // fg_value (given when given_diff, else scratch)
+    bool given_diff = false;        // per-slab og_cressman: diff / fg supplied, one scan
+    bool clean_rh = true;           // apply the final RH clamp (proc_oa.F90:803)
+};
+
+int oa_run_batch(og_ctx* ctx, OaBatch& b);
+int innovation_device(og_ctx* ctx, const float* g, int iew, int jns, const float* x,
+                      const float* y, const float* val, int n, float scale, int use_fg,
+                      float* diff, float* fg);
+
+// ---- QC (og_qc.cu) -------------------------------------------------------------------
+struct QcSlabHost {
+    const float* g = nullptr;   // device: first-guess slab (iew,jns) as error_max sees it
+    int n = 0;
+    int ob_off = 0;
+    int var = 0;
+    float pressure = 0.f;
+    float max_error = 0.f;      // error_difference  (proc_qc.F90:264-309)
+    float max_buddy = 0.f;      // buddy_difference
+};
+
+struct QcBatch {
+    int iew = 0, jns = 0;
+    float dx_km = 0.f, buddy_weight = 1.f;
+    int do_error_max = 1, do_buddy = 1;
+    std::vector<QcSlabHost> slabs;
+    int total_obs = 0;
+    const float* xob = nullptr;
+    const float* yob = nullptr;
+    const float* val = nullptr;
+    const float* elev = nullptr;
+    const int* local_time = nullptr;
+    int* qc = nullptr;                    // in/out flags
+    // optional diagnostics (device, nullable)
+    float* aob = nullptr;
+    float* err_max = nullptr;
+    float* thr_max = nullptr;
+    float* err_buddy = nullptr;
+    float* difmax = nullptr;
+    int* buddy_num_final = nullptr;
+};
+
+int qc_run_batch(og_ctx* ctx, QcBatch& b);
+int local_time_device(og_ctx* ctx, int time_hhmm, const float* lon, int n, int* out);
+
+// ---- misc (og_misc.cu) ---------------------------------------------------------------
+const char* last_error();
+int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches);
+int fp32_peak(og_ctx* ctx, double* lane_ops_per_s);
+// (jns,iew) y-fastest <-> (iew,jns) x-fastest for nlev stacked levels
+int transpose_levels(og_ctx* ctx, const float* src, float* dst, int rows_fast, int cols_slow,
+                     int nlev);
+
+} // namespace og

@@ -1,0 +1,162 @@
+// og_misc.cu -- context management, error reporting, layout kernels and the FP32-pipe
+// micro-benchmark of libobsgrid_gpu.so.
+#include "og_ctx.h"
+#include "og_device.cuh"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace og {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+// ---- tiled transpose: src is [nlev][slow][fast] -> dst [nlev][fast][slow] --------------
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                 int nfast, int nslow)
+{
+    __shared__ float tile[32][33];
+    const size_t lev = (size_t)blockIdx.z * (size_t)nfast * (size_t)nslow;
+    int f = blockIdx.x * 32 + threadIdx.x;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int s = blockIdx.y * 32 + r;
+        if (f < nfast && s < nslow) tile[r][threadIdx.x] = src[lev + (size_t)s * nfast + f];
+    }
+    __syncthreads();
+    int s2 = blockIdx.y * 32 + threadIdx.x;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        int f2 = blockIdx.x * 32 + r;
+        if (f2 < nfast && s2 < nslow) dst[lev + (size_t)f2 * nslow + s2] = tile[threadIdx.x][r];
+    }
+}
+
+int transpose_levels(og_ctx* ctx, const float* src, float* dst, int nfast, int nslow, int nlev)
+{
+    if (nlev <= 0) return OG_OK;
+    dim3 blk(32, 8), grd((nfast + 31) / 32, (nslow + 31) / 32, nlev);
+    transpose_kernel<<<grd, blk, 0, ctx->stream>>>(src, dst, nfast, nslow);
+    ctx->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+// ---- FP32 pipe peak: independent FADD/FMUL chains, no FMA contraction -------------------
+template <int ILP>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b)
+{
+    float v[ILP];
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) v[q] = (float)(threadIdx.x + q) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int q = 0; q < ILP; ++q) v[q] = fadd(fmul(v[q], a), b); // FMUL + FADD, never FFMA
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) s += v[q];
+    if (s == 123.456f) out[0] = s; // keep the chain alive
+}
+
+int fp32_peak(og_ctx* ctx, double* lane_ops_per_s)
+{
+    float* d_out = nullptr;
+    OG_TRY(ctx->reserve_t("misc.peak", 16, &d_out));
+    constexpr int ILP = 8;
+    const int iters = 4096, blocks = ctx->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        OG_CUDA(cudaEventRecord(ctx->ev_a, ctx->stream));
+        fp32_peak_kernel<ILP><<<blocks, 256, 0, ctx->stream>>>(d_out, iters, 0.999f, 1e-3f);
+        OG_CUDA(cudaEventRecord(ctx->ev_b, ctx->stream));
+        OG_CUDA(cudaEventSynchronize(ctx->ev_b));
+        float ms = 0.f;
+        OG_CUDA(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+        double ops = (double)blocks * 256.0 * iters * ILP * 2.0;
+        if (rep > 0) best = std::max(best, ops / (ms * 1e-3));
+    }
+    ctx->count_launch(5);
+    *lane_ops_per_s = best;
+    return OG_OK;
+}
+
+// ---- self test of the fast exact division against __fdiv_rn ------------------------------
+__global__ void div_selftest_kernel(int n, unsigned seed, int rmax, unsigned long long* bad)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    // xorshift -> d2 in [0, R2), R2 = R*R for R in 1..rmax: the operands of the Cressman weight
+    unsigned s = seed ^ (0x9E3779B9u * (unsigned)(q + 1));
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    int R = 1 + (int)(s % (unsigned)rmax);
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    float R2 = (float)(R * R);
+    float d2 = R2 * ((float)(s >> 8) * (1.0f / 16777216.0f));
+    if (!(d2 < R2)) return;
+    float a = fsub(R2, d2), b = fadd(R2, d2);
+    if (__float_as_uint(fdiv_fast_exact(a, b)) != __float_as_uint(fdiv(a, b)))
+        atomicAdd(bad, 1ULL);
+}
+
+int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches)
+{
+    OG_CUDA(cudaMemsetAsync(ctx->d_counters + 2, 0, sizeof(unsigned long long), ctx->stream));
+    div_selftest_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, seed, rmax, ctx->d_counters + 2);
+    ctx->count_launch();
+    unsigned long long h = 0;
+    OG_CUDA(cudaMemcpyAsync(&h, ctx->d_counters + 2, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    OG_CUDA(cudaStreamSynchronize(ctx->stream));
+    *mismatches = (long long)h;
+    return OG_OK;
+}
+
+} // namespace og
+
+int og_ctx::reserve(const char* name, size_t bytes, void** out)
+{
+    og::DevBuf& b = bufs[name];
+    if (bytes > b.cap) {
+        if (b.p) {
+            cudaError_t e = cudaStreamSynchronize(stream);
+            if (e == cudaSuccess) e = cudaFree(b.p);
+            if (e != cudaSuccess) { og::set_error("cudaFree(%s): %s", name, cudaGetErrorString(e)); return OG_ERR_CUDA; }
+            b.p = nullptr; b.cap = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            og::set_error("cudaMalloc(%s, %zu bytes): %s", name, want, cudaGetErrorString(e));
+            b.p = nullptr;
+            return OG_ERR_ALLOC;
+        }
+        b.cap = want;
+    }
+    *out = b.p;
+    return OG_OK;
+}
+
+int og_ctx::timer_begin(int kind)
+{
+    if (!time_kernels) return -1;
+    if (timers_used == timers.size()) {
+        Timer t{};
+        if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) return -1;
+        timers.push_back(t);
+    }
+    Timer& t = timers[timers_used];
+    t.kind = kind;
+    cudaEventRecord(t.a, stream);
+    return (int)timers_used++;
+}
+
+void og_ctx::timer_end(int slot)
+{
+    if (slot >= 0) cudaEventRecord(timers[(size_t)slot].b, stream);
+}

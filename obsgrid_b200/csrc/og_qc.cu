@@ -1,0 +1,416 @@
+// og_qc.cu -- fused qc1 gross-error check + qc2 buddy check on sm_100a.
+//
+// Reference: src/qc1_module.F90:9-300 (error_max), src/qc2_module.F90:9-388 (buddy_check),
+// src/qc0_module.F90:9-76 (flag arithmetic), :236-267 (local).
+//
+// The buddy means are FP32 sums over neighbours in ascending slab index; QC flags have to be
+// bit-identical, so that order is kept: one thread owns one observation and walks the other
+// observations of the slab in index order through shared-memory tiles (all-pairs, the
+// reference's N^2, at FP32-pipe rate).  sqrt(dx*dx+dy*dy)*dx_km compared with the range and
+// with 0.1 km is replaced by two thresholds on dx*dx+dy*dy found on the host by bisection
+// over the float ordering with the very same operations, which is exact because
+// sqrtf and the multiply are monotone.
+//
+// The reference relaxes difmax(num) by 1.2 inside the station loop when exactly two buddies
+// survive (qc2_module.F90:327), and later stations read the relaxed value for buddies with a
+// smaller index (:277-278).  That loop-carried dependency is resolved as a fix-point: the
+// removal pass is re-run with the previous iteration's relaxation mask until the mask is
+// stable (the dependency graph is a DAG ordered by index, so the fix-point is the
+// sequential result).  Only buddies with diff > 1.25*difmax can ever be removed, so the
+// removal pass sweeps a compacted, index-ordered list of those "suspects" only.
+#include "og_ctx.h"
+#include "og_device.cuh"
+
+#include <algorithm>
+#include <math.h>
+#include <string.h>
+
+namespace og {
+
+struct QcSlabDev {
+    const float* g;
+    int n, ob_off, var;
+    float pressure, max_error, max_buddy;
+    float t_lo, t_hi;   // buddy iff t_lo <= dx*dx+dy*dy <= t_hi
+};
+
+struct QcDev {
+    const QcSlabDev* slabs;
+    int iew, jns;
+    float buddy_weight;
+    int do_error_max, do_buddy;
+    const float* xob;
+    const float* yob;
+    const float* val;
+    const float* elev;
+    const int* local_time;
+    int* qc;
+    float4* q4;          // {x, y, ob-aob, difmax0}
+    int* emax_fail;      // error_max verdict per ob
+    int* cnt;            // buddy_num
+    float* sum;          // sum of buddy diffs (index order)
+    int* susp_list;      // per slab, local indices of suspects in index order
+    int* susp_count;     // per slab
+    unsigned char* mod_in;   // relaxation mask of the previous fix-point iteration
+    unsigned char* mod_out;
+    int* kob;            // buddy_num_final
+    float* err;          // buddy err
+    int* changed;
+    // diagnostics (nullable)
+    float* d_aob; float* d_err_max; float* d_thr_max; float* d_err_buddy; float* d_difmax;
+    int* d_bnf;
+};
+
+__device__ __forceinline__ float dewpoint_factor(float ob)
+{   // qc1_module.F90:156-166 == qc2_module.F90:177-186
+    if ((ob < 255.0f) && (ob >= 235.0f)) return 1.25f;
+    if ((ob < 235.0f) && (ob >= 215.0f)) return 1.50f;
+    if (ob < 215.0f) return 1.75f;
+    return 1.00f;
+}
+
+// error_max (qc1_module.F90:102-249) and the per-ob set-up of buddy_check (:121-213).
+__global__ void __launch_bounds__(256) qc_prep_kernel(QcDev A)
+{
+    const QcSlabDev& S = A.slabs[blockIdx.y];
+    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= S.n) return;
+    const int gi = S.ob_off + li;
+    const float x = A.xob[gi], y = A.yob[gi], ob = A.val[gi];
+    const float plevel = S.pressure;
+    const float aob = bilinear(S.g, A.iew, x, y);
+    const float err = fsub(ob, aob);
+
+    int fail = 0;
+    if (A.do_error_max) {
+        float factor = 1.0f;
+        switch (S.var) {
+        case OG_VAR_UU: case OG_VAR_VV:
+            if (plevel <= 499.9f) factor = 1.5f;
+            else if (plevel <= 1000.1f) factor = 1.25f;
+            break;
+        case OG_VAR_TT:
+            if (plevel > 1000.1f) {
+                int lt = A.local_time[gi];
+                factor = (lt >= 1100 && lt <= 2000) ? 1.5f : 1.25f;
+            } else if ((plevel <= 1000.1f) && (plevel > 700.0f)) factor = 0.85f;
+            else factor = 0.65f;
+            break;
+        case OG_VAR_PMSLPSFC:
+            factor = fadd(1.0f, fdiv(fabsf(A.elev[gi]), 2000.0f));
+            break;
+        case OG_VAR_DEWPOINT:
+            factor = dewpoint_factor(ob);
+            break;
+        default: break;
+        }
+        float thr = fmul(factor, S.max_error);
+        if (S.var == OG_VAR_UU || S.var == OG_VAR_VV) thr = fmaxf(thr, fmul(0.15f, aob));
+        fail = fabsf(err) > thr;
+        if (A.d_err_max) A.d_err_max[gi] = err;
+        if (A.d_thr_max) A.d_thr_max[gi] = thr;
+    }
+    A.emax_fail[gi] = fail;
+    if (A.d_aob) A.d_aob[gi] = aob;
+
+    float difmax = S.max_buddy;
+    switch (S.var) { // qc2_module.F90:131-191
+    case OG_VAR_UU: case OG_VAR_VV:
+        if (plevel < 401.f) difmax = fmul(S.max_buddy, 1.7f);
+        else if (plevel < 701.f) difmax = fmul(S.max_buddy, 1.4f);
+        else if (plevel < 851.f) difmax = fmul(S.max_buddy, 1.1f);
+        break;
+    case OG_VAR_PMSLPSFC:
+        difmax = fmul(S.max_buddy, fadd(1.0f, fdiv(A.elev[gi], 2000.0f)));
+        break;
+    case OG_VAR_TT:
+        if (plevel < 401.f) difmax = fmul(S.max_buddy, 0.6f);
+        else if (plevel < 701.f) difmax = fmul(S.max_buddy, 0.8f);
+        break;
+    case OG_VAR_DEWPOINT:
+        difmax = fmul(S.max_buddy, dewpoint_factor(ob));
+        break;
+    default: break;
+    }
+    difmax = fmul(difmax, A.buddy_weight); // :193
+    A.q4[gi] = make_float4(x, y, err, difmax);
+    A.mod_in[gi] = 0;
+}
+
+// station_loop_2/3, first half (qc2_module.F90:223-256): buddy count and index-ordered sum.
+constexpr int BUDDY_THREADS = 256;
+__global__ void __launch_bounds__(BUDDY_THREADS) buddy_pass1_kernel(QcDev A)
+{
+    const QcSlabDev& S = A.slabs[blockIdx.y];
+    if ((int)(blockIdx.x * BUDDY_THREADS) >= S.n) return;
+    const int li = blockIdx.x * BUDDY_THREADS + threadIdx.x;
+    const bool valid = li < S.n;
+    const float4 me = valid ? A.q4[S.ob_off + li] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
+    const float tlo = S.t_lo, thi = S.t_hi;
+    __shared__ float4 tile[BUDDY_THREADS];
+    int cnt = 0;
+    float sum = 0.f;
+    for (int base = 0; base < S.n; base += BUDDY_THREADS) {
+        const int k = base + threadIdx.x;
+        tile[threadIdx.x] = (k < S.n) ? A.q4[S.ob_off + k] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < BUDDY_THREADS; ++c) {
+            const float4 o = tile[c];
+            const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
+            const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+            const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
+            cnt += b ? 1 : 0;
+            sum = fadd(sum, b ? o.z : 0.f);
+        }
+        __syncthreads();
+    }
+    if (valid) { A.cnt[S.ob_off + li] = cnt; A.sum[S.ob_off + li] = sum; }
+}
+
+// Index-ordered list of the obs that can ever be removed from a buddy set: diff >
+// 1.25*difmax (with either the plain or the relaxed difmax), qc2_module.F90:277-282.
+__global__ void __launch_bounds__(256) suspect_kernel(QcDev A)
+{
+    const QcSlabDev& S = A.slabs[blockIdx.x];
+    int* out = A.susp_list + S.ob_off;
+    __shared__ int s_w[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int done = 0;
+    for (int base = 0; base < S.n; base += 256) {
+        const int li = base + threadIdx.x;
+        bool sp = false;
+        if (li < S.n) {
+            float4 o = A.q4[S.ob_off + li];
+            float dm = fminf(o.w, fmul(1.2f, o.w));
+            sp = o.z > fmul(dm, 1.25f);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, sp);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { int v = s_w[w]; woff += (w < warp) ? v : 0; tot += v; }
+        if (sp) out[done + woff + __popc(m & ((1u << lane) - 1u))] = li;
+        done += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) A.susp_count[blockIdx.x] = done;
+}
+
+// remove_bad_ob + err (qc2_module.F90:269-327) for one relaxation mask.
+__global__ void __launch_bounds__(BUDDY_THREADS) buddy_pass2_kernel(QcDev A)
+{
+    const QcSlabDev& S = A.slabs[blockIdx.y];
+    if ((int)(blockIdx.x * BUDDY_THREADS) >= S.n) return;
+    const int li = blockIdx.x * BUDDY_THREADS + threadIdx.x;
+    const bool valid = li < S.n;
+    const int gi = S.ob_off + li;
+    const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
+    const int cnt = valid ? A.cnt[gi] : 0;
+    float sum = valid ? A.sum[gi] : 0.f;
+    const float average = (cnt > 0) ? fdiv(sum, (float)cnt) : 0.f;
+    const float tlo = S.t_lo, thi = S.t_hi;
+    const int ns = A.susp_count[blockIdx.y];
+    const int* __restrict__ sl = A.susp_list + S.ob_off;
+    __shared__ float4 tile[BUDDY_THREADS];
+    __shared__ int tidx[BUDDY_THREADS];   // local index, bit 30 = relaxed
+    int kob = cnt;
+    for (int base = 0; base < ns; base += BUDDY_THREADS) {
+        const int k = base + threadIdx.x;
+        if (k < ns) {
+            int lk = sl[k];
+            tile[threadIdx.x] = A.q4[S.ob_off + lk];
+            tidx[threadIdx.x] = lk | (A.mod_in[S.ob_off + lk] ? (1 << 30) : 0);
+        }
+        __syncthreads();
+        const int lim = min(BUDDY_THREADS, ns - base);
+        if (cnt >= 2) {
+            for (int c = 0; c < lim; ++c) {
+                const float4 o = tile[c];
+                const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
+                const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+                if ((d2 <= thi) && (d2 >= tlo)) {
+                    const int ti = tidx[c];
+                    const int lk = ti & ~(1 << 30);
+                    // stations before `num` have already been relaxed when num is visited
+                    const float dm = ((ti >> 30) && lk < li) ? fmul(1.2f, o.w) : o.w;
+                    const float diff_numj = fabsf(fsub(o.z, average));
+                    if (o.z > fmul(dm, 1.25f) && diff_numj > dm) {
+                        kob -= 1;
+                        sum = fsub(sum, o.z);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!valid) return;
+    float err = 0.f;
+    int bnf = 0;
+    if (cnt >= 2) {
+        bnf = kob;
+        if (kob >= 2) err = fsub(me.z, fdiv(sum, (float)kob));
+    }
+    A.kob[gi] = bnf;
+    A.err[gi] = err;
+    const unsigned char m = (bnf == 2) ? 1 : 0;
+    A.mod_out[gi] = m;
+    if (m != A.mod_in[gi]) *A.changed = 1;
+}
+
+// Flags: error_max (2**16), no_buddies (2**14), buddy (2**17), in the reference's order.
+__global__ void __launch_bounds__(256) qc_flag_kernel(QcDev A)
+{
+    const QcSlabDev& S = A.slabs[blockIdx.y];
+    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= S.n) return;
+    const int gi = S.ob_off + li;
+    int q = A.qc[gi];
+    if (A.do_error_max && A.emax_fail[gi]) q = qc_add_flag(q, OG_FAILS_ERROR_MAX);
+    if (A.do_buddy) {
+        const int cnt = A.cnt[gi], bnf = A.kob[gi];
+        const float err = A.err[gi];
+        float dm = A.q4[gi].w;
+        if (cnt < 2 || bnf < 2) q = qc_add_flag(q, OG_NO_BUDDIES);   // :309 / :322
+        if (bnf == 2) dm = fmul(1.2f, dm);                           // :327
+        if (fabsf(err) > dm) q = qc_add_flag(q, OG_FAILS_BUDDY_CHECK);
+        if (A.d_err_buddy) A.d_err_buddy[gi] = err;
+        if (A.d_difmax) A.d_difmax[gi] = dm;
+        if (A.d_bnf) A.d_bnf[gi] = bnf;
+    }
+    A.qc[gi] = q;
+}
+
+// qc0_module.F90:261-267
+__global__ void local_time_kernel(int hh, const float* __restrict__ lon, int n, int* __restrict__ out)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int lt = (int)fadd((float)hh, fdiv(lon[q], 15.f));
+    if (lt < 0) lt = 24 + lt;
+    out[q] = (lt % 24) * 100;
+}
+
+int local_time_device(og_ctx* ctx, int time_hhmm, const float* lon, int n, int* out)
+{
+    if (n <= 0) return OG_OK;
+    local_time_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(time_hhmm / 100, lon, n, out);
+    ctx->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+// ---- host: exact thresholds on d2 for  lo <= sqrtf(d2)*dx <= hi  ------------------------
+static float bits2f(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static float dist_of(float d2, float dx)
+{
+    volatile float s = sqrtf(d2);
+    volatile float d = s * dx;
+    return d;
+}
+// largest non-negative finite float d2 with dist_of(d2) <= lim (or -1 if none)
+static float threshold_le(float lim, float dx)
+{
+    if (!(dist_of(0.f, dx) <= lim)) return -1.f;
+    uint32_t lo = 0, hi = 0x7f7fffffu; // invariant: pred(lo) true
+    if (dist_of(bits2f(hi), dx) <= lim) return bits2f(hi);
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (dist_of(bits2f(mid), dx) <= lim) lo = mid; else hi = mid;
+    }
+    return bits2f(lo);
+}
+// smallest non-negative float d2 with dist_of(d2) >= lim (or +inf if none)
+static float threshold_ge(float lim, float dx)
+{
+    if (dist_of(0.f, dx) >= lim) return 0.f;
+    uint32_t lo = 0, hi = 0x7f7fffffu; // invariant: pred(lo) false
+    if (!(dist_of(bits2f(hi), dx) >= lim)) return INFINITY;
+    while (hi - lo > 1) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (dist_of(bits2f(mid), dx) >= lim) hi = mid; else lo = mid;
+    }
+    return bits2f(hi);
+}
+
+int qc_run_batch(og_ctx* ctx, QcBatch& b)
+{
+    const int ns = (int)b.slabs.size();
+    if (ns == 0) return OG_OK;
+    cudaStream_t st = ctx->stream;
+    std::vector<QcSlabDev> hs(ns);
+    int max_n = 0;
+    int64_t pair_tests = 0, nobs = 0;
+    // thresholds depend on the range class only: cache the three
+    float thi_c[3], tlo = threshold_ge(0.1f, b.dx_km);
+    const float ranges[3] = {650.f, 300.f, 500.f};
+    for (int r = 0; r < 3; ++r) thi_c[r] = threshold_le(ranges[r], b.dx_km);
+    for (int s = 0; s < ns; ++s) {
+        const QcSlabHost& h = b.slabs[s];
+        QcSlabDev& d = hs[s];
+        d.g = h.g; d.n = h.n; d.ob_off = h.ob_off; d.var = h.var; d.pressure = h.pressure;
+        d.max_error = h.max_error; d.max_buddy = h.max_buddy;
+        int rc = (h.pressure <= 201.0f) ? 0 : ((h.pressure <= 1000.1f) ? 1 : 2); // :121-127
+        d.t_lo = tlo; d.t_hi = thi_c[rc];
+        max_n = std::max(max_n, h.n);
+        pair_tests += (int64_t)h.n * (h.n > 0 ? h.n - 1 : 0);
+        nobs += h.n;
+    }
+    if (max_n == 0) return OG_OK;
+    const size_t tot = (size_t)std::max(b.total_obs, 1);
+    QcSlabDev* d_slabs = nullptr;
+    OG_TRY(ctx->reserve_t("qc.slabs", (size_t)ns, &d_slabs));
+    QcDev A{};
+    A.slabs = d_slabs; A.iew = b.iew; A.jns = b.jns; A.buddy_weight = b.buddy_weight;
+    A.do_error_max = b.do_error_max; A.do_buddy = b.do_buddy;
+    A.xob = b.xob; A.yob = b.yob; A.val = b.val; A.elev = b.elev; A.local_time = b.local_time;
+    A.qc = b.qc;
+    OG_TRY(ctx->reserve_t("qc.q4", tot, &A.q4));
+    OG_TRY(ctx->reserve_t("qc.emax", tot, &A.emax_fail));
+    OG_TRY(ctx->reserve_t("qc.cnt", tot, &A.cnt));
+    OG_TRY(ctx->reserve_t("qc.sum", tot, &A.sum));
+    OG_TRY(ctx->reserve_t("qc.susp", tot, &A.susp_list));
+    OG_TRY(ctx->reserve_t("qc.suspn", (size_t)ns, &A.susp_count));
+    OG_TRY(ctx->reserve_t("qc.mod0", tot, &A.mod_in));
+    OG_TRY(ctx->reserve_t("qc.mod1", tot, &A.mod_out));
+    OG_TRY(ctx->reserve_t("qc.kob", tot, &A.kob));
+    OG_TRY(ctx->reserve_t("qc.err", tot, &A.err));
+    A.changed = ctx->d_flag;
+    A.d_aob = b.aob; A.d_err_max = b.err_max; A.d_thr_max = b.thr_max;
+    A.d_err_buddy = b.err_buddy; A.d_difmax = b.difmax; A.d_bnf = b.buddy_num_final;
+
+    OG_CUDA(cudaMemcpyAsync(d_slabs, hs.data(), sizeof(QcSlabDev) * ns, cudaMemcpyHostToDevice, st));
+    dim3 g_ob((max_n + 255) / 256, ns);
+    qc_prep_kernel<<<g_ob, 256, 0, st>>>(A);
+    ctx->count_launch();
+    if (b.do_buddy) {
+        dim3 g_b((max_n + BUDDY_THREADS - 1) / BUDDY_THREADS, ns);
+        const int tslot = ctx->timer_begin(1);
+        buddy_pass1_kernel<<<g_b, BUDDY_THREADS, 0, st>>>(A);
+        ctx->timer_end(tslot);
+        suspect_kernel<<<ns, 256, 0, st>>>(A);
+        ctx->count_launch(2);
+        int iters = 0;
+        for (;;) {
+            OG_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
+            buddy_pass2_kernel<<<g_b, BUDDY_THREADS, 0, st>>>(A);
+            ctx->count_launch();
+            OG_CUDA(cudaMemcpyAsync(ctx->h_pinned_small, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            OG_CUDA(cudaStreamSynchronize(st));
+            ++iters;
+            if (!ctx->h_pinned_small[0]) break;
+            std::swap(A.mod_in, A.mod_out);
+            if (iters > max_n + 2) { set_error("buddy difmax fix-point did not converge"); return OG_ERR_NOCONV; }
+        }
+        ctx->stats.buddy_fixpoint_iters += iters;
+        ctx->stats.buddy_pair_tests += pair_tests;
+        ctx->stats.buddy_obs += nobs;
+    }
+    qc_flag_kernel<<<g_ob, 256, 0, st>>>(A);
+    ctx->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+} // namespace og

@@ -721,6 +721,7 @@ static void qc_level(const og_time_desc* d, const og_qc_params* p, int k)
         if (k > 0 && (ivar == 5 || ivar == 6)) continue;
         if (ivar == 6) continue;                    /* qc_psfc = .FALSE. (proc_namelist.F90:73) */
         if (ivar == 7 && !p->qc_dewpoint) continue;
+        if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
         float error_difference = 0.f, buddy_difference = 0.f;
         const float* obv = NULL; int* qcv = NULL;
         switch (ivar) {
@@ -828,6 +829,7 @@ static int oa_level(const og_time_desc* d, const og_oa_params* p, int k)
 
     for (int ivar = 1; ivar <= 5; ++ivar) { /* PSFC (6) needs oa_psfc: off */
         if (ivar == 5 && k > 0) continue;
+        if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
         int passes; float scale = (ivar == 5) ? 100.f : 1.f;
         const int psfc[5] = {p->smooth_sfc_wind, p->smooth_sfc_wind, p->smooth_sfc_temp,
                              p->smooth_sfc_rh, p->smooth_sfc_slp};
@@ -861,9 +863,9 @@ static int oa_level(const og_time_desc* d, const og_oa_params* p, int k)
 }
 
 /* mixing_ratio's side effect on the first guess (final_analysis_module.F90:1055) */
-static void clamp_fg_rh(const og_time_desc* d)
+static void clamp_fg_rh(const og_time_desc* d, int k_begin, int k_end)
 {
-    for (int k = 0; k < d->kbu; ++k)
+    for (int k = k_begin; k < k_end; ++k)
         for (int i = 0; i < d->iew - 1; ++i)
             for (int j = 0; j < d->jns - 1; ++j) {
                 float* v = &d->rh[((size_t)k * d->iew + i) * d->jns + j];
@@ -874,7 +876,7 @@ static void clamp_fg_rh(const og_time_desc* d)
 int ogo_oa_time(const og_time_desc* d, const og_oa_params* p, int k_begin, int k_end)
 {
     int rc = OG_OK;
-    if (p->clamp_fg_rh) clamp_fg_rh(d);
+    if (p->clamp_fg_rh) clamp_fg_rh(d, k_begin, k_end);
     for (int k = k_begin; k < k_end; ++k) {
         if (p->surface_only && k > 0) break; /* proc_oa.F90:365 */
         int r = oa_level(d, p, k);
@@ -916,7 +918,7 @@ int ogo_oa_time_mt(const og_time_desc* d, const og_oa_params* p, int k_begin, in
                    int threads)
 {
     if (threads <= 1) return ogo_oa_time(d, p, k_begin, k_end);
-    if (p->clamp_fg_rh) clamp_fg_rh(d);
+    if (p->clamp_fg_rh) clamp_fg_rh(d, k_begin, k_end);
     int next = k_begin, rc = OG_OK;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
     mt_job* jobs = (mt_job*)malloc(sizeof(mt_job) * (size_t)threads);

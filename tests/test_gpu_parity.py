@@ -1,0 +1,331 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): QC flags bit-identical; analysed fields within 1e-5 relative /
+1e-3 absolute.  The kernels keep the reference's summation order, so everything that does not
+go through atan2 (banana shape) or log (DEWPOINT) is in fact compared bit-for-bit here.
+"""
+import numpy as np
+import pytest
+
+from obsgrid_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-3       # north_star tolerance for analysed fields
+
+
+def rng_obs(rng, n, iew, jns, lo=2.0):
+    x = rng.uniform(lo, iew - 1.0, n).astype(np.float32)
+    y = rng.uniform(lo, jns - 1.0, n).astype(np.float32)
+    return x, y
+
+
+def wavy(iew, jns, a=10.0, b=280.0, seed=0):
+    i = np.arange(iew)[None, :]; j = np.arange(jns)[:, None]
+    return (b + a * np.sin(i / 7.0 + seed) * np.cos(j / 5.0)).astype(np.float32)
+
+
+def test_fast_div_is_exact(ctx):
+    """The FCHK-less division used for the Cressman weight equals IEEE division."""
+    assert ctx.selftest_div(1 << 24, seed=7, rmax=100) == 0
+    assert ctx.selftest_div(1 << 22, seed=99, rmax=4000) == 0
+
+
+@pytest.mark.parametrize("iew,jns,n", [(40, 36, 300), (131, 77, 5000), (16, 16, 1), (33, 18, 0)])
+def test_innovation_bit_exact(ctx, oracle, iew, jns, n):
+    rng = np.random.default_rng(iew * 1000 + n)
+    g = wavy(iew, jns)
+    x, y = rng_obs(rng, n, iew, jns)
+    ob = rng.normal(280, 8, n).astype(np.float32)
+    for scale, ufg in ((1.0, True), (100.0, True), (1.0, False)):
+        d0, f0 = oracle.innovation(g, x, y, ob, scale, ufg)
+        d1, f1 = ctx.innovation(g, x, y, ob, scale, ufg)
+        np.testing.assert_array_equal(d0, d1)
+        if ufg:
+            np.testing.assert_array_equal(f0, f1)
+
+
+@pytest.mark.parametrize("var", [3, 5])
+@pytest.mark.parametrize("iew,jns,n,R", [(64, 48, 400, 5), (100, 100, 2000, 10), (37, 29, 60, 2),
+                                         (200, 150, 9000, 12), (20, 20, 5, 30)])
+def test_cressman_circle_bit_exact(ctx, oracle, var, iew, jns, n, R):
+    rng = np.random.default_rng(iew + 7 * n + R)
+    g = wavy(iew, jns)
+    x, y = rng_obs(rng, n, iew, jns, lo=1.0)      # some obs fall in the skipped edge band
+    d = rng.normal(0, 3, n).astype(np.float32)
+    a = oracle.cressman(d, x, y, g, var, R, 12.0)
+    b = ctx.cressman(d, x, y, g, var, R, 12.0)
+    np.testing.assert_array_equal(a, b)
+    a = oracle.cressman(d, x, y, g, var, R, 12.0, use_first_guess=False)
+    b = ctx.cressman(d, x, y, g, var, R, 12.0, use_first_guess=False)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_cressman_dense_cluster_overflows_staging(ctx, oracle):
+    """More candidates per tile than the shared-memory staging holds (batched consumption)."""
+    rng = np.random.default_rng(5)
+    iew, jns, n = 80, 70, 12000
+    g = wavy(iew, jns)
+    x = np.clip(rng.normal(40, 3.0, n), 2, iew - 1).astype(np.float32)
+    y = np.clip(rng.normal(35, 3.0, n), 2, jns - 1).astype(np.float32)
+    d = rng.normal(0, 2, n).astype(np.float32)
+    np.testing.assert_array_equal(oracle.cressman(d, x, y, g, 3, 9, 12.0),
+                                  ctx.cressman(d, x, y, g, 3, 9, 12.0))
+
+
+def wind_fields(iew, jns, jet=40.0, curl=True):
+    i = np.arange(1, iew + 1, dtype=np.float64)[None, :]
+    j = np.arange(1, jns + 1, dtype=np.float64)[:, None]
+    yc = jns / 2 + 0.15 * jns * np.sin(2 * np.pi * i / iew * 1.5)
+    core = np.exp(-((j - yc) / (0.12 * jns)) ** 2)
+    u = 3.0 + jet * core
+    v = jet * core * (0.15 * jns * 2 * np.pi * 1.5 / iew) * np.cos(2 * np.pi * i / iew * 1.5) if curl \
+        else 0 * u
+    return u.astype(np.float32), (v + 0 * u).astype(np.float32)
+
+
+@pytest.mark.parametrize("var", [1, 2, 4])
+@pytest.mark.parametrize("pressure", [300.0, 850.0, 1001.0])
+def test_cressman_anisotropic(ctx, oracle, var, pressure):
+    rng = np.random.default_rng(int(pressure) + var)
+    iew, jns, n, R = 120, 96, 1500, 6
+    g = wavy(iew, jns, 20.0, 50.0)
+    ub, vb = wind_fields(iew, jns)
+    x, y = rng_obs(rng, n, iew, jns, lo=1.0)
+    d = rng.normal(0, 5, n).astype(np.float32)
+    fg = np.abs(rng.normal(50, 20, n)).astype(np.float32) + 1
+    oracle.reset_stats()
+    a = oracle.cressman(d, x, y, g, var, R, 12.0, ub, vb, pressure, fg_value=fg, scale_rh=True)
+    st = oracle.get_stats()
+    b = ctx.cressman(d, x, y, g, var, R, 12.0, ub, vb, pressure, fg_value=fg, scale_rh=True)
+    assert st["n_ellipse"] > 0
+    if st["n_banana"] == 0:
+        np.testing.assert_array_equal(a, b)
+    else:   # atan2f: libdevice vs glibc differ in the last place -> tolerance, not bits
+        np.testing.assert_allclose(b, a, rtol=RTOL, atol=ATOL)
+        assert np.mean(a != b) < 0.2
+
+
+def test_cressman_ellipse_only_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(11)
+    iew, jns, n, R = 90, 60, 800, 5
+    g = wavy(iew, jns)
+    ub, vb = wind_fields(iew, jns, jet=45.0, curl=False)      # straight flow: v = 0 -> ellipse
+    x, y = rng_obs(rng, n, iew, jns)
+    d = rng.normal(0, 5, n).astype(np.float32)
+    oracle.reset_stats()
+    a = oracle.cressman(d, x, y, g, 1, R, 12.0, ub, vb, 300.0)
+    st = oracle.get_stats()
+    assert st["n_banana"] == 0 and st["n_ellipse"] > 50 and st["n_circle"] > 50
+    np.testing.assert_array_equal(a, ctx.cressman(d, x, y, g, 1, R, 12.0, ub, vb, 300.0))
+
+
+@pytest.mark.parametrize("smooth_type,passes", [(1, 1), (1, 3), (2, 2)])
+def test_cressman_smoothing_bit_exact(ctx, oracle, smooth_type, passes):
+    rng = np.random.default_rng(3)
+    iew, jns, n = 70, 55, 500
+    g = wavy(iew, jns)
+    x, y = rng_obs(rng, n, iew, jns)
+    d = rng.normal(0, 3, n).astype(np.float32)
+    a = oracle.cressman(d, x, y, g, 3, 6, 12.0, passes=passes, smooth_type=smooth_type)
+    b = ctx.cressman(d, x, y, g, 3, 6, 12.0, passes=passes, smooth_type=smooth_type)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_oa_slab_multi_scan(ctx, oracle):
+    rng = np.random.default_rng(21)
+    iew, jns, n = 150, 120, 3000
+    g = wavy(iew, jns, 25.0, 60.0)
+    ub, vb = wind_fields(iew, jns, curl=False)
+    x, y = rng_obs(rng, n, iew, jns)
+    for var, scale, p in ((3, 1.0, 500.0), (5, 100.0, 1001.0), (4, 1.0, 700.0)):
+        ob = (rng.normal(60, 15, n) * scale).astype(np.float32)
+        a, rca, nsa = oracle.oa_slab(g, var, p, ob, x, y, [10, 8, 6, 4], 12.0, ub, vb, scale,
+                                     scale_rh=True)
+        b, rcb, nsb = ctx.oa_slab(g, var, p, ob, x, y, [10, 8, 6, 4], 12.0, ub, vb, scale,
+                                  scale_rh=True)
+        assert (rca, nsa) == (rcb, nsb) == (0, 4)
+        np.testing.assert_array_equal(a, b)
+    # surface radius scaling and the 4.5-cell floor (proc_oa.F90:663-707)
+    a, rca, nsa = oracle.oa_slab(g, 3, 1001.0, ob, x, y, [30, 20, 10], 3.0, sfc_mult=0.4)
+    b, rcb, nsb = ctx.oa_slab(g, 3, 1001.0, ob, x, y, [30, 20, 10], 3.0, sfc_mult=0.4)
+    assert (rca, nsa) == (rcb, nsb) == (0, 2)
+    np.testing.assert_array_equal(a, b)
+    a, rca, nsa = oracle.oa_slab(g, 3, 1001.0, ob, x, y, [10, 5], 3.0, sfc_mult=0.4)
+    b, rcb, nsb = ctx.oa_slab(g, 3, 1001.0, ob, x, y, [10, 5], 3.0, sfc_mult=0.4)
+    assert (rca, nsa) == (rcb, nsb) == (-5, 0)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_local_time_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(2)
+    lon = rng.uniform(-180, 180, 5000).astype(np.float32)
+    for hhmm in (0, 100, 1200, 2359):
+        np.testing.assert_array_equal(oracle.local_time(hhmm, lon), ctx.local_time(hhmm, lon))
+
+
+@pytest.mark.parametrize("var,pressure", [(1, 300.0), (2, 1001.0), (3, 1001.0), (3, 850.0), (3, 500.0),
+                                          (4, 700.0), (5, 1001.0), (6, 1001.0), (7, 500.0)])
+def test_error_max_bit_exact(ctx, oracle, var, pressure):
+    rng = np.random.default_rng(var * 10 + int(pressure))
+    iew, jns, n = 90, 70, 4000
+    g = wavy(iew, jns, 12.0, 270.0 if var in (3, 7) else 20.0)
+    x, y = rng_obs(rng, n, iew, jns)
+    ob = (g.mean() + rng.normal(0, 12, n)).astype(np.float32)
+    elev = rng.uniform(-500, 3000, n).astype(np.float32)
+    lt = (rng.integers(0, 24, n) * 100).astype(np.int32)
+    q0 = (rng.integers(0, 4, n) * (1 << 14)).astype(np.int32)
+    a = oracle.error_max(ob, x, y, elev, q0, g, var, 10.0, pressure, lt)
+    b = ctx.error_max(ob, x, y, elev, q0, g, var, 10.0, pressure, lt)
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+    assert 0 < np.count_nonzero(a[0] & (1 << 16)) < n
+
+
+@pytest.mark.parametrize("var,pressure,n,dx", [(3, 1001.0, 3000, 30.0), (1, 300.0, 2500, 30.0),
+                                               (5, 1001.0, 700, 12.0), (4, 150.0, 1200, 60.0),
+                                               (7, 500.0, 300, 90.0), (6, 1001.0, 900, 30.0),
+                                               (3, 500.0, 1, 30.0), (3, 500.0, 2, 30.0),
+                                               (2, 700.0, 257, 150.0)])
+def test_buddy_check_bit_exact(ctx, oracle, var, pressure, n, dx):
+    rng = np.random.default_rng(var + n)
+    iew, jns = 110, 90
+    g = wavy(iew, jns, 6.0, 260.0 if var in (3, 7) else 10.0)
+    x, y = rng_obs(rng, n, iew, jns)
+    if n > 10:                       # co-located pairs: distance < 0.1 km is not a buddy
+        x[1], y[1] = x[0], y[0]
+    ob = (g.mean() + rng.normal(0, 5, n)).astype(np.float32)
+    ob[rng.random(n) < 0.05] += 40.0
+    elev = rng.uniform(-3000, 3000, n).astype(np.float32)
+    q0 = (rng.integers(0, 2, n) * (1 << 16)).astype(np.int32)
+    a = oracle.buddy_check(ob, x, y, q0, elev, g, var, pressure, dx, 1.0, 8.0)
+    b = ctx.buddy_check(ob, x, y, q0, elev, g, var, pressure, dx, 1.0, 8.0)
+    names = ("qc", "aob", "err", "difmax", "buddy_num_final")
+    for nm, u, v in zip(names, a, b):
+        np.testing.assert_array_equal(u, v, err_msg=nm)
+
+
+def test_buddy_relaxation_fixpoint(ctx, oracle):
+    """Sparse network where many obs keep exactly two buddies: the x1.2 relaxation of
+    qc2_module.F90:327 feeds later stations; the GPU fix-point must equal the serial loop."""
+    rng = np.random.default_rng(8)
+    iew, jns, n = 400, 400, 1500
+    g = np.zeros((jns, iew), np.float32)
+    x, y = rng_obs(rng, n, iew, jns)
+    ob = rng.normal(0, 6, n).astype(np.float32)
+    ob[rng.random(n) < 0.3] += 11.0          # many diffs between 1.25*d and 1.25*1.2*d
+    z = np.zeros(n, np.float32)
+    ctx.reset_stats()
+    a = oracle.buddy_check(ob, x, y, np.zeros(n, np.int32), z, g, 5, 500.0, 30.0, 1.0, 8.0)
+    b = ctx.buddy_check(ob, x, y, np.zeros(n, np.int32), z, g, 5, 500.0, 30.0, 1.0, 8.0)
+    assert np.count_nonzero(a[4] == 2) > 20
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+    assert ctx.stats()["buddy_fixpoint_iters"] >= 2
+
+
+def test_qc_slab_fused(ctx, oracle):
+    rng = np.random.default_rng(13)
+    iew, jns, n = 100, 100, 2000
+    g = wavy(iew, jns, 8.0, 285.0)
+    x, y = rng_obs(rng, n, iew, jns)
+    ob = (285 + rng.normal(0, 6, n)).astype(np.float32)
+    ob[rng.random(n) < 0.03] -= 30
+    elev = np.zeros(n, np.float32)
+    lt = (rng.integers(0, 24, n) * 100).astype(np.int32)
+    q0 = np.zeros(n, np.int32)
+    qa, *_ = oracle.error_max(ob, x, y, elev, q0, g, 3, 10.0, 1001.0, lt)
+    qa, *_ = oracle.buddy_check(ob, x, y, qa, elev, g, 3, 1001.0, 30.0, 1.0, 8.0)
+    qb = ctx.qc_slab(g, 3, 1001.0, ob, x, y, elev, lt, q0, 10.0, 8.0, 1.0, 30.0)
+    np.testing.assert_array_equal(qa, qb)
+    assert np.count_nonzero(qa) > 0
+
+
+def _compare_time(case_gpu, case_cpu, exact_fields=("t", "slp"), tol_fields=("u", "v", "rh")):
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_slp"):
+        np.testing.assert_array_equal(getattr(case_cpu, nm), getattr(case_gpu, nm), err_msg=nm)
+    for nm in exact_fields:
+        np.testing.assert_array_equal(getattr(case_cpu, nm), getattr(case_gpu, nm), err_msg=nm)
+    for nm in tol_fields:
+        np.testing.assert_allclose(getattr(case_gpu, nm), getattr(case_cpu, nm), rtol=RTOL,
+                                   atol=ATOL, err_msg=nm)
+
+
+def _rh_flag_mismatches(case_gpu, case_cpu):
+    """DEWPOINT goes through LOG (glibc logf vs a correctly rounded device log): flags may differ
+    only at obs whose test margin is within an ulp.  Returns the mismatching (k, r) list."""
+    return np.argwhere(case_gpu.qc_rh != case_cpu.qc_rh)
+
+
+@pytest.mark.parametrize("scale_rh,sfc_mult", [(False, 1.0), (True, 0.8)])
+def test_time_small(ctx, oracle, scale_rh, sfc_mult):
+    base = synth.small_case(iew=60, jns=52, kbu=6, n_sfc=500, n_snd=120, radii=(6, 4, 2),
+                            scale_rh=scale_rh, sfc_mult=sfc_mult)
+    cpu, gpu = base.copy(), base.copy()
+    oracle.qc_time(cpu); ctx.proc_qc(gpu)
+    bad = _rh_flag_mismatches(gpu, cpu)
+    assert len(bad) <= 2, bad
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_slp"):
+        np.testing.assert_array_equal(getattr(cpu, nm), getattr(gpu, nm), err_msg=nm)
+    assert np.count_nonzero(cpu.qc_t) > 0
+    gpu.qc_rh[...] = cpu.qc_rh          # identical ob selection for the OA comparison
+    assert oracle.oa_time(cpu) == ctx.proc_oa(gpu) == 0
+    _compare_time(gpu, cpu)
+
+
+def test_time_level_sharding_is_exact(ctx):
+    """Levels are independent: ranges and variable masks compose to the full run."""
+    base = synth.small_case(iew=50, jns=44, kbu=7, n_sfc=300, n_snd=100, radii=(5, 3))
+    full, parts = base.copy(), base.copy()
+    ctx.proc_qc(full); ctx.proc_oa(full)
+    for k0, k1 in ((3, 7), (0, 1), (1, 3)):
+        ctx.proc_qc(parts, k0, k1)
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp"):
+        np.testing.assert_array_equal(getattr(full, nm), getattr(parts, nm), err_msg=nm)
+    for k0, k1 in ((4, 7), (0, 2), (2, 4)):
+        ctx.proc_oa(parts, k0, k1)
+    for nm in ("t", "u", "v", "rh", "slp"):
+        np.testing.assert_array_equal(getattr(full, nm), getattr(parts, nm), err_msg=nm)
+
+
+def test_time_cfg1(ctx, oracle):
+    """BASELINE.json configs[0]: 100x100, 27 levels, 2k reports, 4 scans + qc1/qc2."""
+    base = synth.make_case(1)
+    cpu, gpu = base.copy(), base.copy()
+    oracle.qc_time(cpu, threads=8); ctx.proc_qc(gpu)
+    bad = _rh_flag_mismatches(gpu, cpu)
+    assert len(bad) <= 3, bad
+    gpu.qc_rh[...] = cpu.qc_rh
+    oracle.reset_stats(); ctx.reset_stats(); ctx.set_counting(True)
+    assert oracle.oa_time(cpu, threads=8) == ctx.proc_oa(gpu) == 0
+    ctx.set_counting(False)
+    _compare_time(gpu, cpu)
+    # the GPU counts exactly the reference's contributing updates where shapes are exact
+    so, sg = oracle.get_stats(), ctx.stats()
+    assert abs(sg["cressman_updates"] - so["cressman_updates"]) <= 1e-4 * so["cressman_updates"]
+    assert sg["cressman_candidates"] < so["cressman_candidates"]
+
+
+def test_empty_and_degenerate_inputs(ctx, oracle):
+    g = wavy(30, 20)
+    e = np.zeros(0, np.float32)
+    np.testing.assert_array_equal(ctx.cressman(e, e, e, g, 3, 5, 12.0), g)
+    z = np.zeros((20, 30), np.float32)
+    np.testing.assert_array_equal(ctx.cressman(e, e, e, g, 3, 5, 12.0, use_first_guess=False), z)
+    q = ctx.qc_slab(g, 3, 500.0, e, e, e, e, np.zeros(0, np.int32), np.zeros(0, np.int32), 10, 8, 1, 30)
+    assert q.size == 0
+    case = synth.small_case(n_sfc=0, n_snd=0)
+    ref = case.copy()
+    ctx.proc_qc(case); ctx.proc_oa(case)
+    np.testing.assert_array_equal(case.t, ref.t)
+    # RH is clamped even without obs (mixing_ratio clamp + clean_rh)
+    assert case.rh.min() >= 0 and case.rh.max() <= 100
+
+
+def test_bad_arguments_are_reported(ctx):
+    from obsgrid_b200._capi import OgError
+    g = wavy(30, 20)
+    with pytest.raises(OgError):
+        ctx.cressman([1.0], [5.0], [5.0], g, 1, 5, 12.0)       # UU without banana winds
+    with pytest.raises(OgError):
+        ctx.cressman([1.0], [5.0], [5.0], g, 9, 5, 12.0)       # unknown variable
