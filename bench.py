@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""Benchmark of the OBSGRID objective-analysis hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W          # this repo (CUDA, C ABI)
+    python bench.py --impl reference ...                   # CPU: the oracle port of the reference
+
+One step = one analysis time of the workload: the proc_qc pass (error_max + buddy check over
+every level x variable slab) followed by the proc_oa pass (multi-scan Cressman over every
+slab).  Metric (BASELINE.json): Cressman grid-point x observation contributing updates per
+second (pairs with d2 < R2, oa_module.F90:553/616); buddy-check obs/s is reported beside it.
+
+  value  : inputs resident in HBM (og_dev_qc_time + og_dev_oa_time), CUDA events on the
+           library's stream, max over ranks; updates per step / step time.
+  e2e    : the same step through og_qc_time_levels + og_oa_time with pinned HOST arrays
+           (H2D of fields + observation table and D2H of analysed fields + flags inside).
+  N > 1  : one process per GPU (torchrun); every rank analyses its own time of the same
+           configuration (times are independent) -> weak scaling, no collective on
+           the data path; torch.distributed only provides the barrier and the max-reduce.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from obsgrid_b200 import synth  # noqa: E402
+from obsgrid_b200._capi import OgTimeDesc  # noqa: E402
+
+METRIC = "cressman_gridpoint_x_obs_updates_per_s"
+UNIT = "updates/s"
+ALGO_FLOP_PER_UPDATE = 11          # circle update = 11 FP32 ops (divide counted once)
+FIELD_NAMES = ("t", "u", "v", "rh", "slp")
+FLAG_NAMES = ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp")
+TABLE_NAMES = ("xob", "yob", "lon", "elev", "ob_u", "ob_v", "ob_t", "ob_rh", "ob_slp")
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_case(args, rank: int):
+    cfg = args.config
+    case = synth.make_case(cfg, time_index=rank)
+    if args.scale_rh:
+        case.oa_params.scale_cressman_rh_decreases = 1
+    return case
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Fortran original
+    cannot be built in this image) on all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import ogoracle as O
+    case0 = build_case(args, 0)
+    threads = os.cpu_count() or 1
+    k_end = min(case0.kbu, args.ref_levels)
+    sample = (f"proc_oa over levels [0,{k_end}) of {case0.kbu} of {case0.label} "
+              f"(all 5 surface slabs + {4 * (k_end - 1)} upper slabs), {threads} pthreads over levels")
+    times, upd = [], 0
+    qc_done = case0.copy()
+    O.qc_time(qc_done, 1, min(case0.kbu, 3), threads=threads)      # realistic flags aloft
+    for it in range(args.warmup + args.steps):
+        c = qc_done.copy()
+        O.reset_stats()
+        t0 = time.perf_counter()
+        O.oa_time(c, 0, k_end, threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            upd = O.get_stats()["cressman_updates"]
+    ms = 1e3 * float(np.mean(times))
+    val = upd / (ms * 1e-3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": case0.label, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, case0):
+    """Oracle timed on the host cores on a bounded sample of the same workload (rank 0, N=1)."""
+    from oracle import ogoracle as O
+    threads = os.cpu_count() or 1
+    k_end = min(case0.kbu, args.ref_levels)
+    c = case0.copy()
+    O.reset_stats()
+    t0 = time.perf_counter()
+    O.oa_time(c, 0, k_end, threads=threads)
+    t_oa = time.perf_counter() - t0
+    st = O.get_stats()
+    # buddy check: upper levels only (5 k obs each); the 50 k-ob surface slabs are N^2 = 2.5e9
+    # pair tests apiece on one thread and would blow the bound
+    c = case0.copy()
+    O.reset_stats()
+    kq0, kq1 = 1, min(case0.kbu, 1 + args.ref_qc_levels)
+    t0 = time.perf_counter()
+    O.qc_time(c, kq0, kq1, run_consistency=False, threads=threads)
+    t_qc = time.perf_counter() - t0
+    sq = O.get_stats()
+    n_obs_qc = 0
+    for k in range(kq0, kq1):
+        for name in ("ob_u", "ob_v", "ob_t", "ob_rh"):
+            n_obs_qc += int(np.count_nonzero(np.abs(getattr(case0, name)[k] + 888888.0) > 1))
+        n_obs_qc += int(np.count_nonzero((np.abs(case0.ob_rh[k] + 888888.0) > 1) &
+                                         (np.abs(case0.ob_t[k] + 888888.0) > 1)))
+    return {"value": st["cressman_updates"] / t_oa, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": (f"proc_oa levels [0,{k_end}) of {case0.kbu} ({t_oa:.1f} s, "
+                       f"{st['cressman_updates']:.3e} updates, {st['cressman_candidates']:.3e} "
+                       f"window iterations); buddy: proc_qc levels [{kq0},{kq1}) "
+                       f"({t_qc:.1f} s, {sq['buddy_pair_tests']:.3e} pair tests)"),
+            "buddy_obs_per_s": n_obs_qc / t_qc, "buddy_pair_tests_per_s": sq["buddy_pair_tests"] / t_qc,
+            "oa_seconds": t_oa, "qc_seconds": t_qc}
+
+
+# ------------------------------------------------------------------------------------------
+def run_gpu(args, rank: int, world: int, local_rank: int):
+    import torch
+    from obsgrid_b200.api import Context
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = Context(local_rank)
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    case = build_case(args, rank)
+    K = case.kbu
+
+    # ---- resident copy: pristine inputs + working set in HBM ---------------------------------
+    pristine, work = {}, {}
+    for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
+        a = getattr(case, nm)
+        pristine[nm] = torch.from_numpy(a).to(dev)
+        work[nm] = pristine[nm].clone() if nm in FIELD_NAMES + FLAG_NAMES else pristine[nm]
+    ddesc = case.desc()
+    for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
+        setattr(ddesc, nm, work[nm].data_ptr())
+
+    def restore_resident():
+        for nm in FIELD_NAMES + FLAG_NAMES:
+            work[nm].copy_(pristine[nm])
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        ctx.dev_proc_qc(ddesc, case.qc_params, 0, K, True)
+        ctx.dev_proc_oa(ddesc, case.oa_params, 0, K)
+
+    # ---- e2e: pinned host arrays through the host-pointer C ABI -----------------------------
+    host0 = {nm: getattr(case, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
+    pin = {}
+    for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
+        t = torch.from_numpy(getattr(case, nm).copy()).pin_memory()
+        pin[nm] = t
+    hcase = case.copy()
+    for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
+        setattr(hcase, nm, pin[nm].numpy())
+
+    def restore_host():
+        for nm in FIELD_NAMES + FLAG_NAMES:
+            np.copyto(getattr(hcase, nm), host0[nm])
+
+    def step_e2e():
+        ctx.proc_qc(hcase)
+        ctx.proc_oa(hcase)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- one counted, untimed pass: updates per step, parity spot check vs the e2e path ------
+    restore_resident()
+    ctx.reset_stats(); ctx.set_counting(True)
+    step_resident(); ctx.sync()
+    st = ctx.stats()
+    ctx.set_counting(False)
+    updates, candidates = st["cressman_updates"], st["cressman_candidates"]
+    buddy_obs, pair_tests = st["buddy_obs"], st["buddy_pair_tests"]
+    restore_host(); step_e2e()
+    same = all(np.array_equal(work[nm].cpu().numpy(), getattr(hcase, nm)) for nm in FIELD_NAMES + FLAG_NAMES)
+    assert same, "resident and host-pointer paths disagree"
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        restore_resident(); step_resident()
+    ctx.sync()
+
+    # ---- timed: resident -------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ctx.set_timing(True)
+    ctx.reset_stats()
+    barrier()
+    for i in range(args.steps):
+        restore_resident()
+        ev[i][0].record(lib_stream)
+        ctx.dev_proc_qc(ddesc, case.qc_params, 0, K, True)
+        ev[i][1].record(lib_stream)
+        ctx.dev_proc_oa(ddesc, case.oa_params, 0, K)
+        ev[i][2].record(lib_stream)
+    ctx.sync()
+    barrier()
+    launches = ctx.stats()["kernel_launches"]
+    scan_ms, buddy_ms = ctx.kernel_ms()
+    ctx.set_timing(False)
+    qc_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / args.steps
+    oa_ms = sum(b.elapsed_time(c) for _, b, c in ev) / args.steps
+    step_ms = qc_ms + oa_ms
+
+    # ---- timed: e2e --------------------------------------------------------------------------------
+    for _ in range(2):
+        restore_host(); step_e2e()
+    ctx.reset_stats()
+    e2e_t = []
+    barrier()
+    for i in range(args.steps):
+        restore_host()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record(lib_stream)
+        step_e2e()
+        b.record(lib_stream)
+        ctx.sync()
+        wall = (time.perf_counter() - t0) * 1e3
+        e2e_t.append(max(a.elapsed_time(b), wall))   # host-side staging counts as well
+    barrier()
+    clocks = sampler.stop()
+    st_e = ctx.stats()
+    e2e_ms = float(np.mean(e2e_t))
+
+    # ---- reduce over ranks: max time, summed work ------------------------------------------------
+    vec = torch.tensor([step_ms, e2e_ms, qc_ms, oa_ms, scan_ms / args.steps], device=dev, dtype=torch.float64)
+    tot = torch.tensor([updates, buddy_obs, pair_tests, candidates, launches], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(vec, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    step_ms, e2e_ms, qc_ms, oa_ms, scan_ms_step = [float(x) for x in vec.tolist()]
+    g_updates, g_bobs, g_pairs, g_cands, g_launch = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        fp32_peak_ops = ctx.fp32_peak()                     # lane-instructions/s, FADD/FMUL no FMA
+        n_scan_launch = sum(1 for r in case.oa_params.radius_influence if r >= 0)
+        per_launch_ms = scan_ms_step / max(n_scan_launch, 1)
+        flops_per_launch = ALGO_FLOP_PER_UPDATE * updates / max(n_scan_launch, 1)
+        achieved_tf = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+        n_oa_slabs = 5 + 4 * (K - 1)
+        hbm_bytes_launch = n_oa_slabs * 8.0 * case.iew * case.jns
+        roofline = {
+            "kernel": "cressman_scan_kernel", "bound": "fp32",
+            "achieved": achieved_tf, "peak": fp32_peak_ops / 1e12, "unit": "TFLOP/s",
+            "frac": achieved_tf / (fp32_peak_ops / 1e12) if fp32_peak_ops else None,
+            "peak_source": "measured in this run: og_fp32_peak (FMUL+FADD chains, no FMA: the "
+                           "parity build has -fmad=false, 1 lane-instruction = 1 FLOP)",
+            "algorithmic_flop_per_update": ALGO_FLOP_PER_UPDATE,
+            "avg_launch_ms": per_launch_ms, "launches_per_step": n_scan_launch,
+            "traffic": None,
+            "hbm": {"achieved": hbm_bytes_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0,
+                    "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": hbm_bytes_launch},
+            "scan_kernel_share_of_oa": scan_ms_step / oa_ms if oa_ms > 0 else None,
+        }
+        roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / hbm_peak
+        cpu = cpu_baseline(args, case) if (world == 1 and not args.no_cpu) else None
+        line = {
+            "metric": METRIC, "value": g_updates / (step_ms * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": case.label, "times_per_step": world,
+                       "grid": [case.iew, case.jns], "levels": K, "reports": case.nrep,
+                       "scans": [int(r) for r in case.oa_params.radius_influence if r >= 0],
+                       "scale_cressman_rh_decreases": bool(case.oa_params.scale_cressman_rh_decreases),
+                       "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
+                             "pristine copy before every step",
+                       "parallelism": f"{world} x independent analysis time"},
+            "e2e": {"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
+                    "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps},
+            "gpu_launches": int(g_launch),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "breakdown": {"qc_ms": qc_ms, "oa_ms": oa_ms, "cressman_scan_kernels_ms": scan_ms_step,
+                          "buddy_allpairs_kernel_ms": buddy_ms / args.steps,
+                          "cressman_updates_per_step": g_updates, "cressman_candidates_per_step": g_cands,
+                          "cressman_updates_per_s_oa_only": g_updates / (oa_ms * 1e-3),
+                          "buddy_obs_per_step": g_bobs, "buddy_pair_tests_per_step": g_pairs,
+                          "buddy_obs_per_s": g_bobs / (qc_ms * 1e-3),
+                          "buddy_pair_tests_per_s": g_pairs / (qc_ms * 1e-3)},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs[config-1]")
+    ap.add_argument("--scale-rh", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-levels", type=int, default=64,
+                    help="levels in the CPU sample of proc_oa (bounds the CPU time)")
+    ap.add_argument("--ref-qc-levels", type=int, default=8)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -207,7 +207,7 @@ def first_guess(iew: int, jns: int, pressure: np.ndarray, phase: float = 0.0):
     X = i / iew; Y = j / jns
     t = np.empty((kbu, iew, jns), np.float32); u = np.empty_like(t); v = np.empty_like(t)
     rh = np.empty_like(t)
-    amp = 0.12 * jns; kw = 2 * np.pi * 1.5 / iew
+    amp = 0.09 * jns; kw = 2 * np.pi * 3.0 / iew
     yc = jns / 2.0 + amp * np.sin(kw * i + phase)
     dyc = amp * kw * np.cos(kw * i + phase)
     width = 0.11 * jns

@@ -699,7 +699,7 @@ typedef struct {
 } qc_level_job;
 
 /* proc_qc.F90:247-406 for one level kp (0-based k). */
-static void qc_level(const og_time_desc* d, const og_qc_params* p, int k)
+static void qc_level(const og_time_desc* d, const og_qc_params* p, int k, int job_mask)
 {
     const int iew = d->iew, jns = d->jns, nrep = d->nrep;
     const size_t npts = (size_t)iew * jns;
@@ -722,6 +722,7 @@ static void qc_level(const og_time_desc* d, const og_qc_params* p, int k)
         if (ivar == 6) continue;                    /* qc_psfc = .FALSE. (proc_namelist.F90:73) */
         if (ivar == 7 && !p->qc_dewpoint) continue;
         if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
+        if (job_mask && !(job_mask & (1 << (ivar - 1)))) continue;
         float error_difference = 0.f, buddy_difference = 0.f;
         const float* obv = NULL; int* qcv = NULL;
         switch (ivar) {
@@ -801,18 +802,20 @@ static void qc_consistency(const og_time_desc* d, int k_begin, int k_end)
 int ogo_qc_time(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
                 int run_consistency)
 {
-    for (int k = k_begin; k < k_end; ++k) qc_level(d, p, k);
+    for (int k = k_begin; k < k_end; ++k) qc_level(d, p, k, 0);
     if (run_consistency) qc_consistency(d, k_begin, k_end);
     return OG_OK;
 }
 
-/* proc_oa.F90:356-849 for one level. */
-static int oa_level(const og_time_desc* d, const og_oa_params* p, int k)
+/* proc_oa.F90:390-847 for one (level, variable) slab.  u_banana/v_banana are the
+ * pre-analysis winds of the level in (iew,jns) order (proc_oa.F90:376-386). */
+static int oa_slab_job(const og_time_desc* d, const og_oa_params* p, int k, int ivar,
+                       const float* u_banana, const float* v_banana)
 {
     const int iew = d->iew, jns = d->jns, nrep = d->nrep;
     const size_t npts = (size_t)iew * jns;
-    float* u_banana = (float*)malloc(sizeof(float) * npts);
-    float* v_banana = (float*)malloc(sizeof(float) * npts);
+    if (ivar == 5 && k > 0) return OG_OK;
+    if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) return OG_OK;
     float* dum2d = (float*)malloc(sizeof(float) * npts);
     size_t nn = (size_t)(nrep > 0 ? nrep : 1);
     float* val = (float*)malloc(sizeof(float) * nn);
@@ -822,43 +825,50 @@ static int oa_level(const og_time_desc* d, const og_oa_params* p, int k)
     const size_t off = (size_t)k * nrep;
     const int qc_max = OG_FAILS_ERROR_MAX < OG_FAILS_BUDDY_CHECK ? OG_FAILS_ERROR_MAX
                                                                  : OG_FAILS_BUDDY_CHECK;
-    int rc = OG_OK;
-
-    slab_get(d->u, iew, jns, k, u_banana); /* :376-386 (pre-analysis winds of this level) */
-    slab_get(d->v, iew, jns, k, v_banana);
-
-    for (int ivar = 1; ivar <= 5; ++ivar) { /* PSFC (6) needs oa_psfc: off */
-        if (ivar == 5 && k > 0) continue;
-        if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
-        int passes; float scale = (ivar == 5) ? 100.f : 1.f;
-        const int psfc[5] = {p->smooth_sfc_wind, p->smooth_sfc_wind, p->smooth_sfc_temp,
-                             p->smooth_sfc_rh, p->smooth_sfc_slp};
-        const int pup[5] = {p->smooth_upper_wind, p->smooth_upper_wind, p->smooth_upper_temp,
-                            p->smooth_upper_rh, 0};
-        passes = (k == 0) ? psfc[ivar - 1] : pup[ivar - 1];
-        float* f3 = NULL; const float* obv = NULL; const int* qcv = NULL;
-        switch (ivar) {
-        case 1: f3 = d->u; obv = d->ob_u + off; qcv = d->qc_u + off; break;
-        case 2: f3 = d->v; obv = d->ob_v + off; qcv = d->qc_v + off; break;
-        case 3: f3 = d->t; obv = d->ob_t + off; qcv = d->qc_t + off; break;
-        case 4: f3 = d->rh; obv = d->ob_rh + off; qcv = d->qc_rh + off; break;
-        case 5: f3 = d->slp; obv = d->ob_slp; qcv = d->qc_slp; break;
-        }
-        int n = 0; /* 'use' (proc_ob_access.F90:270-355) */
-        for (int r = 0; r < nrep; ++r) {
-            if (!(not_missing(obv[r]) && qcv[r] < qc_max)) continue;
-            if (!in_domain(d->xob[r], d->yob[r], iew, jns)) continue;
-            val[n] = obv[r]; x[n] = d->xob[r]; y[n] = d->yob[r]; ++n;
-        }
-        slab_get(f3, iew, jns, ivar == 5 ? 0 : k, dum2d);
-        int r1 = ogo_oa_slab(dum2d, iew, jns, ivar, pk, val, x, y, n, scale, p->radius_influence,
-                             p->radius_influence_sfc_mult, d->dx_km, u_banana, v_banana, passes,
-                             p->smooth_type, p->use_first_guess,
-                             p->scale_cressman_rh_decreases, NULL);
-        if (r1 != OG_OK) rc = r1;
-        slab_put(f3, iew, jns, ivar == 5 ? 0 : k, dum2d);
+    int passes; float scale = (ivar == 5) ? 100.f : 1.f;
+    const int psfc[5] = {p->smooth_sfc_wind, p->smooth_sfc_wind, p->smooth_sfc_temp,
+                         p->smooth_sfc_rh, p->smooth_sfc_slp};
+    const int pup[5] = {p->smooth_upper_wind, p->smooth_upper_wind, p->smooth_upper_temp,
+                        p->smooth_upper_rh, 0};
+    passes = (k == 0) ? psfc[ivar - 1] : pup[ivar - 1];
+    float* f3 = NULL; const float* obv = NULL; const int* qcv = NULL;
+    switch (ivar) {
+    case 1: f3 = d->u; obv = d->ob_u + off; qcv = d->qc_u + off; break;
+    case 2: f3 = d->v; obv = d->ob_v + off; qcv = d->qc_v + off; break;
+    case 3: f3 = d->t; obv = d->ob_t + off; qcv = d->qc_t + off; break;
+    case 4: f3 = d->rh; obv = d->ob_rh + off; qcv = d->qc_rh + off; break;
+    default: f3 = d->slp; obv = d->ob_slp; qcv = d->qc_slp; break;
     }
-    free(u_banana); free(v_banana); free(dum2d); free(val); free(x); free(y);
+    int n = 0; /* 'use' (proc_ob_access.F90:270-355) */
+    for (int r = 0; r < nrep; ++r) {
+        if (!(not_missing(obv[r]) && qcv[r] < qc_max)) continue;
+        if (!in_domain(d->xob[r], d->yob[r], iew, jns)) continue;
+        val[n] = obv[r]; x[n] = d->xob[r]; y[n] = d->yob[r]; ++n;
+    }
+    slab_get(f3, iew, jns, ivar == 5 ? 0 : k, dum2d);
+    int rc = ogo_oa_slab(dum2d, iew, jns, ivar, pk, val, x, y, n, scale, p->radius_influence,
+                         p->radius_influence_sfc_mult, d->dx_km, u_banana, v_banana, passes,
+                         p->smooth_type, p->use_first_guess, p->scale_cressman_rh_decreases,
+                         NULL);
+    slab_put(f3, iew, jns, ivar == 5 ? 0 : k, dum2d);
+    free(dum2d); free(val); free(x); free(y);
+    return rc;
+}
+
+/* proc_oa.F90:356-849 for one level: variables in the reference's order. */
+static int oa_level(const og_time_desc* d, const og_oa_params* p, int k)
+{
+    const size_t npts = (size_t)d->iew * d->jns;
+    float* u_banana = (float*)malloc(sizeof(float) * npts);
+    float* v_banana = (float*)malloc(sizeof(float) * npts);
+    int rc = OG_OK;
+    slab_get(d->u, d->iew, d->jns, k, u_banana); /* :376-386 (pre-analysis winds) */
+    slab_get(d->v, d->iew, d->jns, k, v_banana);
+    for (int ivar = 1; ivar <= 5; ++ivar) { /* PSFC (6) needs oa_psfc: off */
+        int r1 = oa_slab_job(d, p, k, ivar, u_banana, v_banana);
+        if (r1 != OG_OK) rc = r1;
+    }
+    free(u_banana); free(v_banana);
     return rc;
 }
 
@@ -885,20 +895,28 @@ int ogo_oa_time(const og_time_desc* d, const og_oa_params* p, int k_begin, int k
     return rc;
 }
 
-/* ---- pthread fan-out over levels (levels are independent) -------------- */
+/* ---- pthread fan-out -------------------------------------------------------------------
+ * OA: one job per (level, variable) slab -- slabs are independent once the pre-analysis winds
+ * of every level have been snapshotted; QC: one job per level (DEWPOINT reads the
+ * RH flags of its own level). */
 typedef struct {
     const og_time_desc* d; const og_oa_params* po; const og_qc_params* pq;
     int k_begin, k_end; int* next; int rc;
+    const float* ub_all; const float* vb_all;   /* [k_end-k_begin][jns][iew] */
 } mt_job;
 
 static void* oa_worker(void* arg)
 {
     mt_job* j = (mt_job*)arg;
+    const size_t npts = (size_t)j->d->iew * j->d->jns;
+    const int nlev = j->k_end - j->k_begin;
     for (;;) {
-        int k = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
-        if (k >= j->k_end) break;
+        int q = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+        if (q >= nlev * 5) break;
+        int k = j->k_begin + q / 5, ivar = 1 + q % 5;   /* surface (largest) slabs first */
         if (j->po->surface_only && k > 0) continue;
-        int r = oa_level(j->d, j->po, k);
+        int r = oa_slab_job(j->d, j->po, k, ivar, j->ub_all + npts * (size_t)(k - j->k_begin),
+                            j->vb_all + npts * (size_t)(k - j->k_begin));
         if (r != OG_OK) j->rc = r;
     }
     return NULL;
@@ -906,10 +924,14 @@ static void* oa_worker(void* arg)
 static void* qc_worker(void* arg)
 {
     mt_job* j = (mt_job*)arg;
+    /* per level five independent jobs: UU, VV, TT, PMSL, and RH followed by DEWPOINT (which
+     * reads the RH flags, ob_access_module.F90:466-487) */
+    static const int masks[5] = {1 << 0, 1 << 1, 1 << 2, 1 << 4, (1 << 3) | (1 << 6)};
+    const int nlev = j->k_end - j->k_begin;
     for (;;) {
-        int k = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
-        if (k >= j->k_end) break;
-        qc_level(j->d, j->pq, k);
+        int q = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+        if (q >= nlev * 5) break;
+        qc_level(j->d, j->pq, j->k_begin + q / 5, masks[q % 5]);
     }
     return NULL;
 }
@@ -919,15 +941,24 @@ int ogo_oa_time_mt(const og_time_desc* d, const og_oa_params* p, int k_begin, in
 {
     if (threads <= 1) return ogo_oa_time(d, p, k_begin, k_end);
     if (p->clamp_fg_rh) clamp_fg_rh(d, k_begin, k_end);
-    int next = k_begin, rc = OG_OK;
+    const size_t npts = (size_t)d->iew * d->jns;
+    const int nlev = k_end - k_begin;
+    if (nlev <= 0) return OG_OK;
+    float* ub = (float*)malloc(sizeof(float) * npts * (size_t)nlev);
+    float* vb = (float*)malloc(sizeof(float) * npts * (size_t)nlev);
+    for (int k = k_begin; k < k_end; ++k) {
+        slab_get(d->u, d->iew, d->jns, k, ub + npts * (size_t)(k - k_begin));
+        slab_get(d->v, d->iew, d->jns, k, vb + npts * (size_t)(k - k_begin));
+    }
+    int next = 0, rc = OG_OK;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
     mt_job* jobs = (mt_job*)malloc(sizeof(mt_job) * (size_t)threads);
     for (int t = 0; t < threads; ++t) {
-        jobs[t] = (mt_job){d, p, NULL, k_begin, k_end, &next, OG_OK};
+        jobs[t] = (mt_job){d, p, NULL, k_begin, k_end, &next, OG_OK, ub, vb};
         pthread_create(&th[t], NULL, oa_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; ++t) { pthread_join(th[t], NULL); if (jobs[t].rc) rc = jobs[t].rc; }
-    free(th); free(jobs);
+    free(th); free(jobs); free(ub); free(vb);
     return rc;
 }
 
@@ -935,11 +966,11 @@ int ogo_qc_time_mt(const og_time_desc* d, const og_qc_params* p, int k_begin, in
                    int run_consistency, int threads)
 {
     if (threads <= 1) return ogo_qc_time(d, p, k_begin, k_end, run_consistency);
-    int next = k_begin;
+    int next = 0;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
     mt_job* jobs = (mt_job*)malloc(sizeof(mt_job) * (size_t)threads);
     for (int t = 0; t < threads; ++t) {
-        jobs[t] = (mt_job){d, NULL, p, k_begin, k_end, &next, OG_OK};
+        jobs[t] = (mt_job){d, NULL, p, k_begin, k_end, &next, OG_OK, NULL, NULL};
         pthread_create(&th[t], NULL, qc_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
