@@ -103,6 +103,16 @@ __global__ void div_selftest_kernel(int n, unsigned seed, int rmax, unsigned lon
     float a = fsub(R2, d2), b = fadd(R2, d2);
     if (__float_as_uint(fdiv_fast_exact(a, b)) != __float_as_uint(fdiv(a, b)))
         atomicAdd(bad, 1ULL);
+    // the ellipse's divisions: numerator of either sign over ~14 decades (incl. exact zero),
+    // divisor = speed_ob (>= vcrit >= 5 m/s) or elongation (>= 1), reciprocal computed once
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    float mag = exp2f(-24.f + 48.f * ((float)(s >> 8) * (1.0f / 16777216.0f)));
+    s ^= s << 13; s ^= s >> 17; s ^= s << 5;
+    float a2 = ((s & 1u) ? -mag : mag) * ((s & 14u) ? 1.f : 0.f);
+    float b2 = 1.0f + 400.f * ((float)(s >> 8) * (1.0f / 16777216.0f));
+    // compared by value: -0/b comes back +0 from the residual step, and the callers square it
+    if (!(fdiv_with_rcp(a2, b2, refined_rcp(b2)) == fdiv(a2, b2)))
+        atomicAdd(bad, 1ULL);
 }
 
 int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches)
