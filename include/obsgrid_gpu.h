@@ -102,6 +102,8 @@ typedef struct og_stats {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     int64_t buddy_fixpoint_iters;
+    int64_t buddy_pairs_examined;   /* pair tests the binned kernel actually ran; buddy_pair_tests
+                                       is the reference's N*(N-1) for the same slabs */
 } og_stats;
 int  og_get_stats(og_ctx* ctx, og_stats* out);
 int  og_reset_stats(og_ctx* ctx);

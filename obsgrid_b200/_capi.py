@@ -32,7 +32,8 @@ ip = C.POINTER(C.c_int)
 class OgStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "kernel_launches", "cressman_updates", "cressman_candidates", "buddy_pair_tests",
-        "buddy_obs", "h2d_bytes", "d2h_bytes", "buddy_fixpoint_iters")]
+        "buddy_obs", "h2d_bytes", "d2h_bytes", "buddy_fixpoint_iters",
+        "buddy_pairs_examined")]
 
 
 class OgQcParams(C.Structure):

@@ -1,0 +1,221 @@
+// og_bin.cu -- stable spatial binning of observations on the device.
+//
+// Both hot loops of the reference sum over observations in ascending slab index
+// (oa_module.F90:116, qc2_module.F90:230,250-252) and the results have to be bit-identical,
+// so every spatial candidate list handed to a kernel must keep that order.  Given one
+// bounding box per ob (1-based inclusive grid coordinates) and a cell size per slab, this
+// builds, for every cell of every slab of a batch, the list of obs whose box touches the cell:
+//   count (atomics) -> exclusive prefix over all cells of the batch -> fill (atomics, any
+//   order) -> per-cell sort by ob index (shared-memory rank / bitonic sort).
+#include "og_ctx.h"
+#include "og_device.cuh"
+
+#include <algorithm>
+#include <string>
+
+namespace og {
+
+namespace {
+
+constexpr int BIN_THREADS = 256;
+constexpr int SORT_CAP = 8192;       // cell lists up to this length are sorted in shared memory
+
+struct BinDev {
+    const BinSlab* slabs;
+    const short4* box;
+    int* cell_count;
+    int* cell_cursor;
+    int* cell_start;
+    int* cell_list;
+    int* cell_sorted;
+};
+
+template <class F>
+__device__ __forceinline__ void for_each_cell(const BinSlab& S, short4 b, F f)
+{
+    if (b.x > b.y || b.z > b.w) return;
+    const int cx0 = max((b.x - 1) / S.cell, 0), cx1 = min((b.y - 1) / S.cell, S.ncx - 1);
+    const int cy0 = max((b.z - 1) / S.cell, 0), cy1 = min((b.w - 1) / S.cell, S.ncy - 1);
+    for (int cy = cy0; cy <= cy1; ++cy)
+        for (int cx = cx0; cx <= cx1; ++cx) f(S.cell_off + cy * S.ncx + cx);
+}
+
+__global__ void __launch_bounds__(256) bin_count_kernel(BinDev A)
+{
+    const BinSlab S = A.slabs[blockIdx.y];
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= S.n) return;
+    for_each_cell(S, A.box[S.ob_off + li], [&](int c) { atomicAdd(&A.cell_count[c], 1); });
+}
+
+// Exclusive scan of all cell counts of the batch: one block, coalesced tiles of 1024.
+__global__ void __launch_bounds__(1024) cell_prefix_kernel(const int* __restrict__ cnt,
+                                                           int* __restrict__ start, int n,
+                                                           int* __restrict__ total)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < n) ? cnt[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;    // exclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int excl = carry + s_warp[warp] + inc - v;
+        if (i < n) start[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) { start[n] = s_carry; *total = s_carry; }
+}
+
+__global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
+{
+    const BinSlab S = A.slabs[blockIdx.y];
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= S.n) return;
+    for_each_cell(S, A.box[S.ob_off + li], [&](int c) {
+        const int pos = atomicAdd(&A.cell_cursor[c], 1);
+        A.cell_list[A.cell_start[c] + pos] = li;
+    });
+}
+
+// Every cell list into ascending ob index -- the reference's summation order.
+__global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A, int ncells)
+{
+    const int c = blockIdx.x;
+    if (c >= ncells) return;
+    const int L = A.cell_count[c];
+    if (L == 0) return;
+    const int* __restrict__ in = A.cell_list + A.cell_start[c];
+    int* __restrict__ out = A.cell_sorted + A.cell_start[c];
+    const int tid = threadIdx.x;
+    extern __shared__ int s_key[];
+    if (L <= SORT_CAP) {
+        int P = 1;
+        while (P < L) P <<= 1;
+        for (int t = tid; t < P; t += BIN_THREADS) s_key[t] = (t < L) ? in[t] : 0x7fffffff;
+        __syncthreads();
+        if (L <= 2 * BIN_THREADS) {
+            // rank by counting (keys are distinct)
+            for (int t = tid; t < L; t += BIN_THREADS) {
+                const int key = s_key[t];
+                int rank = 0;
+                for (int j = 0; j < L; ++j) rank += (s_key[j] < key) ? 1 : 0;
+                out[rank] = key;
+            }
+            return;
+        }
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (P >> 1); t += BIN_THREADS) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int hi = lo | j;
+                    const bool up = ((lo & k) == 0);
+                    const int a = s_key[lo], b = s_key[hi];
+                    if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int t = tid; t < L; t += BIN_THREADS) out[t] = s_key[t];
+    } else {
+        // longer than the shared-memory sorter: rank by counting against shared-memory tiles
+        for (int t0 = 0; t0 < L; t0 += BIN_THREADS) {
+            const int t = t0 + tid;
+            const int key = (t < L) ? in[t] : 0x7fffffff;
+            int rank = 0;
+            for (int b0 = 0; b0 < L; b0 += SORT_CAP) {
+                const int bn = min(SORT_CAP, L - b0);
+                __syncthreads();
+                for (int q = tid; q < bn; q += BIN_THREADS) s_key[q] = in[b0 + q];
+                __syncthreads();
+                for (int j = 0; j < bn; ++j) rank += (s_key[j] < key) ? 1 : 0;
+            }
+            if (t < L) out[rank] = key;
+        }
+    }
+}
+
+} // namespace
+
+int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, const short4* d_box,
+              bool sorted, BinLists* out)
+{
+    const int ns = (int)slabs.size();
+    cudaStream_t st = ctx->stream;
+    const std::string t(tag);
+    long long ncells = 0;
+    int max_n = 0;
+    for (const BinSlab& s : slabs) {
+        if (s.cell_off != (int)ncells) { set_error("bin_build: cell offsets are not cumulative"); return OG_ERR_INVALID; }
+        ncells += (long long)s.ncx * s.ncy;
+        max_n = std::max(max_n, s.n);
+    }
+    if (ncells > 0x7fff0000LL) { set_error("batch too large: slabs x cells overflows"); return OG_ERR_INVALID; }
+    BinDev A{};
+    BinSlab* d_slabs = nullptr;
+    OG_TRY(ctx->reserve_t((t + ".slabs").c_str(), (size_t)std::max(ns, 1), &d_slabs));
+    OG_TRY(ctx->reserve_t((t + ".count").c_str(), (size_t)ncells + 1, &A.cell_count));
+    OG_TRY(ctx->reserve_t((t + ".cursor").c_str(), (size_t)ncells + 1, &A.cell_cursor));
+    OG_TRY(ctx->reserve_t((t + ".start").c_str(), (size_t)ncells + 1, &A.cell_start));
+    A.slabs = d_slabs; A.box = d_box;
+    OG_CUDA(cudaMemsetAsync(A.cell_count, 0, sizeof(int) * ((size_t)ncells + 1), st));
+    OG_CUDA(cudaMemsetAsync(A.cell_start, 0, sizeof(int) * ((size_t)ncells + 1), st));
+    int list_total = 0;
+    if (ns > 0 && max_n > 0 && ncells > 0) {
+        OG_CUDA(cudaMemcpyAsync(d_slabs, slabs.data(), sizeof(BinSlab) * ns, cudaMemcpyHostToDevice, st));
+        OG_CUDA(cudaMemsetAsync(A.cell_cursor, 0, sizeof(int) * ((size_t)ncells + 1), st));
+        dim3 g_ob((max_n + 255) / 256, ns);
+        bin_count_kernel<<<g_ob, 256, 0, st>>>(A);
+        cell_prefix_kernel<<<1, 1024, 0, st>>>(A.cell_count, A.cell_start, (int)ncells, ctx->d_flag);
+        ctx->count_launch(2);
+        OG_CUDA(cudaMemcpyAsync(ctx->h_pinned_small, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OG_CUDA(cudaStreamSynchronize(st));
+        list_total = ctx->h_pinned_small[0];
+        if (list_total < 0) { set_error("cell lists overflow 2^31 entries; split the batch"); return OG_ERR_INVALID; }
+    }
+    const size_t nlist = (size_t)std::max(list_total, 1);
+    OG_TRY(ctx->reserve_t((t + ".list").c_str(), nlist, &A.cell_list));
+    A.cell_sorted = A.cell_list;
+    if (sorted) OG_TRY(ctx->reserve_t((t + ".sorted").c_str(), nlist, &A.cell_sorted));
+    if (list_total > 0) {
+        dim3 g_ob((max_n + 255) / 256, ns);
+        bin_fill_kernel<<<g_ob, 256, 0, st>>>(A);
+        ctx->count_launch();
+        if (sorted) {
+            cell_sort_kernel<<<(unsigned)ncells, BIN_THREADS, SORT_CAP * sizeof(int), st>>>(A, (int)ncells);
+            ctx->count_launch();
+        }
+        OG_CUDA(cudaGetLastError());
+    }
+    out->slabs = d_slabs;
+    out->cell_count = A.cell_count;
+    out->cell_start = A.cell_start;
+    out->cell_list = A.cell_sorted;
+    out->total_cells = (int)ncells;
+    out->list_total = list_total;
+    return OG_OK;
+}
+
+} // namespace og

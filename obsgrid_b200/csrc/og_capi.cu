@@ -68,11 +68,12 @@ extern "C" int og_finalize(og_ctx* c)
 
 static int fetch_counters(og_ctx* c)
 {
-    unsigned long long h[2];
+    unsigned long long h[4];
     OG_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     OG_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.cressman_updates = (int64_t)h[0];
     c->stats.cressman_candidates = (int64_t)h[1];
+    c->stats.buddy_pairs_examined = (int64_t)h[3];
     return OG_OK;
 }
 
@@ -87,7 +88,7 @@ extern "C" int og_reset_stats(og_ctx* c)
 {
     if (!c) return OG_ERR_INVALID;
     c->stats = og_stats{};
-    OG_CUDA(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    OG_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
     return OG_OK;
 }
 extern "C" int og_set_counting(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->counting = on; return OG_OK; }

@@ -141,6 +141,26 @@ struct QcBatch {
 int qc_run_batch(og_ctx* ctx, QcBatch& b);
 int local_time_device(og_ctx* ctx, int time_hhmm, const float* lon, int n, int* out);
 
+// ---- stable binning (og_bin.cu) --------------------------------------------------------
+struct BinSlab {
+    int n, ob_off;      // obs of the slab in the batch-wide per-ob arrays
+    int cell;           // cell edge in grid points
+    int ncx, ncy;       // cells per row / column
+    int cell_off;       // first cell of the slab in the per-cell arrays (cumulative)
+};
+struct BinLists {
+    const BinSlab* slabs = nullptr;   // device copy of the slab table
+    int* cell_count = nullptr;        // [total_cells+1] obs whose box touches the cell
+    int* cell_start = nullptr;        // [total_cells+1] exclusive prefix over the whole batch
+    int* cell_list = nullptr;         // [list_total] local ob indices; ascending when sorted
+    int total_cells = 0;
+    int list_total = 0;
+};
+// box: device, one 1-based inclusive {i0,i1,j0,j1} per ob (i0>i1 = not binned).  Synchronises
+// the stream once (the list size comes back to the host to size the lists).
+int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, const short4* d_box,
+              bool sorted, BinLists* out);
+
 // ---- misc (og_misc.cu) ---------------------------------------------------------------
 const char* last_error();
 int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches);

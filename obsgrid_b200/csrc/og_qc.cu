@@ -4,9 +4,11 @@
 // src/qc0_module.F90:9-76 (flag arithmetic), :236-267 (local).
 //
 // The buddy means are FP32 sums over neighbours in ascending slab index; QC flags have to be
-// bit-identical, so that order is kept: one thread owns one observation and walks the other
-// observations of the slab in index order through shared-memory tiles (all-pairs, the
-// reference's N^2, at FP32-pipe rate).  sqrt(dx*dx+dy*dy)*dx_km compared with the range and
+// bit-identical, so that order is kept: one thread owns one observation and walks, in index
+// order through shared-memory tiles, the observations that can be within range of its cell --
+// the slab is cut into cells one buddy range wide and og_bin.cu hands every cell the
+// index-ordered list of the obs within range of it, so the reference's N^2 pair loop shrinks
+// to N x (obs within ~3 ranges).  sqrt(dx*dx+dy*dy)*dx_km compared with the range and
 // with 0.1 km is replaced by two thresholds on dx*dx+dy*dy found on the host by bisection
 // over the float ordering with the very same operations, which is exact because
 // sqrtf and the multiply are monotone.
@@ -32,6 +34,8 @@ struct QcSlabDev {
     int n, ob_off, var;
     float pressure, max_error, max_buddy;
     float t_lo, t_hi;   // buddy iff t_lo <= dx*dx+dy*dy <= t_hi
+    float reach;        // >= the largest |dx| or |dy| (grid cells) a buddy pair can have
+    int ncx, ncy, cell_off;   // cells of the slab (edge ~ reach), first cell in the per-cell arrays
 };
 
 struct QcDev {
@@ -56,6 +60,11 @@ struct QcDev {
     int* kob;            // buddy_num_final
     float* err;          // buddy err
     int* changed;
+    short4* home_box;    // the grid cell an ob sits in
+    short4* range_box;   // every grid cell within `reach` of it
+    const int* home_count; const int* home_start; const int* home_list;      // targets of a cell
+    const int* range_count; const int* range_start; const int* range_list;  // its candidates
+    unsigned long long* pairs_examined;
     // diagnostics (nullable)
     float* d_aob; float* d_err_max; float* d_thr_max; float* d_err_buddy; float* d_difmax;
     int* d_bnf;
@@ -135,37 +144,63 @@ __global__ void __launch_bounds__(256) qc_prep_kernel(QcDev A)
     difmax = fmul(difmax, A.buddy_weight); // :193
     A.q4[gi] = make_float4(x, y, err, difmax);
     A.mod_in[gi] = 0;
+    if (A.home_box) {
+        // the same monotone clamp on both boxes keeps "within reach" => "lists meet" for any x, y
+        const float fi = (float)A.iew, fj = (float)A.jns;
+        const int hx = (int)fminf(fmaxf(floorf(x), 1.f), fi), hy = (int)fminf(fmaxf(floorf(y), 1.f), fj);
+        A.home_box[gi] = make_short4((short)hx, (short)hx, (short)hy, (short)hy);
+        const float r = S.reach;
+        A.range_box[gi] = make_short4((short)fminf(fmaxf(floorf(x - r) - 1.f, 1.f), fi),
+                                      (short)fminf(fmaxf(ceilf(x + r) + 1.f, 1.f), fi),
+                                      (short)fminf(fmaxf(floorf(y - r) - 1.f, 1.f), fj),
+                                      (short)fminf(fmaxf(ceilf(y + r) + 1.f, 1.f), fj));
+    }
 }
 
 // station_loop_2/3, first half (qc2_module.F90:223-256): buddy count and index-ordered sum.
+// One CTA per cell: its targets are the obs sitting in the cell, its candidates the
+// index-ordered list of the obs within reach of the cell.
 constexpr int BUDDY_THREADS = 256;
-__global__ void __launch_bounds__(BUDDY_THREADS) buddy_pass1_kernel(QcDev A)
+constexpr int BP1_THREADS = 128;
+constexpr int BP1_CHUNK = 512;
+__global__ void __launch_bounds__(BP1_THREADS) buddy_pass1_kernel(QcDev A)
 {
     const QcSlabDev& S = A.slabs[blockIdx.y];
-    if ((int)(blockIdx.x * BUDDY_THREADS) >= S.n) return;
-    const int li = blockIdx.x * BUDDY_THREADS + threadIdx.x;
-    const bool valid = li < S.n;
-    const float4 me = valid ? A.q4[S.ob_off + li] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
+    if ((int)blockIdx.x >= S.ncx * S.ncy) return;
+    const int c = S.cell_off + blockIdx.x;
+    const int T = A.home_count[c];
+    if (T == 0) return;
+    const int L = A.range_count[c];
+    const int* __restrict__ tl = A.home_list + A.home_start[c];
+    const int* __restrict__ cl = A.range_list + A.range_start[c];
     const float tlo = S.t_lo, thi = S.t_hi;
-    __shared__ float4 tile[BUDDY_THREADS];
-    int cnt = 0;
-    float sum = 0.f;
-    for (int base = 0; base < S.n; base += BUDDY_THREADS) {
-        const int k = base + threadIdx.x;
-        tile[threadIdx.x] = (k < S.n) ? A.q4[S.ob_off + k] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
-        __syncthreads();
+    __shared__ float4 tile[BP1_CHUNK];
+    if (threadIdx.x == 0) atomicAdd(A.pairs_examined, (unsigned long long)T * (unsigned long long)L);
+    for (int t0 = 0; t0 < T; t0 += BP1_THREADS) {
+        const bool valid = t0 + (int)threadIdx.x < T;
+        const int gi = S.ob_off + (valid ? tl[t0 + threadIdx.x] : 0);
+        const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
+        int cnt = 0;
+        float sum = 0.f;
+        for (int base = 0; base < L; base += BP1_CHUNK) {
+            const int lim = min(BP1_CHUNK, L - base);
+            __syncthreads();
+            for (int k = threadIdx.x; k < BP1_CHUNK; k += BP1_THREADS)
+                tile[k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
+            __syncthreads();
+            const int lim8 = (lim + 7) & ~7;
 #pragma unroll 8
-        for (int c = 0; c < BUDDY_THREADS; ++c) {
-            const float4 o = tile[c];
-            const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
-            const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
-            const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
-            cnt += b ? 1 : 0;
-            sum = fadd(sum, b ? o.z : 0.f);
+            for (int q = 0; q < lim8; ++q) {
+                const float4 o = tile[q];
+                const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
+                const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+                const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
+                cnt += b ? 1 : 0;
+                sum = fadd(sum, b ? o.z : 0.f);
+            }
         }
-        __syncthreads();
+        if (valid) { A.cnt[gi] = cnt; A.sum[gi] = sum; }
     }
-    if (valid) { A.cnt[S.ob_off + li] = cnt; A.sum[S.ob_off + li] = sum; }
 }
 
 // Index-ordered list of the obs that can ever be removed from a buddy set: diff >
@@ -340,7 +375,8 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     if (ns == 0) return OG_OK;
     cudaStream_t st = ctx->stream;
     std::vector<QcSlabDev> hs(ns);
-    int max_n = 0;
+    int max_n = 0, ncells_all = 0, max_cells = 0;
+    std::vector<BinSlab> bslabs(ns);
     int64_t pair_tests = 0, nobs = 0;
     // thresholds depend on the range class only: cache the three
     float thi_c[3], tlo = threshold_ge(0.1f, b.dx_km);
@@ -353,6 +389,15 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         d.max_error = h.max_error; d.max_buddy = h.max_buddy;
         int rc = (h.pressure <= 201.0f) ? 0 : ((h.pressure <= 1000.1f) ? 1 : 2); // :121-127
         d.t_lo = tlo; d.t_hi = thi_c[rc];
+        // |dx| <= sqrt(d2) for a pair that passes d2 <= t_hi; the margin swallows the roundings
+        const float reach_max = (float)std::max(b.iew, b.jns) + 2.f;
+        d.reach = (d.t_hi >= 0.f) ? std::min(sqrtf(d.t_hi) * 1.0001f + 0.01f, reach_max) : 0.f;
+        const int cell = std::max(8, (int)ceilf(d.reach));
+        d.ncx = (b.iew + cell - 1) / cell; d.ncy = (b.jns + cell - 1) / cell;
+        d.cell_off = ncells_all;
+        bslabs[s] = BinSlab{h.n, h.ob_off, cell, d.ncx, d.ncy, d.cell_off};
+        ncells_all += d.ncx * d.ncy;
+        max_cells = std::max(max_cells, d.ncx * d.ncy);
         max_n = std::max(max_n, h.n);
         pair_tests += (int64_t)h.n * (h.n > 0 ? h.n - 1 : 0);
         nobs += h.n;
@@ -377,6 +422,11 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     OG_TRY(ctx->reserve_t("qc.kob", tot, &A.kob));
     OG_TRY(ctx->reserve_t("qc.err", tot, &A.err));
     A.changed = ctx->d_flag;
+    if (b.do_buddy) {
+        OG_TRY(ctx->reserve_t("qc.home_box", tot, &A.home_box));
+        OG_TRY(ctx->reserve_t("qc.range_box", tot, &A.range_box));
+    }
+    A.pairs_examined = ctx->d_counters + 3;
     A.d_aob = b.aob; A.d_err_max = b.err_max; A.d_thr_max = b.thr_max;
     A.d_err_buddy = b.err_buddy; A.d_difmax = b.difmax; A.d_bnf = b.buddy_num_final;
 
@@ -385,9 +435,17 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     qc_prep_kernel<<<g_ob, 256, 0, st>>>(A);
     ctx->count_launch();
     if (b.do_buddy) {
+        // targets of a cell: the obs sitting in it (any order); candidates: the obs within reach
+        // of it, in ascending index -- the order the reference sums in
+        BinLists home, range;
+        OG_TRY(bin_build(ctx, "qc.home", bslabs, A.home_box, false, &home));
+        OG_TRY(bin_build(ctx, "qc.range", bslabs, A.range_box, true, &range));
+        A.home_count = home.cell_count; A.home_start = home.cell_start; A.home_list = home.cell_list;
+        A.range_count = range.cell_count; A.range_start = range.cell_start; A.range_list = range.cell_list;
         dim3 g_b((max_n + BUDDY_THREADS - 1) / BUDDY_THREADS, ns);
+        dim3 g_c(max_cells, ns);
         const int tslot = ctx->timer_begin(1);
-        buddy_pass1_kernel<<<g_b, BUDDY_THREADS, 0, st>>>(A);
+        buddy_pass1_kernel<<<g_c, BP1_THREADS, 0, st>>>(A);
         ctx->timer_end(tslot);
         suspect_kernel<<<ns, 256, 0, st>>>(A);
         ctx->count_launch(2);
