@@ -40,15 +40,34 @@ __device__ __forceinline__ void for_each_cell(const BinSlab& S, short4 b, F f)
         for (int cx = cx0; cx <= cx1; ++cx) f(S.cell_off + cy * S.ncx + cx);
 }
 
+// Slabs with at most HCAP cells histogram in shared memory first, so that the global atomics
+// are one per (block, touched cell) instead of one per (ob, cell): with cells one buddy range
+// wide a few hundred counters would otherwise take every ob of the slab nine times.
+constexpr int HCAP = 4096;
+
 __global__ void __launch_bounds__(256) bin_count_kernel(BinDev A)
 {
     const BinSlab S = A.slabs[blockIdx.y];
+    if ((int)(blockIdx.x * blockDim.x) >= S.n) return;
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= S.n) return;
-    for_each_cell(S, A.box[S.ob_off + li], [&](int c) { atomicAdd(&A.cell_count[c], 1); });
+    const int nc = S.ncx * S.ncy;
+    const short4 box = (li < S.n) ? A.box[S.ob_off + li] : make_short4(1, 0, 1, 0);
+    if (nc > HCAP) {
+        for_each_cell(S, box, [&](int c) { atomicAdd(&A.cell_count[c], 1); });
+        return;
+    }
+    __shared__ int s_hist[HCAP];
+    for (int q = threadIdx.x; q < nc; q += blockDim.x) s_hist[q] = 0;
+    __syncthreads();
+    for_each_cell(S, box, [&](int c) { atomicAdd(&s_hist[c - S.cell_off], 1); });
+    __syncthreads();
+    for (int q = threadIdx.x; q < nc; q += blockDim.x) {
+        const int v = s_hist[q];
+        if (v) atomicAdd(&A.cell_count[S.cell_off + q], v);
+    }
 }
 
-// Exclusive scan of all cell counts of the batch: one block, coalesced tiles of 1024.
+// Exclusive scan of all cell counts of the batch: one block, coalesced tiles of 4096.
 __global__ void __launch_bounds__(1024) cell_prefix_kernel(const int* __restrict__ cnt,
                                                            int* __restrict__ start, int n,
                                                            int* __restrict__ total)
@@ -58,10 +77,13 @@ __global__ void __launch_bounds__(1024) cell_prefix_kernel(const int* __restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_carry = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + tid;
-        const int v = (i < n) ? cnt[i] : 0;
-        int inc = v;
+    for (int base = 0; base < n; base += 4096) {
+        const int i = base + 4 * tid;
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (i + q < n) ? cnt[i + q] : 0;
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -79,11 +101,14 @@ __global__ void __launch_bounds__(1024) cell_prefix_kernel(const int* __restrict
             s_warp[lane] = winc - w;    // exclusive over warps
         }
         __syncthreads();
-        const int carry = s_carry;
-        const int excl = carry + s_warp[warp] + inc - v;
-        if (i < n) start[i] = excl;
+        int run = s_carry + s_warp[warp] + inc - mine;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i + q < n) start[i + q] = run;
+            run += v[q];
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = excl + v;
+        if (tid == 1023) s_carry = run;
         __syncthreads();
     }
     if (tid == 0) { start[n] = s_carry; *total = s_carry; }
@@ -92,11 +117,32 @@ __global__ void __launch_bounds__(1024) cell_prefix_kernel(const int* __restrict
 __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
 {
     const BinSlab S = A.slabs[blockIdx.y];
+    if ((int)(blockIdx.x * blockDim.x) >= S.n) return;
     const int li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= S.n) return;
-    for_each_cell(S, A.box[S.ob_off + li], [&](int c) {
-        const int pos = atomicAdd(&A.cell_cursor[c], 1);
-        A.cell_list[A.cell_start[c] + pos] = li;
+    const int nc = S.ncx * S.ncy;
+    const short4 box = (li < S.n) ? A.box[S.ob_off + li] : make_short4(1, 0, 1, 0);
+    if (nc > HCAP) {
+        for_each_cell(S, box, [&](int c) {
+            const int pos = atomicAdd(&A.cell_cursor[c], 1);
+            A.cell_list[A.cell_start[c] + pos] = li;
+        });
+        return;
+    }
+    __shared__ int s_hist[HCAP];    // entries of this block per cell, then the block's cursor
+    __shared__ int s_base[HCAP];    // first slot of the block in the cell's list
+    for (int q = threadIdx.x; q < nc; q += blockDim.x) s_hist[q] = 0;
+    __syncthreads();
+    for_each_cell(S, box, [&](int c) { atomicAdd(&s_hist[c - S.cell_off], 1); });
+    __syncthreads();
+    for (int q = threadIdx.x; q < nc; q += blockDim.x) {
+        const int v = s_hist[q];
+        if (v) s_base[q] = A.cell_start[S.cell_off + q] + atomicAdd(&A.cell_cursor[S.cell_off + q], v);
+        s_hist[q] = 0;
+    }
+    __syncthreads();
+    for_each_cell(S, box, [&](int c) {
+        const int q = c - S.cell_off;
+        A.cell_list[s_base[q] + atomicAdd(&s_hist[q], 1)] = li;
     });
 }
 

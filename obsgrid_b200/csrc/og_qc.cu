@@ -53,8 +53,11 @@ struct QcDev {
     int* emax_fail;      // error_max verdict per ob
     int* cnt;            // buddy_num
     float* sum;          // sum of buddy diffs (index order)
-    int* susp_list;      // per slab, local indices of suspects in index order
-    int* susp_count;     // per slab
+    unsigned char* susp; // ob can ever be removed from a buddy set
+    int* susp_list;      // per cell (at range_start), local indices of its suspect candidates
+    int* susp_count;     // per cell
+    int4* items;         // work items {slab, cell, target group}
+    int* n_items;
     unsigned char* mod_in;   // relaxation mask of the previous fix-point iteration
     unsigned char* mod_out;
     int* kob;            // buddy_num_final
@@ -144,6 +147,7 @@ __global__ void __launch_bounds__(256) qc_prep_kernel(QcDev A)
     difmax = fmul(difmax, A.buddy_weight); // :193
     A.q4[gi] = make_float4(x, y, err, difmax);
     A.mod_in[gi] = 0;
+    A.susp[gi] = (err > fmul(fminf(difmax, fmul(1.2f, difmax)), 1.25f)) ? 1 : 0;
     if (A.home_box) {
         // the same monotone clamp on both boxes keeps "within reach" => "lists meet" for any x, y
         const float fi = (float)A.iew, fj = (float)A.jns;
@@ -157,116 +161,134 @@ __global__ void __launch_bounds__(256) qc_prep_kernel(QcDev A)
     }
 }
 
+// Work items of the two pair passes: (slab, cell, group of BP_THREADS targets of the cell).
+// Cells differ wildly in weight (targets x candidates grows with the square of the local
+// station density), so the passes run one CTA per item instead of one per cell.
+constexpr int BP_THREADS = 128;
+constexpr int BP_CHUNK = 512;
+__global__ void __launch_bounds__(128) buddy_items_kernel(QcDev A)
+{
+    const QcSlabDev& S = A.slabs[blockIdx.y];
+    const int lc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lc >= S.ncx * S.ncy) return;
+    const int c = S.cell_off + lc;
+    const int T = A.home_count[c];
+    if (T == 0) return;
+    const int G = (T + BP_THREADS - 1) / BP_THREADS;
+    const int base = atomicAdd(A.n_items, G);
+    for (int g = 0; g < G; ++g) A.items[base + g] = make_int4((int)blockIdx.y, c, g, 0);
+    atomicAdd(A.pairs_examined, (unsigned long long)T * (unsigned long long)A.range_count[c]);
+}
+
 // station_loop_2/3, first half (qc2_module.F90:223-256): buddy count and index-ordered sum.
-// One CTA per cell: its targets are the obs sitting in the cell, its candidates the
-// index-ordered list of the obs within reach of the cell.
-constexpr int BUDDY_THREADS = 256;
-constexpr int BP1_THREADS = 128;
-constexpr int BP1_CHUNK = 512;
-__global__ void __launch_bounds__(BP1_THREADS) buddy_pass1_kernel(QcDev A)
+// Targets: obs sitting in the cell; candidates: the index-ordered list of the obs within
+// reach of the cell.
+__global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
+{
+    if ((int)blockIdx.x >= *A.n_items) return;
+    const int4 it = A.items[blockIdx.x];
+    const QcSlabDev& S = A.slabs[it.x];
+    const int c = it.y, t0 = it.z * BP_THREADS;
+    const int T = A.home_count[c], L = A.range_count[c];
+    const int* __restrict__ tl = A.home_list + A.home_start[c];
+    const int* __restrict__ cl = A.range_list + A.range_start[c];
+    const float tlo = S.t_lo, thi = S.t_hi;
+    __shared__ float4 tile[BP_CHUNK];
+    const bool valid = t0 + (int)threadIdx.x < T;
+    const int gi = S.ob_off + (valid ? tl[t0 + threadIdx.x] : 0);
+    const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
+    int cnt = 0;
+    float sum = 0.f;
+    for (int base = 0; base < L; base += BP_CHUNK) {
+        const int lim = min(BP_CHUNK, L - base);
+        const int lim8 = (lim + 7) & ~7;
+        __syncthreads();
+        for (int k = threadIdx.x; k < lim8; k += BP_THREADS)
+            tile[k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
+        __syncthreads();
+#pragma unroll 8
+        for (int q = 0; q < lim8; ++q) {
+            const float4 o = tile[q];
+            const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
+            const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+            const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
+            cnt += b ? 1 : 0;
+            sum = fadd(sum, b ? o.z : 0.f);
+        }
+    }
+    if (valid) { A.cnt[gi] = cnt; A.sum[gi] = sum; }
+}
+
+// Per cell, the index-ordered sub-list of its candidates that can ever be removed from a
+// buddy set: diff > 1.25*difmax with either the plain or the relaxed difmax
+// (qc2_module.F90:277-282; flagged per ob by qc_prep_kernel).
+__global__ void __launch_bounds__(128) suspect_kernel(QcDev A)
 {
     const QcSlabDev& S = A.slabs[blockIdx.y];
     if ((int)blockIdx.x >= S.ncx * S.ncy) return;
     const int c = S.cell_off + blockIdx.x;
-    const int T = A.home_count[c];
-    if (T == 0) return;
-    const int L = A.range_count[c];
-    const int* __restrict__ tl = A.home_list + A.home_start[c];
+    const int L = (A.home_count[c] > 0) ? A.range_count[c] : 0;   // cells without targets are never read
     const int* __restrict__ cl = A.range_list + A.range_start[c];
-    const float tlo = S.t_lo, thi = S.t_hi;
-    __shared__ float4 tile[BP1_CHUNK];
-    if (threadIdx.x == 0) atomicAdd(A.pairs_examined, (unsigned long long)T * (unsigned long long)L);
-    for (int t0 = 0; t0 < T; t0 += BP1_THREADS) {
-        const bool valid = t0 + (int)threadIdx.x < T;
-        const int gi = S.ob_off + (valid ? tl[t0 + threadIdx.x] : 0);
-        const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
-        int cnt = 0;
-        float sum = 0.f;
-        for (int base = 0; base < L; base += BP1_CHUNK) {
-            const int lim = min(BP1_CHUNK, L - base);
-            __syncthreads();
-            for (int k = threadIdx.x; k < BP1_CHUNK; k += BP1_THREADS)
-                tile[k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
-            __syncthreads();
-            const int lim8 = (lim + 7) & ~7;
-#pragma unroll 8
-            for (int q = 0; q < lim8; ++q) {
-                const float4 o = tile[q];
-                const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
-                const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
-                const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
-                cnt += b ? 1 : 0;
-                sum = fadd(sum, b ? o.z : 0.f);
-            }
-        }
-        if (valid) { A.cnt[gi] = cnt; A.sum[gi] = sum; }
-    }
-}
-
-// Index-ordered list of the obs that can ever be removed from a buddy set: diff >
-// 1.25*difmax (with either the plain or the relaxed difmax), qc2_module.F90:277-282.
-__global__ void __launch_bounds__(256) suspect_kernel(QcDev A)
-{
-    const QcSlabDev& S = A.slabs[blockIdx.x];
-    int* out = A.susp_list + S.ob_off;
-    __shared__ int s_w[8];
+    int* __restrict__ out = A.susp_list + A.range_start[c];
+    __shared__ int s_w[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int done = 0;
-    for (int base = 0; base < S.n; base += 256) {
-        const int li = base + threadIdx.x;
+    for (int base = 0; base < L; base += 128) {
+        const int k = base + threadIdx.x;
+        int lk = 0;
         bool sp = false;
-        if (li < S.n) {
-            float4 o = A.q4[S.ob_off + li];
-            float dm = fminf(o.w, fmul(1.2f, o.w));
-            sp = o.z > fmul(dm, 1.25f);
-        }
+        if (k < L) { lk = cl[k]; sp = A.susp[S.ob_off + lk] != 0; }
         const unsigned m = __ballot_sync(0xffffffffu, sp);
         if (lane == 0) s_w[warp] = __popc(m);
         __syncthreads();
         int woff = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { int v = s_w[w]; woff += (w < warp) ? v : 0; tot += v; }
-        if (sp) out[done + woff + __popc(m & ((1u << lane) - 1u))] = li;
+        for (int w = 0; w < 4; ++w) { int v = s_w[w]; woff += (w < warp) ? v : 0; tot += v; }
+        if (sp) out[done + woff + __popc(m & ((1u << lane) - 1u))] = lk;
         done += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) A.susp_count[blockIdx.x] = done;
+    if (threadIdx.x == 0) A.susp_count[c] = done;
 }
 
 // remove_bad_ob + err (qc2_module.F90:269-327) for one relaxation mask.
-__global__ void __launch_bounds__(BUDDY_THREADS) buddy_pass2_kernel(QcDev A)
+__global__ void __launch_bounds__(BP_THREADS) buddy_pass2_kernel(QcDev A)
 {
-    const QcSlabDev& S = A.slabs[blockIdx.y];
-    if ((int)(blockIdx.x * BUDDY_THREADS) >= S.n) return;
-    const int li = blockIdx.x * BUDDY_THREADS + threadIdx.x;
-    const bool valid = li < S.n;
+    if ((int)blockIdx.x >= *A.n_items) return;
+    const int4 it = A.items[blockIdx.x];
+    const QcSlabDev& S = A.slabs[it.x];
+    const int c = it.y, t0 = it.z * BP_THREADS;
+    const int T = A.home_count[c];
+    const bool valid = t0 + (int)threadIdx.x < T;
+    const int li = valid ? A.home_list[A.home_start[c] + t0 + threadIdx.x] : 0;
     const int gi = S.ob_off + li;
     const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
     const int cnt = valid ? A.cnt[gi] : 0;
     float sum = valid ? A.sum[gi] : 0.f;
     const float average = (cnt > 0) ? fdiv(sum, (float)cnt) : 0.f;
     const float tlo = S.t_lo, thi = S.t_hi;
-    const int ns = A.susp_count[blockIdx.y];
-    const int* __restrict__ sl = A.susp_list + S.ob_off;
-    __shared__ float4 tile[BUDDY_THREADS];
-    __shared__ int tidx[BUDDY_THREADS];   // local index, bit 30 = relaxed
+    const int ns = A.susp_count[c];
+    const int* __restrict__ sl = A.susp_list + A.range_start[c];
+    __shared__ float4 tile[BP_THREADS];
+    __shared__ int tidx[BP_THREADS];   // local index, bit 30 = relaxed
     int kob = cnt;
-    for (int base = 0; base < ns; base += BUDDY_THREADS) {
+    for (int base = 0; base < ns; base += BP_THREADS) {
         const int k = base + threadIdx.x;
+        __syncthreads();
         if (k < ns) {
             int lk = sl[k];
             tile[threadIdx.x] = A.q4[S.ob_off + lk];
             tidx[threadIdx.x] = lk | (A.mod_in[S.ob_off + lk] ? (1 << 30) : 0);
         }
         __syncthreads();
-        const int lim = min(BUDDY_THREADS, ns - base);
+        const int lim = min(BP_THREADS, ns - base);
         if (cnt >= 2) {
-            for (int c = 0; c < lim; ++c) {
-                const float4 o = tile[c];
+            for (int q = 0; q < lim; ++q) {
+                const float4 o = tile[q];
                 const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
                 const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
                 if ((d2 <= thi) && (d2 >= tlo)) {
-                    const int ti = tidx[c];
+                    const int ti = tidx[q];
                     const int lk = ti & ~(1 << 30);
                     // stations before `num` have already been relaxed when num is visited
                     const float dm = ((ti >> 30) && lk < li) ? fmul(1.2f, o.w) : o.w;
@@ -278,7 +300,6 @@ __global__ void __launch_bounds__(BUDDY_THREADS) buddy_pass2_kernel(QcDev A)
                 }
             }
         }
-        __syncthreads();
     }
     if (!valid) return;
     float err = 0.f;
@@ -415,8 +436,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     OG_TRY(ctx->reserve_t("qc.emax", tot, &A.emax_fail));
     OG_TRY(ctx->reserve_t("qc.cnt", tot, &A.cnt));
     OG_TRY(ctx->reserve_t("qc.sum", tot, &A.sum));
-    OG_TRY(ctx->reserve_t("qc.susp", tot, &A.susp_list));
-    OG_TRY(ctx->reserve_t("qc.suspn", (size_t)ns, &A.susp_count));
+    OG_TRY(ctx->reserve_t("qc.suspflag", tot, &A.susp));
     OG_TRY(ctx->reserve_t("qc.mod0", tot, &A.mod_in));
     OG_TRY(ctx->reserve_t("qc.mod1", tot, &A.mod_out));
     OG_TRY(ctx->reserve_t("qc.kob", tot, &A.kob));
@@ -442,17 +462,25 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         OG_TRY(bin_build(ctx, "qc.range", bslabs, A.range_box, true, &range));
         A.home_count = home.cell_count; A.home_start = home.cell_start; A.home_list = home.cell_list;
         A.range_count = range.cell_count; A.range_start = range.cell_start; A.range_list = range.cell_list;
-        dim3 g_b((max_n + BUDDY_THREADS - 1) / BUDDY_THREADS, ns);
-        dim3 g_c(max_cells, ns);
+        OG_TRY(ctx->reserve_t("qc.susp_list", (size_t)std::max(range.list_total, 1), &A.susp_list));
+        OG_TRY(ctx->reserve_t("qc.susp_count", (size_t)ncells_all + 1, &A.susp_count));
+        // one work item per (cell, group of BP_THREADS targets): at most one per non-empty cell
+        // plus one per BP_THREADS obs
+        const size_t max_items = (size_t)ncells_all + (size_t)b.total_obs / BP_THREADS + 1;
+        OG_TRY(ctx->reserve_t("qc.items", max_items, &A.items));
+        A.n_items = ctx->d_flag + 2;
+        OG_CUDA(cudaMemsetAsync(A.n_items, 0, sizeof(int), st));
+        dim3 g_c(max_cells, ns), g_ci((max_cells + 127) / 128, ns);
+        buddy_items_kernel<<<g_ci, 128, 0, st>>>(A);
         const int tslot = ctx->timer_begin(1);
-        buddy_pass1_kernel<<<g_c, BP1_THREADS, 0, st>>>(A);
+        buddy_pass1_kernel<<<(unsigned)max_items, BP_THREADS, 0, st>>>(A);
         ctx->timer_end(tslot);
-        suspect_kernel<<<ns, 256, 0, st>>>(A);
-        ctx->count_launch(2);
+        suspect_kernel<<<g_c, 128, 0, st>>>(A);
+        ctx->count_launch(3);
         int iters = 0;
         for (;;) {
             OG_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
-            buddy_pass2_kernel<<<g_b, BUDDY_THREADS, 0, st>>>(A);
+            buddy_pass2_kernel<<<(unsigned)max_items, BP_THREADS, 0, st>>>(A);
             ctx->count_launch();
             OG_CUDA(cudaMemcpyAsync(ctx->h_pinned_small, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
             OG_CUDA(cudaStreamSynchronize(st));
