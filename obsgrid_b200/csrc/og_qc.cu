@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
     const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
     int cnt = 0;
     float sum = 0.f;
+    const bool warp_on = t0 + (int)(threadIdx.x & ~31u) < T;   // warps without a target only stage
     for (int base = 0; base < L; base += BP_CHUNK) {
         const int lim = min(BP_CHUNK, L - base);
         const int lim8 = (lim + 7) & ~7;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
         for (int k = threadIdx.x; k < lim8; k += BP_THREADS)
             tile[k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
         __syncthreads();
+        if (!warp_on) continue;
 #pragma unroll 8
         for (int q = 0; q < lim8; ++q) {
             const float4 o = tile[q];
@@ -413,7 +415,11 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         // |dx| <= sqrt(d2) for a pair that passes d2 <= t_hi; the margin swallows the roundings
         const float reach_max = (float)std::max(b.iew, b.jns) + 2.f;
         d.reach = (d.t_hi >= 0.f) ? std::min(sqrtf(d.t_hi) * 1.0001f + 0.01f, reach_max) : 0.f;
-        const int cell = std::max(8, (int)ceilf(d.reach));
+        // cells one reach wide (9 cells per ob) where stations are sparse, half a reach wide
+        // (25 cells per ob, a third fewer pair tests) where a half-reach cell still fills a warp
+        const float dens = (float)h.n / ((float)b.iew * (float)b.jns);
+        const float edge = (dens * 0.25f * d.reach * d.reach >= 32.f) ? 0.5f * d.reach : d.reach;
+        const int cell = std::max(8, (int)ceilf(edge));
         d.ncx = (b.iew + cell - 1) / cell; d.ncy = (b.jns + cell - 1) / cell;
         d.cell_off = ncells_all;
         bslabs[s] = BinSlab{h.n, h.ob_off, cell, d.ncx, d.ncy, d.cell_off};
