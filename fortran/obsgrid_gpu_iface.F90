@@ -1,0 +1,306 @@
+!  obsgrid_gpu_iface.F90 -- the Fortran side of the drop-in boundary.
+!
+!  OBSGRID's driver, namelist handling, little_r ingest and netCDF output stay in Fortran.
+!  The three procedures its stage drivers call for the hot path keep their names, argument
+!  order and meaning (so proc_oa.F90:728-736 and proc_qc.F90:372-391 do not change) and
+!  forward to libobsgrid_gpu.so through ISO_C_BINDING:
+!
+!     cressman     src/oa_module.F90:25-32     ->  og_cressman
+!     error_max    src/qc1_module.F90:9-15     ->  og_error_max
+!     buddy_check  src/qc2_module.F90:9-14     ->  og_buddy_check
+!
+!  Build: compile this file instead of the bodies of oa_module.F90 (cressman), qc1_module.F90
+!  and qc2_module.F90 (see INTEGRATION.md), link with -lobsgrid_gpu.  The image this library
+!  is developed in has no Fortran compiler, so this file is reviewed, not compiled, there; the
+!  C ABI it binds (include/obsgrid_gpu.h) is exercised by the ctypes tests with the very same
+!  argument lists.
+!
+!  Conventions (include/obsgrid_gpu.h): arrays are passed as they are (column-major
+!  gridded(iew,jns), 1-based REAL(4) coordinates), LOGICALs as INTEGER(C_INT) 0/1,
+!  CHARACTER(8) variable names as integer codes, every C function returns 0 or a negative
+!  status and never STOPs -- the wrappers turn a failure into the reference's fatal
+!  error_handler call (src/error_handler.F90:53-92).
+
+MODULE obsgrid_gpu
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   IMPLICIT NONE
+   PRIVATE
+   PUBLIC :: og_start , og_stop , og_handle , og_var_code
+
+   TYPE ( C_PTR ) , SAVE :: og_handle = C_NULL_PTR
+
+   INTERFACE
+
+      INTEGER ( C_INT ) FUNCTION og_init ( ctx , device ) BIND ( C , NAME = 'og_init' )
+         IMPORT :: C_PTR , C_INT
+         TYPE ( C_PTR ) , INTENT ( OUT ) :: ctx
+         INTEGER ( C_INT ) , VALUE :: device
+      END FUNCTION og_init
+
+      INTEGER ( C_INT ) FUNCTION og_finalize ( ctx ) BIND ( C , NAME = 'og_finalize' )
+         IMPORT :: C_PTR , C_INT
+         TYPE ( C_PTR ) , VALUE :: ctx
+      END FUNCTION og_finalize
+
+      FUNCTION og_last_error ( ) BIND ( C , NAME = 'og_last_error' ) RESULT ( msg )
+         IMPORT :: C_PTR
+         TYPE ( C_PTR ) :: msg
+      END FUNCTION og_last_error
+
+      INTEGER ( C_INT ) FUNCTION og_cressman ( ctx , diff , xob , yob , n , gridded , iew , jns , &
+      crsdot , var , radius_influence , dxd_km , u_banana , v_banana , pressure_hpa , passes , &
+      smooth_type , use_first_guess , fg_value , scale_cressman_rh_decreases ) &
+      BIND ( C , NAME = 'og_cressman' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: diff ( * ) , xob ( * ) , yob ( * )
+         INTEGER ( C_INT ) , VALUE :: n
+         REAL ( C_FLOAT ) , INTENT ( INOUT ) :: gridded ( * )
+         INTEGER ( C_INT ) , VALUE :: iew , jns , crsdot , var , radius_influence
+         REAL ( C_FLOAT ) , VALUE :: dxd_km
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: u_banana ( * ) , v_banana ( * )
+         REAL ( C_FLOAT ) , VALUE :: pressure_hpa
+         INTEGER ( C_INT ) , VALUE :: passes , smooth_type , use_first_guess
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: fg_value ( * )
+         INTEGER ( C_INT ) , VALUE :: scale_cressman_rh_decreases
+      END FUNCTION og_cressman
+
+      INTEGER ( C_INT ) FUNCTION og_error_max ( ctx , obs , xob , yob , station_elevation , &
+      qc_flag , n , gridded , iew , jns , var , max_difference , pressure_hpa , local_time , &
+      aob , err , thr ) BIND ( C , NAME = 'og_error_max' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: obs ( * ) , xob ( * ) , yob ( * ) , station_elevation ( * )
+         INTEGER ( C_INT ) , INTENT ( INOUT ) :: qc_flag ( * )
+         INTEGER ( C_INT ) , VALUE :: n
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: gridded ( * )
+         INTEGER ( C_INT ) , VALUE :: iew , jns , var
+         REAL ( C_FLOAT ) , VALUE :: max_difference , pressure_hpa
+         INTEGER ( C_INT ) , INTENT ( IN ) :: local_time ( * )
+         TYPE ( C_PTR ) , VALUE :: aob , err , thr          ! nullable diagnostics
+      END FUNCTION og_error_max
+
+      INTEGER ( C_INT ) FUNCTION og_buddy_check ( ctx , obs , n , xob , yob , qc_flag , &
+      station_elevation , gridded , iew , jns , var , pressure_hpa , dx_km , buddy_weight , &
+      buddy_difference , aob , err , difmax , buddy_num_final ) BIND ( C , NAME = 'og_buddy_check' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: obs ( * )
+         INTEGER ( C_INT ) , VALUE :: n
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: xob ( * ) , yob ( * )
+         INTEGER ( C_INT ) , INTENT ( INOUT ) :: qc_flag ( * )
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: station_elevation ( * ) , gridded ( * )
+         INTEGER ( C_INT ) , VALUE :: iew , jns , var
+         REAL ( C_FLOAT ) , VALUE :: pressure_hpa , dx_km , buddy_weight , buddy_difference
+         TYPE ( C_PTR ) , VALUE :: aob , err , difmax , buddy_num_final   ! nullable diagnostics
+      END FUNCTION og_buddy_check
+
+   END INTERFACE
+
+   PUBLIC :: og_cressman , og_error_max , og_buddy_check , og_fail
+
+CONTAINS
+
+   !  One context per process, created before the first time period (driver.F90, before the
+   !  time loop) and destroyed after the last.
+   SUBROUTINE og_start ( device )
+      INTEGER , INTENT ( IN ) :: device
+      IF ( og_init ( og_handle , INT ( device , C_INT ) ) .NE. 0 ) CALL og_fail ( 'og_init' )
+   END SUBROUTINE og_start
+
+   SUBROUTINE og_stop
+      INTEGER ( C_INT ) :: rc
+      rc = og_finalize ( og_handle )
+      og_handle = C_NULL_PTR
+   END SUBROUTINE og_stop
+
+   !  CHARACTER(8) variable name -> og_var code (include/obsgrid_gpu.h: OG_VAR_*).
+   INTEGER ( C_INT ) FUNCTION og_var_code ( name )
+      CHARACTER ( LEN = 8 ) , INTENT ( IN ) :: name
+      SELECT CASE ( name )
+         CASE ( 'UU      ' ) ; og_var_code = 1
+         CASE ( 'VV      ' ) ; og_var_code = 2
+         CASE ( 'TT      ' ) ; og_var_code = 3
+         CASE ( 'RH      ' ) ; og_var_code = 4
+         CASE ( 'PMSL    ' ) ; og_var_code = 5
+         CASE ( 'PSFC    ' , 'PMSLPSFC' ) ; og_var_code = 6
+         CASE ( 'DEWPOINT' ) ; og_var_code = 7
+         CASE DEFAULT ; og_var_code = -1
+      END SELECT
+   END FUNCTION og_var_code
+
+   !  The library never STOPs; the reference's convention for an unrecoverable error is a
+   !  fatal error_handler call (src/error_handler.F90:53-92).
+   SUBROUTINE og_fail ( where )
+      CHARACTER ( LEN = * ) , INTENT ( IN ) :: where
+      INCLUDE 'error.inc'
+      INTERFACE
+         INCLUDE 'error.int'
+      END INTERFACE
+      CHARACTER ( KIND = C_CHAR ) , POINTER :: cmsg ( : )
+      CHARACTER ( LEN = 200 ) :: msg
+      INTEGER :: i
+      msg = ' '
+      CALL C_F_POINTER ( og_last_error ( ) , cmsg , (/ 200 /) )
+      DO i = 1 , 200
+         IF ( cmsg ( i ) .EQ. C_NULL_CHAR ) EXIT
+         msg ( i : i ) = cmsg ( i )
+      END DO
+      error_number = 00363001
+      error_message ( 1 : 31 ) = 'obsgrid_gpu                    '
+      error_message ( 32 : ) = ' ' // where // ': ' // TRIM ( msg )
+      fatal = .TRUE.
+      listing = .FALSE.
+      CALL error_handler ( error_number , error_message , fatal , listing )
+   END SUBROUTINE og_fail
+
+END MODULE obsgrid_gpu
+
+!  ---------------------------------------------------------------------------------------
+!  Replacement bodies with the reference's exact interfaces.  They live in the modules the
+!  callers already USE (oa_module, qc1, qc2): see INTEGRATION.md for the three-line patch that
+!  swaps each body for an INCLUDE of the matching block below.
+!  ---------------------------------------------------------------------------------------
+
+!  MODULE oa_module :: cressman          (replaces src/oa_module.F90:25-218)
+SUBROUTINE cressman ( obs_value , obs , xob , yob , numobs , &
+gridded , iew , jns , &
+crsdot , name , radius_influence , &
+dxd , u_banana , v_banana , pressure , passes , smooth_type , lat_center , &
+use_first_guess , fg_value , scale_cressman_rh_decreases )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER , INTENT ( IN )                             :: numobs
+   INTEGER , INTENT ( IN )                             :: iew , jns
+   REAL , INTENT ( IN ) , DIMENSION ( numobs )         :: obs_value , obs , xob , yob
+   REAL , INTENT ( IN ) , DIMENSION ( numobs )         :: fg_value
+   REAL , INTENT ( INOUT ) , DIMENSION ( iew , jns )   :: gridded
+   INTEGER , INTENT ( IN )                             :: radius_influence
+   CHARACTER ( 8 ) , INTENT ( IN )                     :: name
+   REAL , INTENT ( IN ) , DIMENSION ( iew , jns )      :: u_banana , v_banana
+   REAL , INTENT ( IN )                                :: dxd , pressure
+   INTEGER                                             :: crsdot
+   INTEGER , INTENT ( IN )                             :: passes , smooth_type
+   REAL , INTENT ( IN )                                :: lat_center
+   LOGICAL , INTENT ( IN )                             :: use_first_guess
+   LOGICAL                                             :: scale_cressman_rh_decreases
+
+   INTEGER ( C_INT ) :: rc
+
+   !  obs_value and lat_center are unused by the reference body as well.
+   rc = og_cressman ( og_handle , obs , xob , yob , INT ( numobs , C_INT ) , gridded , &
+                      INT ( iew , C_INT ) , INT ( jns , C_INT ) , INT ( crsdot , C_INT ) , &
+                      og_var_code ( name ) , INT ( radius_influence , C_INT ) , dxd , &
+                      u_banana , v_banana , pressure , INT ( passes , C_INT ) , &
+                      INT ( smooth_type , C_INT ) , MERGE ( 1_C_INT , 0_C_INT , use_first_guess ) , &
+                      fg_value , MERGE ( 1_C_INT , 0_C_INT , scale_cressman_rh_decreases ) )
+   IF ( rc .NE. 0 ) CALL og_fail ( 'cressman' )
+
+END SUBROUTINE cressman
+
+!  MODULE qc1 :: error_max               (replaces src/qc1_module.F90:9-300)
+SUBROUTINE error_max ( station_id , obs , ship_report , xob , yob ,  &
+station_elevation , &
+index , qc_flag , numobs , &
+gridded ,  iew , jns ,  &
+name , max_difference , pressure , local_time , print_error_max )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER                                        :: numobs
+   CHARACTER ( LEN =   8 ) , DIMENSION ( : )      :: station_id
+   REAL                    , DIMENSION ( : )      :: obs , xob , yob
+   REAL                    , DIMENSION ( : )      :: station_elevation
+   LOGICAL                 , DIMENSION ( : )      :: ship_report
+   INTEGER                 , DIMENSION ( : )      :: index
+   INTEGER                 , DIMENSION ( : )      :: qc_flag
+   REAL                    , DIMENSION( : , : )   :: gridded
+   INTEGER                                        :: iew , jns
+   CHARACTER ( LEN =   8 )                        :: name
+   INTEGER                 , DIMENSION ( : )      :: local_time
+   REAL                                           :: max_difference
+   REAL                                           :: pressure
+   LOGICAL                                        :: print_error_max
+
+   REAL ( C_FLOAT ) , DIMENSION ( numobs ) , TARGET :: aob , err , thr
+   INTEGER ( C_INT ) :: rc
+   INTEGER :: num
+
+   !  Assumed-shape dummies may be non-contiguous: hand contiguous sections to C (the compiler
+   !  copies in/out when it has to; proc_qc passes whole automatic arrays, so it does not).
+   rc = og_error_max ( og_handle , obs ( 1 : numobs ) , xob ( 1 : numobs ) , yob ( 1 : numobs ) , &
+                       station_elevation ( 1 : numobs ) , qc_flag ( 1 : numobs ) , &
+                       INT ( numobs , C_INT ) , gridded ( 1 : iew , 1 : jns ) , &
+                       INT ( iew , C_INT ) , INT ( jns , C_INT ) , og_var_code ( name ) , &
+                       max_difference , pressure , local_time ( 1 : numobs ) , &
+                       C_LOC ( aob ) , C_LOC ( err ) , C_LOC ( thr ) )
+   IF ( rc .NE. 0 ) CALL og_fail ( 'error_max' )
+
+   !  The reference's optional listing (src/qc1_module.F90:251-296) from the returned
+   !  diagnostics; station_id / ship_report / index only ever fed this print.
+   IF ( print_error_max ) THEN
+      DO num = 1 , numobs
+         IF ( ABS ( err ( num ) ) .GT. thr ( num ) ) THEN
+            WRITE ( UNIT = * , FMT = '(A8,1X,A8,1X,I5,4(1X,F12.3))' ) name , station_id ( num ) , &
+               index ( num ) , obs ( num ) , aob ( num ) , err ( num ) , thr ( num )
+         END IF
+      END DO
+   END IF
+
+END SUBROUTINE error_max
+
+!  MODULE qc2 :: buddy_check             (replaces src/qc2_module.F90:9-388)
+SUBROUTINE buddy_check ( station_id , obs , numobs , xob , yob , qc_flag ,   &
+station_elevation , &
+gridded , iew , jns , name ,                      &
+pressure , local_time , dx , buddy_weight , buddy_difference , print_buddy )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER                                        :: numobs
+   CHARACTER ( LEN =   8 ) , DIMENSION ( : )      :: station_id
+   REAL                    , DIMENSION ( : )      :: obs , xob , yob
+   INTEGER                 , DIMENSION ( : )      :: qc_flag
+   REAL                    , DIMENSION ( : )      :: station_elevation
+   REAL                    , DIMENSION( : , : )   :: gridded
+   INTEGER                                        :: iew , jns
+   CHARACTER ( LEN =   8 )                        :: name
+   REAL                                           :: buddy_weight ,   &
+                                                     buddy_difference , &
+                                                     dx          , &
+                                                     pressure
+   INTEGER                 , DIMENSION ( : )      :: local_time
+   LOGICAL                                        :: print_buddy
+
+   REAL ( C_FLOAT ) , DIMENSION ( numobs ) , TARGET    :: aob , err , difmax
+   INTEGER ( C_INT ) , DIMENSION ( numobs ) , TARGET   :: buddy_num_final
+   INTEGER ( C_INT ) :: rc
+   INTEGER :: num
+
+   !  local_time is not used by the reference body either (src/qc2_module.F90:9-388).
+   rc = og_buddy_check ( og_handle , obs ( 1 : numobs ) , INT ( numobs , C_INT ) , &
+                         xob ( 1 : numobs ) , yob ( 1 : numobs ) , qc_flag ( 1 : numobs ) , &
+                         station_elevation ( 1 : numobs ) , gridded ( 1 : iew , 1 : jns ) , &
+                         INT ( iew , C_INT ) , INT ( jns , C_INT ) , og_var_code ( name ) , &
+                         pressure , dx , buddy_weight , buddy_difference , &
+                         C_LOC ( aob ) , C_LOC ( err ) , C_LOC ( difmax ) , C_LOC ( buddy_num_final ) )
+   IF ( rc .NE. 0 ) CALL og_fail ( 'buddy_check' )
+
+   IF ( print_buddy ) THEN   ! src/qc2_module.F90:339-384
+      DO num = 1 , numobs
+         IF ( ABS ( err ( num ) ) .GT. difmax ( num ) ) THEN
+            WRITE ( UNIT = * , FMT = '(A8,1X,A8,1X,3(1X,F12.3),1X,I6)' ) name , station_id ( num ) , &
+               obs ( num ) , err ( num ) , difmax ( num ) , buddy_num_final ( num )
+         END IF
+      END DO
+   END IF
+
+END SUBROUTINE buddy_check

@@ -1,0 +1,131 @@
+"""Sharding one analysis time over several processes (one per GPU).
+
+The hot path has no exchange step: every (level, variable) slab reads only its
+own field plus the pre-analysis winds of its level, DEWPOINT reads the RH flags of its own
+level, and `qc_consistency` is per level -- so a time period is cut into contiguous level
+ranges `[k_begin, k_end)` (the unit `og_qc_time_levels` / `og_oa_time` take), each rank runs its
+range, and the analysed levels and flags are gathered to the rank that owns the host writer.
+The surface pseudo-level carries every report (upper levels only the soundings), so ranges are
+balanced on a cost estimate, not on level counts.
+
+`run_time_sharded` is backend-agnostic: the compute callables are the GPU context's
+`proc_qc` / `proc_oa` in production and anything with the same signature in the CPU tests
+(`gloo`, world size 2, tests/test_shard.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import numpy as np
+
+from ._capi import OG_MISSING_R
+
+FIELDS3 = ("t", "u", "v", "rh")
+FLAGS3 = ("qc_u", "qc_v", "qc_t", "qc_rh")
+
+
+def level_costs(case) -> np.ndarray:
+    """Relative cost of each level: obs at the level x (Cressman reach + buddy reach)."""
+    radii = [int(r) for r in case.oa_params.radius_influence if r >= 0]
+    r2 = float(sum(r * r for r in radii)) or 1.0
+    cost = np.zeros(case.kbu, np.float64)
+    area = float(case.iew * case.jns)
+    for k in range(case.kbu):
+        n = 0
+        for nm in ("ob_u", "ob_v", "ob_t", "ob_rh"):
+            n += int(np.count_nonzero(np.abs(getattr(case, nm)[k] - OG_MISSING_R) > 1.0))
+        if k == 0:
+            n += int(np.count_nonzero(np.abs(case.ob_slp - OG_MISSING_R) > 1.0))
+        p = float(case.pressure[k])
+        rng_km = 650.0 if p <= 201.0 else (300.0 if p <= 1000.1 else 500.0)
+        rc = rng_km / float(case.dx_km)
+        per_var = n / 4.0
+        cost[k] = n * np.pi * r2 + 4.0 * per_var * per_var * min(9.0 * rc * rc / area, 1.0)
+    return cost + 1.0
+
+
+def plan_levels(costs: Sequence[float], world: int) -> list[tuple[int, int]]:
+    """Contiguous level ranges, one per rank, minimising the heaviest range (linear-partition
+    DP).  Ranks beyond the number of levels get empty ranges."""
+    c = np.asarray(costs, np.float64)
+    K = len(c)
+    world = max(int(world), 1)
+    parts = min(world, K)
+    pre = np.concatenate([[0.0], np.cumsum(c)])
+    best = np.full((parts + 1, K + 1), np.inf)
+    cut = np.zeros((parts + 1, K + 1), np.int64)
+    best[0, 0] = 0.0
+    for p in range(1, parts + 1):
+        for k in range(p, K + 1):
+            for j in range(p - 1, k):
+                v = max(best[p - 1, j], pre[k] - pre[j])
+                if v < best[p, k]:
+                    best[p, k] = v
+                    cut[p, k] = j
+    bounds = [K]
+    k = K
+    for p in range(parts, 0, -1):
+        k = int(cut[p, k])
+        bounds.append(k)
+    bounds = bounds[::-1]
+    ranges = [(bounds[i], bounds[i + 1]) for i in range(parts)]
+    ranges += [(K, K)] * (world - parts)
+    return ranges
+
+
+def _gather_rows(dist, arr: np.ndarray, ranges, rank: int, dst: int, device=None) -> None:
+    """Gather the level rows [k0,k1) each rank owns into `arr` on rank `dst` (in place)."""
+    import torch
+
+    world = len(ranges)
+    rows = max(k1 - k0 for k0, k1 in ranges)
+    if rows == 0:
+        return
+    k0, k1 = ranges[rank]
+    per = int(np.prod(arr.shape[1:])) if arr.ndim > 1 else 1
+    buf = np.zeros((rows, per), arr.dtype)
+    buf[: k1 - k0] = arr[k0:k1].reshape(k1 - k0, per)
+    t = torch.from_numpy(buf)
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, out, dst=dst)
+    if rank == dst:
+        for r, (a, b) in enumerate(ranges):
+            if b > a and r != dst:
+                arr[a:b] = out[r][: b - a].cpu().numpy().reshape((b - a,) + arr.shape[1:])
+
+
+def run_time_sharded(case, rank: int, world: int, proc_qc: Callable, proc_oa: Callable,
+                     dist=None, dst: int = 0, device=None, ranges=None):
+    """QC then OA of one time period, levels sharded over `world` ranks.
+
+    proc_qc(case, k_begin, k_end, run_consistency) and proc_oa(case, k_begin, k_end) update
+    `case` in place for their level range.  Between the two stages nothing is exchanged: OA of a
+    level reads only that level's flags.  Returns the ranges; on rank `dst` `case` then holds
+    every level (fields and flags), elsewhere only the rank's own range is valid.
+    """
+    ranges = plan_levels(level_costs(case), world) if ranges is None else ranges
+    k0, k1 = ranges[rank]
+    if k1 > k0:
+        proc_qc(case, k0, k1, True)
+        proc_oa(case, k0, k1)
+    if world > 1:
+        assert dist is not None, "world > 1 needs torch.distributed"
+        for nm in FIELDS3 + FLAGS3:
+            _gather_rows(dist, getattr(case, nm), ranges, rank, dst, device)
+        # slp / qc_slp belong to the surface level: ship them from its owner
+        import torch
+        owner = next(r for r, (a, b) in enumerate(ranges) if a <= 0 < b)
+        if owner != dst:
+            for nm in ("slp", "qc_slp"):
+                a = getattr(case, nm)
+                t = torch.from_numpy(a)
+                if device is not None:
+                    t = t.to(device)
+                if rank == owner:
+                    dist.send(t, dst=dst)
+                elif rank == dst:
+                    dist.recv(t, src=owner)
+                    a[...] = t.cpu().numpy()
+    return ranges
