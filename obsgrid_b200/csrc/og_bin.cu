@@ -19,6 +19,7 @@ namespace {
 
 constexpr int BIN_THREADS = 256;
 constexpr int SORT_CAP = 8192;       // cell lists up to this length are sorted in shared memory
+constexpr int NB_MAX = 4096;         // value buckets of the long-list sorter
 
 struct BinDev {
     const BinSlab* slabs;
@@ -186,19 +187,92 @@ __global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A, int nc
         }
         for (int t = tid; t < L; t += BIN_THREADS) out[t] = s_key[t];
     } else {
-        // longer than the shared-memory sorter: rank by counting against shared-memory tiles
-        for (int t0 = 0; t0 < L; t0 += BIN_THREADS) {
-            const int t = t0 + tid;
-            const int key = (t < L) ? in[t] : 0x7fffffff;
-            int rank = 0;
-            for (int b0 = 0; b0 < L; b0 += SORT_CAP) {
-                const int bn = min(SORT_CAP, L - b0);
+        // Longer than the shared-memory sorter: bucket the keys by value (ob indices are spread
+        // evenly, whatever the stations' positions), then sort every bucket in shared memory.
+        __shared__ int s_hist[NB_MAX + 1];
+        __shared__ int s_red[BIN_THREADS / 32];
+        int kmax = 0;
+        for (int t = tid; t < L; t += BIN_THREADS) kmax = max(kmax, in[t]);
+        for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        if ((tid & 31) == 0) s_red[tid >> 5] = kmax;
+        __syncthreads();
+        kmax = 0;
+        for (int w = 0; w < BIN_THREADS / 32; ++w) kmax = max(kmax, s_red[w]);
+        const int nb = min(NB_MAX, max(1, L / 1024));
+        const long long span = (long long)kmax + 1;
+        for (int q = tid; q <= nb; q += BIN_THREADS) s_hist[q] = 0;
+        __syncthreads();
+        for (int t = tid; t < L; t += BIN_THREADS)
+            atomicAdd(&s_hist[(int)(((long long)in[t] * nb) / span)], 1);
+        __syncthreads();
+        // exclusive prefix over the nb bucket counts (nb <= 4096: 16 per thread)
+        {
+            constexpr int PER = NB_MAX / BIN_THREADS;
+            int v[PER], sum = 0;
+#pragma unroll
+            for (int q = 0; q < PER; ++q) { int i = tid * PER + q; v[q] = (i < nb) ? s_hist[i] : 0; sum += v[q]; }
+            int inc = sum;
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            __syncthreads();
+            if (lane == 31) s_red[warp] = inc;
+            __syncthreads();
+            int woff = 0;
+            for (int w = 0; w < warp; ++w) woff += s_red[w];
+            int run = woff + inc - sum;
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < PER; ++q) { int i = tid * PER + q; if (i < nb) s_hist[i] = run; run += v[q]; }
+            if (tid == BIN_THREADS - 1) s_hist[nb] = L;
+        }
+        __syncthreads();
+        // scatter into the buckets (any order inside a bucket); s_key doubles as the cursors
+        for (int q = tid; q < nb; q += BIN_THREADS) s_key[q] = 0;
+        __syncthreads();
+        for (int t = tid; t < L; t += BIN_THREADS) {
+            const int key = in[t];
+            const int bk = (int)(((long long)key * nb) / span);
+            out[s_hist[bk] + atomicAdd(&s_key[bk], 1)] = key;
+        }
+        __syncthreads();
+        // sort each bucket in place
+        for (int bk = 0; bk < nb; ++bk) {
+            const int b0 = s_hist[bk], m = s_hist[bk + 1] - b0;
+            if (m <= 1) continue;
+            if (m > SORT_CAP) {
+                // cannot happen for evenly spread indices; kept correct: rank by counting into
+                // the (now free) input list, then copy back
+                int* tmp = const_cast<int*>(in) + b0;
+                for (int t = tid; t < m; t += BIN_THREADS) {
+                    const int key = out[b0 + t];
+                    int rank = 0;
+                    for (int j = 0; j < m; ++j) rank += (out[b0 + j] < key) ? 1 : 0;
+                    tmp[rank] = key;
+                }
                 __syncthreads();
-                for (int q = tid; q < bn; q += BIN_THREADS) s_key[q] = in[b0 + q];
+                for (int t = tid; t < m; t += BIN_THREADS) out[b0 + t] = tmp[t];
                 __syncthreads();
-                for (int j = 0; j < bn; ++j) rank += (s_key[j] < key) ? 1 : 0;
+                continue;
             }
-            if (t < L) out[rank] = key;
+            int P = 1;
+            while (P < m) P <<= 1;
+            __syncthreads();
+            for (int t = tid; t < P; t += BIN_THREADS) s_key[t] = (t < m) ? out[b0 + t] : 0x7fffffff;
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int t = tid; t < (P >> 1); t += BIN_THREADS) {
+                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                        const int hi = lo | j;
+                        const bool up = ((lo & k) == 0);
+                        const int a = s_key[lo], b = s_key[hi];
+                        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int t = tid; t < m; t += BIN_THREADS) out[b0 + t] = s_key[t];
         }
     }
 }
@@ -250,6 +324,9 @@ int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, c
         bin_fill_kernel<<<g_ob, 256, 0, st>>>(A);
         ctx->count_launch();
         if (sorted) {
+            // static (bucket table) + dynamic (sort buffer) shared memory exceed the 48 KB default
+            OG_CUDA(cudaFuncSetAttribute(cell_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SORT_CAP * (int)sizeof(int)));
             cell_sort_kernel<<<(unsigned)ncells, BIN_THREADS, SORT_CAP * sizeof(int), st>>>(A, (int)ncells);
             ctx->count_launch();
         }

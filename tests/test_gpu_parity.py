@@ -205,6 +205,30 @@ def test_buddy_check_bit_exact(ctx, oracle, var, pressure, n, dx):
         np.testing.assert_array_equal(u, v, err_msg=nm)
 
 
+def test_buddy_check_long_cell_lists(ctx, oracle):
+    """Dense network on a coarse grid: every cell's candidate list is longer than the
+    shared-memory sorter (8192), so the value-bucket sorter of og_bin.cu orders it; a Gaussian
+    cluster makes the cells very unequal (one CTA per (cell, 128 targets) work item)."""
+    rng = np.random.default_rng(21)
+    iew, jns, n = 40, 40, 30000
+    g = wavy(iew, jns, 6.0, 280.0)
+    x, y = rng_obs(rng, n, iew, jns)
+    k = n // 3
+    x[:k] = np.clip(rng.normal(20, 2.0, k), 2, iew - 1).astype(np.float32)
+    y[:k] = np.clip(rng.normal(22, 2.0, k), 2, jns - 1).astype(np.float32)
+    p = rng.permutation(n); x, y = x[p], y[p]
+    ob = (280 + rng.normal(0, 5, n)).astype(np.float32)
+    ob[rng.random(n) < 0.03] += 30.0
+    z = np.zeros(n, np.float32)
+    ctx.reset_stats()
+    a = oracle.buddy_check(ob, x, y, np.zeros(n, np.int32), z, g, 3, 850.0, 50.0, 1.0, 8.0)
+    b = ctx.buddy_check(ob, x, y, np.zeros(n, np.int32), z, g, 3, 850.0, 50.0, 1.0, 8.0)
+    for nm, u, v in zip(("qc", "aob", "err", "difmax", "buddy_num_final"), a, b):
+        np.testing.assert_array_equal(u, v, err_msg=nm)
+    st = ctx.stats()
+    assert st["buddy_pairs_examined"] < st["buddy_pair_tests"]
+
+
 def test_buddy_relaxation_fixpoint(ctx, oracle):
     """Sparse network where many obs keep exactly two buddies: the x1.2 relaxation of
     qc2_module.F90:327 feeds later stations; the GPU fix-point must equal the serial loop."""
