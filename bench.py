@@ -231,8 +231,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             np.copyto(getattr(hcase, nm), host0[nm])
 
     def step_e2e():
-        ctx.proc_qc(hcase)
-        ctx.proc_oa(hcase)
+        # the reference's driver calls proc_qc then proc_oa for a time period; og_qc_oa_time is
+        # that pair in one call, levels pipelined through the copy engines
+        ctx.proc_qc_oa(hcase, pipeline_groups=args.pipeline_groups)
 
     def barrier():
         if dist is not None:
@@ -378,6 +379,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs[config-1]")
     ap.add_argument("--scale-rh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pipeline-groups", type=int, default=0,
+                    help="level groups of the pipelined e2e call (0: library default)")
     ap.add_argument("--ref-levels", type=int, default=64,
                     help="levels in the CPU sample of proc_oa (bounds the CPU time)")
     ap.add_argument("--ref-qc-levels", type=int, default=8)

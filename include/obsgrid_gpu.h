@@ -234,6 +234,14 @@ int og_oa_time(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
                int k_begin, int k_end);
 int og_qc_time_levels(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p,
                       int k_begin, int k_end, int run_consistency);
+/* proc_qc followed by proc_oa of one time period in one call (driver.F90 calls them back to
+ * back): levels [k_begin,k_end) go up once, in `pipeline_groups` groups of levels (<= 0: the
+ * library chooses); a group's QC + OA runs while the next group is on its way in and the
+ * previous group's analysed fields and flags are on their way out, on separate copy streams.
+ * Levels are independent, so the results are those of og_qc_time_levels followed
+ * by og_oa_time.  Flags and fields are updated in place. */
+int og_qc_oa_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* qp,
+                  const og_oa_params* op, int k_begin, int k_end, int pipeline_groups);
 
 /* ---- resident (device-pointer) API ---------------------------------------------- */
 /* Same semantics as og_qc_time / og_oa_time but every pointer inside `d` is a DEVICE

@@ -172,6 +172,16 @@ class Context:
             check(rc, "og_oa_time")
         return rc
 
+    def proc_qc_oa(self, case, k_begin=0, k_end=None, pipeline_groups=0):
+        """proc_qc then proc_oa of one time period in one pipelined call (og_qc_oa_time)."""
+        d = case.desc()
+        k_end = case.kbu if k_end is None else k_end
+        rc = self._lib.og_qc_oa_time(self._h, C.byref(d), C.byref(case.qc_params),
+                                     C.byref(case.oa_params), k_begin, k_end, pipeline_groups)
+        if rc not in (0, -5):
+            check(rc, "og_qc_oa_time")
+        return rc
+
     # resident variants: `desc` holds device pointers (see bench.py)
     def dev_proc_qc(self, desc, qc_params, k_begin, k_end, run_consistency=True):
         check(self._lib.og_dev_qc_time(self._h, C.byref(desc), C.byref(qc_params), k_begin, k_end,

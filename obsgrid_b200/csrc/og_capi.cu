@@ -39,6 +39,8 @@ extern "C" int og_init(og_ctx** out, int device)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_out, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
         cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&c->d_flag, 64 * sizeof(int)) != cudaSuccess ||
@@ -61,6 +63,9 @@ extern "C" int og_finalize(og_ctx* c)
     for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     cudaFree(c->d_counters); cudaFree(c->d_flag); cudaFreeHost(c->h_pinned_small);
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
+    for (auto& e : c->pipe_events) cudaEventDestroy(e);
+    if (c->stream_in) cudaStreamDestroy(c->stream_in);
+    if (c->stream_out) cudaStreamDestroy(c->stream_out);
     cudaStreamDestroy(c->stream);
     delete c;
     return OG_OK;
@@ -903,6 +908,100 @@ extern "C" int og_qc_time_levels(og_ctx* c, const og_time_desc* d, const og_qc_p
     if (k0 == 0) OG_TRY(download(c, d->qc_slp, T.qc_slp, nrep));
     OG_CUDA(cudaStreamSynchronize(c->stream));
     return OG_OK;
+}
+
+// proc_qc + proc_oa of one time period, levels pipelined through the copy engines.
+extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_params* qp,
+                             const og_oa_params* op, int k0, int k1, int groups)
+{
+    REQUIRE(c && qp && op, "null argument");
+    OG_TRY(check_desc(d, k0, k1, true));
+    if (k1 == k0) return OG_OK;
+    const int nlev = k1 - k0;
+    if (groups <= 0) groups = std::min(6, std::max(1, nlev / 8));
+    groups = std::min(groups, nlev);
+    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep;
+    while (c->pipe_events.size() < (size_t)(2 * groups)) {
+        cudaEvent_t e;
+        OG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->pipe_events.push_back(e);
+    }
+    // device mirrors keep the full [kbu] extent so that row offsets match the host arrays
+    TimeDev T = view_of(d);
+    struct Arr { const char* name; const void* host; void** dev; size_t row; bool sfc_only; bool out; };
+    float *m_t, *m_u, *m_v, *m_rh, *m_slp, *m_x, *m_y, *m_lon, *m_elev, *o_u, *o_v, *o_t, *o_rh, *o_slp;
+    int *q_u, *q_v, *q_t, *q_rh, *q_slp;
+    Arr arrs[] = {
+        {"m.t", d->t, (void**)&m_t, per, false, true},      {"m.u", d->u, (void**)&m_u, per, false, true},
+        {"m.v", d->v, (void**)&m_v, per, false, true},      {"m.rh", d->rh, (void**)&m_rh, per, false, true},
+        {"m.ob_u", d->ob_u, (void**)&o_u, nrep, false, false}, {"m.ob_v", d->ob_v, (void**)&o_v, nrep, false, false},
+        {"m.ob_t", d->ob_t, (void**)&o_t, nrep, false, false}, {"m.ob_rh", d->ob_rh, (void**)&o_rh, nrep, false, false},
+        {"m.qc_u", d->qc_u, (void**)&q_u, nrep, false, true},  {"m.qc_v", d->qc_v, (void**)&q_v, nrep, false, true},
+        {"m.qc_t", d->qc_t, (void**)&q_t, nrep, false, true},  {"m.qc_rh", d->qc_rh, (void**)&q_rh, nrep, false, true},
+        {"m.slp", d->slp, (void**)&m_slp, per, true, true},    {"m.ob_slp", d->ob_slp, (void**)&o_slp, nrep, true, false},
+        {"m.qc_slp", d->qc_slp, (void**)&q_slp, nrep, true, true},
+    };
+    for (Arr& a : arrs)
+        OG_TRY(c->reserve(a.name, std::max<size_t>(a.row * (a.sfc_only ? 1 : d->kbu), 1) * 4, a.dev));
+    OG_TRY(c->reserve_t("m.x", std::max<size_t>(nrep, 1), &m_x));
+    OG_TRY(c->reserve_t("m.y", std::max<size_t>(nrep, 1), &m_y));
+    OG_TRY(c->reserve_t("m.lon", std::max<size_t>(nrep, 1), &m_lon));
+    OG_TRY(c->reserve_t("m.elev", std::max<size_t>(nrep, 1), &m_elev));
+    T.t = m_t; T.u = m_u; T.v = m_v; T.rh = m_rh; T.slp = m_slp;
+    T.xob = m_x; T.yob = m_y; T.lon = m_lon; T.elev = m_elev;
+    T.ob_u = o_u; T.ob_v = o_v; T.ob_t = o_t; T.ob_rh = o_rh; T.ob_slp = o_slp;
+    T.qc_u = q_u; T.qc_v = q_v; T.qc_t = q_t; T.qc_rh = q_rh; T.qc_slp = q_slp;
+
+    // the copy streams must not run ahead of work already queued on the compute stream
+    // (earlier calls may still be reading the mirrors)
+    cudaEvent_t ev0 = c->pipe_events[0];
+    OG_CUDA(cudaEventRecord(ev0, c->stream));
+    OG_CUDA(cudaStreamWaitEvent(c->stream_in, ev0, 0));
+    OG_CUDA(cudaStreamWaitEvent(c->stream_out, ev0, 0));
+    auto h2d = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!bytes) return OG_OK;
+        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream_in));
+        c->stats.h2d_bytes += (int64_t)bytes;
+        return OG_OK;
+    };
+    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!bytes) return OG_OK;
+        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream_out));
+        c->stats.d2h_bytes += (int64_t)bytes;
+        return OG_OK;
+    };
+    OG_TRY(h2d(m_x, d->xob, nrep * 4)); OG_TRY(h2d(m_y, d->yob, nrep * 4));
+    OG_TRY(h2d(m_lon, d->lon, nrep * 4)); OG_TRY(h2d(m_elev, d->elev, nrep * 4));
+    // every group's upload is queued up front: the copy engine streams them in while the
+    // host is busy launching (and, inside the stages, briefly waiting on) the compute
+    std::vector<int> gb(groups + 1);
+    for (int g = 0; g <= groups; ++g) gb[g] = k0 + (int)((long long)nlev * g / groups);
+    for (int g = 0; g < groups; ++g) {
+        const int a0 = gb[g], a1 = gb[g + 1];
+        for (Arr& a : arrs) {
+            if (a.sfc_only) { if (a0 == 0) OG_TRY(h2d(*a.dev, a.host, a.row * 4)); continue; }
+            OG_TRY(h2d((char*)*a.dev + a.row * a0 * 4, (const char*)a.host + a.row * a0 * 4, a.row * (a1 - a0) * 4));
+        }
+        OG_CUDA(cudaEventRecord(c->pipe_events[2 * g], c->stream_in));
+    }
+    int rc_radius = OG_OK;
+    for (int g = 0; g < groups; ++g) {
+        const int a0 = gb[g], a1 = gb[g + 1];
+        OG_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_events[2 * g], 0));
+        OG_TRY(qc_time_core(c, T, qp, a0, a1, 1));
+        int rc = oa_time_core(c, T, op, a0, a1);
+        if (rc == OG_ERR_RADIUS) rc_radius = rc; else if (rc != OG_OK) return rc;
+        OG_CUDA(cudaEventRecord(c->pipe_events[2 * g + 1], c->stream));
+        OG_CUDA(cudaStreamWaitEvent(c->stream_out, c->pipe_events[2 * g + 1], 0));
+        for (Arr& a : arrs) {
+            if (!a.out) continue;
+            if (a.sfc_only) { if (a0 == 0) OG_TRY(d2h(const_cast<void*>(a.host), *a.dev, a.row * 4)); continue; }
+            OG_TRY(d2h((char*)const_cast<void*>(a.host) + a.row * a0 * 4, (const char*)*a.dev + a.row * a0 * 4, a.row * (a1 - a0) * 4));
+        }
+    }
+    OG_CUDA(cudaStreamSynchronize(c->stream_out));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return rc_radius;
 }
 
 extern "C" int og_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p)

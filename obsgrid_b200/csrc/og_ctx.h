@@ -40,6 +40,8 @@ struct og_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;   // copy streams of og_qc_oa_time
+    std::vector<cudaEvent_t> pipe_events;
     og_stats stats{};
     int counting = 0;
     unsigned long long* d_counters = nullptr;   // [0] updates, [1] candidates

@@ -297,6 +297,24 @@ def test_time_small(ctx, oracle, scale_rh, sfc_mult):
     _compare_time(gpu, cpu)
 
 
+@pytest.mark.parametrize("groups", [0, 1, 3, 5])
+def test_fused_pipelined_time_equals_the_two_stage_calls(ctx, groups):
+    """og_qc_oa_time (levels pipelined through the copy engines) == og_qc_time_levels followed
+    by og_oa_time, bit for bit, for any grouping of the levels."""
+    base = synth.small_case(iew=64, jns=48, kbu=9, n_sfc=500, n_snd=120, seed=5, radii=(6, 4, 2))
+    a, b = base.copy(), base.copy()
+    ctx.proc_qc(a); ctx.proc_oa(a)
+    ctx.proc_qc_oa(b, pipeline_groups=groups)
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
+        np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=nm)
+    c = base.copy()
+    ctx.proc_qc_oa(c, 2, 7, pipeline_groups=2)          # a level sub-range leaves the rest alone
+    for nm in ("t", "u", "qc_t"):
+        np.testing.assert_array_equal(getattr(c, nm)[2:7], getattr(a, nm)[2:7], err_msg=nm)
+        np.testing.assert_array_equal(getattr(c, nm)[:2], getattr(base, nm)[:2], err_msg=nm)
+        np.testing.assert_array_equal(getattr(c, nm)[7:], getattr(base, nm)[7:], err_msg=nm)
+
+
 def test_time_level_sharding_is_exact(ctx):
     """Levels are independent: ranges and variable masks compose to the full run."""
     base = synth.small_case(iew=50, jns=44, kbu=7, n_sfc=300, n_snd=100, radii=(5, 3))
