@@ -918,7 +918,7 @@ extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_param
     OG_TRY(check_desc(d, k0, k1, true));
     if (k1 == k0) return OG_OK;
     const int nlev = k1 - k0;
-    if (groups <= 0) groups = std::min(6, std::max(1, nlev / 8));
+    if (groups <= 0) groups = (nlev >= 16) ? 2 : 1;   // each group costs ~1 ms of fixed work
     groups = std::min(groups, nlev);
     const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep;
     while (c->pipe_events.size() < (size_t)(2 * groups)) {
