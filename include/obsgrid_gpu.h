@@ -243,6 +243,24 @@ int og_qc_time_levels(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p,
 int og_qc_oa_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* qp,
                   const og_oa_params* op, int k_begin, int k_end, int pipeline_groups);
 
+/* ---- asynchronous per-time API: several time periods in flight ------------------------ */
+/* A run over many analysis times (cfg3: 16, cfg4: 24) keeps the copy engines and the SMs busy
+ * at once: while time t computes, time t+1 is on its way in and time t-1 on its way out.
+ * Each of the OG_SLOTS slots owns a device mirror of one time period.
+ *   og_time_upload   queues the H2D copies of levels [k_begin,k_end) of `d` (returns at once;
+ *                    waits, on the device, for the slot's previous download)
+ *   og_time_compute  proc_qc + proc_oa on the slot's mirror (the host arrays are not touched)
+ *   og_time_download queues the D2H copies of the analysed fields and flags into `d_out`
+ *                    (may be `d` itself for in-place semantics, or separate arrays)
+ *   og_time_wait     blocks until the slot's download has landed
+ * Host arrays should be pinned (og_host_alloc) for the copies to overlap. */
+#define OG_SLOTS 4
+int og_time_upload(og_ctx* ctx, const og_time_desc* d, int k_begin, int k_end, int slot);
+int og_time_compute(og_ctx* ctx, const og_time_desc* d, const og_qc_params* qp,
+                    const og_oa_params* op, int k_begin, int k_end, int slot);
+int og_time_download(og_ctx* ctx, const og_time_desc* d_out, int k_begin, int k_end, int slot);
+int og_time_wait(og_ctx* ctx, int slot);
+
 /* ---- resident (device-pointer) API ---------------------------------------------- */
 /* Same semantics as og_qc_time / og_oa_time but every pointer inside `d` is a DEVICE
  * pointer on the context's device and nothing is copied; used to time the kernels with

@@ -109,6 +109,11 @@ SIGNATURES = {
     "og_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgOaParams), C.c_int, C.c_int]),
     "og_qc_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.POINTER(OgOaParams),
                                 C.c_int, C.c_int, C.c_int]),
+    "og_time_upload": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.c_int, C.c_int, C.c_int]),
+    "og_time_compute": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.POINTER(OgOaParams),
+                                  C.c_int, C.c_int, C.c_int]),
+    "og_time_download": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.c_int, C.c_int, C.c_int]),
+    "og_time_wait": (C.c_int, [_vp, C.c_int]),
     "og_qc_time_levels": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.c_int,
                                     C.c_int, C.c_int]),
     "og_dev_qc_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.c_int,

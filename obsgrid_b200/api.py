@@ -182,6 +182,30 @@ class Context:
             check(rc, "og_qc_oa_time")
         return rc
 
+    # asynchronous per-time API: several time periods in flight (og_time_*)
+    def time_upload(self, case, slot, k_begin=0, k_end=None):
+        d = case.desc()
+        check(self._lib.og_time_upload(self._h, C.byref(d), k_begin,
+                                       case.kbu if k_end is None else k_end, slot), "og_time_upload")
+
+    def time_compute(self, case, slot, k_begin=0, k_end=None):
+        d = case.desc()
+        rc = self._lib.og_time_compute(self._h, C.byref(d), C.byref(case.qc_params),
+                                       C.byref(case.oa_params), k_begin,
+                                       case.kbu if k_end is None else k_end, slot)
+        if rc not in (0, -5):
+            check(rc, "og_time_compute")
+        return rc
+
+    def time_download(self, case_out, slot, k_begin=0, k_end=None):
+        d = case_out.desc()
+        check(self._lib.og_time_download(self._h, C.byref(d), k_begin,
+                                         case_out.kbu if k_end is None else k_end, slot),
+              "og_time_download")
+
+    def time_wait(self, slot):
+        check(self._lib.og_time_wait(self._h, slot), "og_time_wait")
+
     # resident variants: `desc` holds device pointers (see bench.py)
     def dev_proc_qc(self, desc, qc_params, k_begin, k_end, run_consistency=True):
         check(self._lib.og_dev_qc_time(self._h, C.byref(desc), C.byref(qc_params), k_begin, k_end,

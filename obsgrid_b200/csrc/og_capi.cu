@@ -64,6 +64,11 @@ extern "C" int og_finalize(og_ctx* c)
     cudaFree(c->d_counters); cudaFree(c->d_flag); cudaFreeHost(c->h_pinned_small);
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
     for (auto& e : c->pipe_events) cudaEventDestroy(e);
+    for (auto& sl : c->slots) {
+        if (sl.up) cudaEventDestroy(sl.up);
+        if (sl.comp) cudaEventDestroy(sl.comp);
+        if (sl.down) cudaEventDestroy(sl.down);
+    }
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
     if (c->stream_out) cudaStreamDestroy(c->stream_out);
     cudaStreamDestroy(c->stream);
@@ -1002,6 +1007,148 @@ extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_param
     OG_CUDA(cudaStreamSynchronize(c->stream_out));
     OG_CUDA(cudaStreamSynchronize(c->stream));
     return rc_radius;
+}
+
+// ---- asynchronous per-time API ------------------------------------------------------------
+namespace {
+
+struct MirrorArr { const char* name; size_t row; bool sfc_only; bool out; };
+const MirrorArr kMirror[] = {
+    {"t", 0, false, true},     {"u", 0, false, true},     {"v", 0, false, true},     {"rh", 0, false, true},
+    {"ob_u", 1, false, false}, {"ob_v", 1, false, false}, {"ob_t", 1, false, false}, {"ob_rh", 1, false, false},
+    {"qc_u", 1, false, true},  {"qc_v", 1, false, true},  {"qc_t", 1, false, true},  {"qc_rh", 1, false, true},
+    {"slp", 0, true, true},    {"ob_slp", 1, true, false}, {"qc_slp", 1, true, true},
+};
+constexpr int kNMirror = sizeof(kMirror) / sizeof(kMirror[0]);
+
+void* host_of(const og_time_desc* d, int i)
+{
+    void* h[] = {d->t, d->u, d->v, d->rh, (void*)d->ob_u, (void*)d->ob_v, (void*)d->ob_t, (void*)d->ob_rh,
+                 d->qc_u, d->qc_v, d->qc_t, d->qc_rh, d->slp, (void*)d->ob_slp, d->qc_slp};
+    return h[i];
+}
+
+// Device mirror of one slot (full [kbu] extent so that row offsets match the host arrays).
+int slot_mirror(og_ctx* c, const og_time_desc* d, int slot, TimeDev& T, void* dev[kNMirror])
+{
+    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep;
+    char name[32];
+    for (int i = 0; i < kNMirror; ++i) {
+        const size_t row = kMirror[i].row ? nrep : per;
+        snprintf(name, sizeof name, "s%d.%s", slot, kMirror[i].name);
+        OG_TRY(c->reserve(name, std::max<size_t>(row * (kMirror[i].sfc_only ? 1 : d->kbu), 1) * 4, &dev[i]));
+    }
+    float* f4[4];
+    const char* tn[4] = {"x", "y", "lon", "elev"};
+    for (int i = 0; i < 4; ++i) {
+        snprintf(name, sizeof name, "s%d.%s", slot, tn[i]);
+        OG_TRY(c->reserve_t(name, std::max<size_t>(nrep, 1), &f4[i]));
+    }
+    T = view_of(d);
+    T.t = (float*)dev[0]; T.u = (float*)dev[1]; T.v = (float*)dev[2]; T.rh = (float*)dev[3];
+    T.ob_u = (float*)dev[4]; T.ob_v = (float*)dev[5]; T.ob_t = (float*)dev[6]; T.ob_rh = (float*)dev[7];
+    T.qc_u = (int*)dev[8]; T.qc_v = (int*)dev[9]; T.qc_t = (int*)dev[10]; T.qc_rh = (int*)dev[11];
+    T.slp = (float*)dev[12]; T.ob_slp = (float*)dev[13]; T.qc_slp = (int*)dev[14];
+    T.xob = f4[0]; T.yob = f4[1]; T.lon = f4[2]; T.elev = f4[3];
+    return OG_OK;
+}
+
+int slot_events(og_ctx* c, int slot)
+{
+    og_ctx::Slot& s = c->slots[slot];
+    if (!s.up) {
+        OG_CUDA(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming));
+        OG_CUDA(cudaEventCreateWithFlags(&s.comp, cudaEventDisableTiming));
+        OG_CUDA(cudaEventCreateWithFlags(&s.down, cudaEventDisableTiming));
+    }
+    return OG_OK;
+}
+
+} // namespace
+
+extern "C" int og_time_upload(og_ctx* c, const og_time_desc* d, int k0, int k1, int slot)
+{
+    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
+    OG_TRY(check_desc(d, k0, k1, true));
+    OG_TRY(slot_events(c, slot));
+    TimeDev T; void* dev[kNMirror];
+    OG_TRY(slot_mirror(c, d, slot, T, dev));
+    og_ctx::Slot& s = c->slots[slot];
+    // the mirror may still be read by the slot's previous compute / download
+    OG_CUDA(cudaEventRecord(s.up, c->stream));
+    OG_CUDA(cudaStreamWaitEvent(c->stream_in, s.up, 0));
+    if (s.down_pending) OG_CUDA(cudaStreamWaitEvent(c->stream_in, s.down, 0));
+    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
+    auto h2d = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!bytes) return OG_OK;
+        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream_in));
+        c->stats.h2d_bytes += (int64_t)bytes;
+        return OG_OK;
+    };
+    OG_TRY(h2d((void*)T.xob, d->xob, nrep * 4)); OG_TRY(h2d((void*)T.yob, d->yob, nrep * 4));
+    OG_TRY(h2d((void*)T.lon, d->lon, nrep * 4)); OG_TRY(h2d((void*)T.elev, d->elev, nrep * 4));
+    for (int i = 0; i < kNMirror; ++i) {
+        const size_t row = kMirror[i].row ? nrep : per;
+        if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(h2d(dev[i], host_of(d, i), row * 4)); continue; }
+        OG_TRY(h2d((char*)dev[i] + row * k0 * 4, (const char*)host_of(d, i) + row * k0 * 4, row * nlev * 4));
+    }
+    OG_CUDA(cudaEventRecord(s.up, c->stream_in));
+    return OG_OK;
+}
+
+extern "C" int og_time_compute(og_ctx* c, const og_time_desc* d, const og_qc_params* qp,
+                               const og_oa_params* op, int k0, int k1, int slot)
+{
+    REQUIRE(c && qp && op && slot >= 0 && slot < OG_SLOTS, "bad argument");
+    OG_TRY(check_desc(d, k0, k1, true));
+    OG_TRY(slot_events(c, slot));
+    TimeDev T; void* dev[kNMirror];
+    OG_TRY(slot_mirror(c, d, slot, T, dev));
+    og_ctx::Slot& s = c->slots[slot];
+    OG_CUDA(cudaStreamWaitEvent(c->stream, s.up, 0));
+    int rc_radius = OG_OK;
+    if (k1 > k0) {
+        OG_TRY(qc_time_core(c, T, qp, k0, k1, 1));
+        int rc = oa_time_core(c, T, op, k0, k1);
+        if (rc == OG_ERR_RADIUS) rc_radius = rc; else if (rc != OG_OK) return rc;
+    }
+    OG_CUDA(cudaEventRecord(s.comp, c->stream));
+    return rc_radius;
+}
+
+extern "C" int og_time_download(og_ctx* c, const og_time_desc* d, int k0, int k1, int slot)
+{
+    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
+    OG_TRY(check_desc(d, k0, k1, true));
+    OG_TRY(slot_events(c, slot));
+    TimeDev T; void* dev[kNMirror];
+    OG_TRY(slot_mirror(c, d, slot, T, dev));
+    og_ctx::Slot& s = c->slots[slot];
+    OG_CUDA(cudaStreamWaitEvent(c->stream_out, s.comp, 0));
+    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
+    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!bytes) return OG_OK;
+        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream_out));
+        c->stats.d2h_bytes += (int64_t)bytes;
+        return OG_OK;
+    };
+    for (int i = 0; i < kNMirror; ++i) {
+        if (!kMirror[i].out) continue;
+        const size_t row = kMirror[i].row ? nrep : per;
+        if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(d2h(host_of(d, i), dev[i], row * 4)); continue; }
+        OG_TRY(d2h((char*)host_of(d, i) + row * k0 * 4, (const char*)dev[i] + row * k0 * 4, row * nlev * 4));
+    }
+    OG_CUDA(cudaEventRecord(s.down, c->stream_out));
+    s.down_pending = true;
+    return OG_OK;
+}
+
+extern "C" int og_time_wait(og_ctx* c, int slot)
+{
+    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
+    og_ctx::Slot& s = c->slots[slot];
+    if (s.down_pending) { OG_CUDA(cudaEventSynchronize(s.down)); s.down_pending = false; }
+    return OG_OK;
 }
 
 extern "C" int og_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p)

@@ -42,6 +42,8 @@ struct og_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;   // copy streams of og_qc_oa_time
     std::vector<cudaEvent_t> pipe_events;
+    struct Slot { cudaEvent_t up = nullptr, comp = nullptr, down = nullptr; bool down_pending = false; };
+    Slot slots[OG_SLOTS];
     og_stats stats{};
     int counting = 0;
     unsigned long long* d_counters = nullptr;   // [0] updates, [1] candidates

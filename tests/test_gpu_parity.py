@@ -315,6 +315,31 @@ def test_fused_pipelined_time_equals_the_two_stage_calls(ctx, groups):
         np.testing.assert_array_equal(getattr(c, nm)[7:], getattr(base, nm)[7:], err_msg=nm)
 
 
+def test_async_time_slots_pipeline(ctx):
+    """Several time periods in flight through og_time_upload/_compute/_download/_wait give the
+    results of the blocking calls; inputs are left untouched when the output arrays differ."""
+    times = [synth.small_case(iew=48, jns=40, kbu=6, n_sfc=300, n_snd=80, seed=30 + t, radii=(5, 3))
+             for t in range(5)]
+    want = [c.copy() for c in times]
+    for c in want:
+        ctx.proc_qc(c); ctx.proc_oa(c)
+    pristine = [c.copy() for c in times]
+    outs = [c.copy() for c in times]
+    NS = 3
+    ctx.time_upload(times[0], 0)
+    for i, c in enumerate(times):
+        if i + 1 < len(times):
+            ctx.time_upload(times[i + 1], (i + 1) % NS)
+        ctx.time_compute(c, i % NS)
+        ctx.time_download(outs[i], i % NS)
+    for s in range(NS):
+        ctx.time_wait(s)
+    for i in range(len(times)):
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
+            np.testing.assert_array_equal(getattr(outs[i], nm), getattr(want[i], nm), err_msg=f"{i}:{nm}")
+            np.testing.assert_array_equal(getattr(times[i], nm), getattr(pristine[i], nm))
+
+
 def test_time_level_sharding_is_exact(ctx):
     """Levels are independent: ranges and variable masks compose to the full run."""
     base = synth.small_case(iew=50, jns=44, kbu=7, n_sfc=300, n_snd=100, radii=(5, 3))
