@@ -11,8 +11,10 @@ second (pairs with d2 < R2, oa_module.F90:553/616); buddy-check obs/s is reporte
 
   value  : inputs resident in HBM (og_dev_qc_time + og_dev_oa_time), CUDA events on the
            library's stream, max over ranks; updates per step / step time.
-  e2e    : the same step through og_qc_time_levels + og_oa_time with pinned HOST arrays
-           (H2D of fields + observation table and D2H of analysed fields + flags inside).
+  e2e    : the same step through the asynchronous per-time C ABI with pinned HOST arrays
+           (og_time_upload / _compute / _download / _wait): every step uploads its inputs and
+           reads the analysed fields + flags back; up to 3 time periods are in flight.  The
+           blocking one-call form (og_qc_oa_time) is timed beside it (e2e.blocking_call_ms).
   N > 1  : one process per GPU (torchrun); every rank analyses its own time of the same
            configuration (times are independent) -> weak scaling, no collective on
            the data path; torch.distributed only provides the barrier and the max-reduce.
@@ -180,9 +182,37 @@ def cpu_baseline(args, case0):
 
 
 # ------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pin this process to the CPUs next to its GPU (pinned staging memory then lands on the
+    GPU's NUMA node).  Best effort: returns what was done for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i",
+                              str(local_rank)], capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        cpus = Path(f"/sys/bus/pci/devices/{bus}/local_cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+            return f"cpus {cpus}"
+    except Exception as e:          # noqa: BLE001
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def run_gpu(args, rank: int, world: int, local_rank: int):
     import torch
     from obsgrid_b200.api import Context
+
+    # stdout carries exactly one JSON line; NCCL and friends print banners there
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else "not needed (1 process)"
 
     dist = None
     if world > 1:
@@ -373,7 +403,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                        "scale_cressman_rh_decreases": bool(case.oa_params.scale_cressman_rh_decreases),
                        "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
                              "pristine copy before every step",
-                       "parallelism": f"{world} x independent analysis time"},
+                       "parallelism": f"{world} x independent analysis time",
+                       "cpu_affinity": affinity},
             "e2e": {"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "api": "og_time_upload/_compute/_download/_wait, 3 time periods in flight, pinned host arrays",
                     "blocking_call_ms": e2e_blocking_ms,
@@ -391,7 +422,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                           "buddy_obs_per_s": g_bobs / (qc_ms * 1e-3),
                           "buddy_pair_tests_per_s": g_pairs / (qc_ms * 1e-3)},
         }
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
