@@ -304,15 +304,16 @@ int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, c
     OG_CUDA(cudaMemsetAsync(A.cell_start, 0, sizeof(int) * ((size_t)ncells + 1), st));
     int list_total = 0;
     if (ns > 0 && max_n > 0 && ncells > 0) {
-        OG_CUDA(cudaMemcpyAsync(d_slabs, slabs.data(), sizeof(BinSlab) * ns, cudaMemcpyHostToDevice, st));
+        OG_TRY(ctx->put_small(d_slabs, slabs.data(), sizeof(BinSlab) * ns));
         OG_CUDA(cudaMemsetAsync(A.cell_cursor, 0, sizeof(int) * ((size_t)ncells + 1), st));
         dim3 g_ob((max_n + 255) / 256, ns);
         bin_count_kernel<<<g_ob, 256, 0, st>>>(A);
         cell_prefix_kernel<<<1, 1024, 0, st>>>(A.cell_count, A.cell_start, (int)ncells, ctx->d_flag);
         ctx->count_launch(2);
-        OG_CUDA(cudaMemcpyAsync(ctx->h_pinned_small, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        void* h_total = nullptr;
+        OG_TRY(ctx->get_small(ctx->d_flag, sizeof(int), &h_total));
         OG_CUDA(cudaStreamSynchronize(st));
-        list_total = ctx->h_pinned_small[0];
+        list_total = *(const int*)h_total;
         if (list_total < 0) { set_error("cell lists overflow 2^31 entries; split the batch"); return OG_ERR_INVALID; }
     }
     const size_t nlist = (size_t)std::max(list_total, 1);

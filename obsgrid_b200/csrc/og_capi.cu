@@ -62,6 +62,7 @@ extern "C" int og_finalize(og_ctx* c)
     for (auto& kv : c->bufs) if (kv.second.p) cudaFree(kv.second.p);
     for (auto& t : c->timers) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     cudaFree(c->d_counters); cudaFree(c->d_flag); cudaFreeHost(c->h_pinned_small);
+    if (c->arena) cudaFreeHost(c->arena);
     cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
     for (auto& e : c->pipe_events) cudaEventDestroy(e);
     for (auto& sl : c->slots) {
@@ -578,15 +579,17 @@ int run_selection(og_ctx* c, const TimeDev& T, std::vector<SelSlab>& sel, bool q
     n_out.assign(ns, 0);
     total = 0;
     if (T.nrep == 0) return OG_OK;
-    OG_CUDA(cudaMemcpyAsync(d_sel, sel.data(), sizeof(SelSlab) * ns, cudaMemcpyHostToDevice, c->stream));
+    OG_TRY(c->put_small(d_sel, sel.data(), sizeof(SelSlab) * ns));
     dim3 g(nchunk, ns);
     sel_count_kernel<<<g, SEL_THREADS, 0, c->stream>>>(A);
     sel_scan_kernel<<<ns, 1024, 0, c->stream>>>(A);
     c->count_launch(2);
-    OG_CUDA(cudaMemcpyAsync(n_out.data(), A.slab_n, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
+    void* h_n = nullptr;
+    OG_TRY(c->get_small(A.slab_n, sizeof(int) * ns, &h_n));
     OG_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(n_out.data(), h_n, sizeof(int) * ns);
     for (int s = 0; s < ns; ++s) { sel[s].ob_off = total; total += n_out[s]; }
-    OG_CUDA(cudaMemcpyAsync(d_sel, sel.data(), sizeof(SelSlab) * ns, cudaMemcpyHostToDevice, c->stream));
+    OG_TRY(c->put_small(d_sel, sel.data(), sizeof(SelSlab) * ns));
     const size_t tot = (size_t)std::max(total, 1);
     OG_TRY(c->reserve_t("sel.x", tot, &A.ox));
     OG_TRY(c->reserve_t("sel.y", tot, &A.oy));
@@ -620,8 +623,9 @@ int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int
     OG_TRY(c->reserve_t("oa.b_v", per * nlev, &b_v));
     const size_t lo = per * (size_t)k0;
     OG_TRY(transpose_levels(c, T.t + lo, w_t, jns, iew, nlev));
-    OG_TRY(transpose_levels(c, T.u + lo, w_u, jns, iew, nlev));
-    OG_TRY(transpose_levels(c, T.v + lo, w_v, jns, iew, nlev));
+    // u, v twice: the pre-analysis winds of each level feed the banana scheme (proc_oa.F90:376-386)
+    OG_TRY(transpose_levels(c, T.u + lo, w_u, jns, iew, nlev, b_u));
+    OG_TRY(transpose_levels(c, T.v + lo, w_v, jns, iew, nlev, b_v));
     OG_TRY(transpose_levels(c, T.rh + lo, w_rh, jns, iew, nlev));
     const bool has_sfc = (k0 == 0);
     if (has_sfc) OG_TRY(transpose_levels(c, T.slp, w_slp, jns, iew, 1));
@@ -629,9 +633,6 @@ int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int
         clamp_fg_rh_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_rh, iew, jns, nlev);
         c->count_launch();
     }
-    // pre-analysis winds of each level for the banana scheme (proc_oa.F90:376-386)
-    OG_CUDA(cudaMemcpyAsync(b_u, w_u, per * nlev * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
-    OG_CUDA(cudaMemcpyAsync(b_v, w_v, per * nlev * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
 
     // slabs in the reference's loop order: level, then UU VV TT RH PMSL
     const int qc_max = std::min(OG_FAILS_ERROR_MAX, OG_FAILS_BUDDY_CHECK); // proc_oa.F90:462
@@ -773,12 +774,10 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
         if (max_n > 0) {
             PutSlab* d_put;
             OG_TRY(c->reserve_t("qc.put", puts.size(), &d_put));
-            OG_CUDA(cudaMemcpyAsync(d_put, puts.data(), sizeof(PutSlab) * puts.size(), cudaMemcpyHostToDevice, c->stream));
+            OG_TRY(c->put_small(d_put, puts.data(), sizeof(PutSlab) * puts.size()));
             dim3 g(nblk((size_t)max_n), (unsigned)puts.size());
             put_kernel<<<g, 256, 0, c->stream>>>(d_put, SA.oqc, SA.oidx);
             c->count_launch();
-            // `puts` is consumed by the copy engine before it goes out of scope
-            OG_CUDA(cudaStreamSynchronize(c->stream));
         }
     }
     if (run_consistency && T.nrep > 0) {

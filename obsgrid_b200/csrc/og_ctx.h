@@ -70,6 +70,17 @@ struct og_ctx {
         return rc;
     }
     void count_launch(int n = 1) { stats.kernel_launches += n; }
+
+    // Small host<->device transfers on the compute stream go through a mapped pinned arena and
+    // a copy kernel, NOT the DMA engines: a 4-byte readback queued behind another time period's
+    // 180 MB download on the (in-order) D2H engine would stall the compute stream for
+    // milliseconds (og_time_* pipeline).  put_small: the source may be reused on return.
+    // get_small: *host points into the arena, valid after the next stream synchronisation.
+    unsigned char* arena = nullptr;
+    size_t arena_size = 0, arena_pos = 0;
+    int arena_take(size_t bytes, unsigned char** p);
+    int put_small(void* dev_dst, const void* host_src, size_t bytes);
+    int get_small(const void* dev_src, size_t bytes, void** host);
 };
 
 namespace og {
@@ -171,6 +182,6 @@ int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatc
 int fp32_peak(og_ctx* ctx, double* lane_ops_per_s);
 // (jns,iew) y-fastest <-> (iew,jns) x-fastest for nlev stacked levels
 int transpose_levels(og_ctx* ctx, const float* src, float* dst, int rows_fast, int cols_slow,
-                     int nlev);
+                     int nlev, float* dst2 = nullptr);   // dst2: optional second copy of the result
 
 } // namespace og

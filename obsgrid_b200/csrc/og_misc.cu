@@ -21,7 +21,7 @@ const char* last_error() { return g_err; }
 
 // ---- tiled transpose: src is [nlev][slow][fast] -> dst [nlev][fast][slow] --------------
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
-                                 int nfast, int nslow)
+                                 float* __restrict__ dst2, int nfast, int nslow)
 {
     __shared__ float tile[32][33];
     const size_t lev = (size_t)blockIdx.z * (size_t)nfast * (size_t)nslow;
@@ -34,15 +34,20 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
     int s2 = blockIdx.y * 32 + threadIdx.x;
     for (int r = threadIdx.y; r < 32; r += 8) {
         int f2 = blockIdx.x * 32 + r;
-        if (f2 < nfast && s2 < nslow) dst[lev + (size_t)f2 * nslow + s2] = tile[threadIdx.x][r];
+        if (f2 < nfast && s2 < nslow) {
+            const float v = tile[threadIdx.x][r];
+            dst[lev + (size_t)f2 * nslow + s2] = v;
+            if (dst2) dst2[lev + (size_t)f2 * nslow + s2] = v;
+        }
     }
 }
 
-int transpose_levels(og_ctx* ctx, const float* src, float* dst, int nfast, int nslow, int nlev)
+int transpose_levels(og_ctx* ctx, const float* src, float* dst, int nfast, int nslow, int nlev,
+                     float* dst2)
 {
     if (nlev <= 0) return OG_OK;
     dim3 blk(32, 8), grd((nfast + 31) / 32, (nslow + 31) / 32, nlev);
-    transpose_kernel<<<grd, blk, 0, ctx->stream>>>(src, dst, nfast, nslow);
+    transpose_kernel<<<grd, blk, 0, ctx->stream>>>(src, dst, dst2, nfast, nslow);
     ctx->count_launch();
     OG_CUDA(cudaGetLastError());
     return OG_OK;
@@ -149,6 +154,68 @@ int og_ctx::reserve(const char* name, size_t bytes, void** out)
         b.cap = want;
     }
     *out = b.p;
+    return OG_OK;
+}
+
+namespace og {
+__global__ void copy_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n)
+{
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) dst[q] = src[q];
+}
+} // namespace og
+
+int og_ctx::arena_take(size_t bytes, unsigned char** p)
+{
+    if (!arena) {
+        arena_size = 8u << 20;
+        if (cudaHostAlloc((void**)&arena, arena_size, cudaHostAllocMapped) != cudaSuccess) {
+            og::set_error("cudaHostAlloc(staging arena) failed");
+            arena = nullptr;
+            return OG_ERR_ALLOC;
+        }
+        arena_pos = 0;
+    }
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes > arena_size / 2) { og::set_error("small transfer of %zu bytes exceeds the staging arena", bytes); return OG_ERR_INVALID; }
+    if (arena_pos + bytes > arena_size) {
+        // wrap: everything handed out so far has been consumed once the stream is idle
+        OG_CUDA(cudaStreamSynchronize(stream));
+        arena_pos = 0;
+    }
+    *p = arena + arena_pos;
+    arena_pos += bytes;
+    return OG_OK;
+}
+
+int og_ctx::put_small(void* dev_dst, const void* host_src, size_t bytes)
+{
+    if (!bytes) return OG_OK;
+    if (bytes > (1u << 20) || (bytes & 3)) {      // large or odd: the DMA engine is the right tool
+        OG_CUDA(cudaMemcpyAsync(dev_dst, host_src, bytes, cudaMemcpyHostToDevice, stream));
+        return OG_OK;
+    }
+    unsigned char* a;
+    OG_TRY(arena_take(bytes, &a));
+    memcpy(a, host_src, bytes);
+    const size_t n = bytes / 4;
+    og::copy_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((uint32_t*)dev_dst, (const uint32_t*)a, n);
+    count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+int og_ctx::get_small(const void* dev_src, size_t bytes, void** host)
+{
+    unsigned char* a;
+    OG_TRY(arena_take(std::max<size_t>(bytes, 4), &a));
+    *host = a;
+    if (!bytes) return OG_OK;
+    if (bytes & 3) { og::set_error("get_small: size not a multiple of 4"); return OG_ERR_INVALID; }
+    const size_t n = bytes / 4;
+    og::copy_words_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((uint32_t*)a, (const uint32_t*)dev_src, n);
+    count_launch();
+    OG_CUDA(cudaGetLastError());
     return OG_OK;
 }
 

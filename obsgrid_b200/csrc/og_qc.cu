@@ -456,7 +456,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     A.d_aob = b.aob; A.d_err_max = b.err_max; A.d_thr_max = b.thr_max;
     A.d_err_buddy = b.err_buddy; A.d_difmax = b.difmax; A.d_bnf = b.buddy_num_final;
 
-    OG_CUDA(cudaMemcpyAsync(d_slabs, hs.data(), sizeof(QcSlabDev) * ns, cudaMemcpyHostToDevice, st));
+    OG_TRY(ctx->put_small(d_slabs, hs.data(), sizeof(QcSlabDev) * ns));
     dim3 g_ob((max_n + 255) / 256, ns);
     qc_prep_kernel<<<g_ob, 256, 0, st>>>(A);
     ctx->count_launch();
@@ -488,10 +488,11 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
             OG_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
             buddy_pass2_kernel<<<(unsigned)max_items, BP_THREADS, 0, st>>>(A);
             ctx->count_launch();
-            OG_CUDA(cudaMemcpyAsync(ctx->h_pinned_small, ctx->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            void* h_changed = nullptr;
+            OG_TRY(ctx->get_small(ctx->d_flag, sizeof(int), &h_changed));
             OG_CUDA(cudaStreamSynchronize(st));
             ++iters;
-            if (!ctx->h_pinned_small[0]) break;
+            if (!*(const int*)h_changed) break;
             std::swap(A.mod_in, A.mod_out);
             if (iters > max_n + 2) { set_error("buddy difmax fix-point did not converge"); return OG_ERR_NOCONV; }
         }
