@@ -29,6 +29,8 @@ struct BinDev {
     int* cell_start;
     int* cell_list;
     int* cell_sorted;
+    int* big_cells;     // cells whose list is too long for the warp sorter
+    int* n_big;
 };
 
 template <class F>
@@ -147,32 +149,97 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
     });
 }
 
-// Every cell list into ascending ob index -- the reference's summation order.
-__global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A, int ncells)
+// ---- per-cell sort by ob index ---------------------------------------------------------------
+constexpr int NB_IN = 1024;          // value buckets of the shared-memory sorter
+
+__device__ __forceinline__ int block_max(int v, int* s_red)
 {
-    const int c = blockIdx.x;
-    if (c >= ncells) return;
-    const int L = A.cell_count[c];
-    if (L == 0) return;
-    const int* __restrict__ in = A.cell_list + A.cell_start[c];
-    int* __restrict__ out = A.cell_sorted + A.cell_start[c];
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    v = s_red[0];
+    for (int w = 1; w < BIN_THREADS / 32; ++w) v = max(v, s_red[w]);
+    return v;
+}
+
+// In-place exclusive prefix of s[0..n), n <= PER * BIN_THREADS; s[n] = total.  Block-wide.
+template <int PER>
+__device__ __forceinline__ void block_exclusive_prefix(int* s, int n, int* s_red)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int v[PER], sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { const int i = tid * PER + q; v[q] = (i < n) ? s[i] : 0; sum += v[q]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) s_red[warp] = inc;
+    __syncthreads();
+    int run = inc - sum;
+    for (int w = 0; w < warp; ++w) run += s_red[w];
+    int total = 0;
+    for (int w = 0; w < BIN_THREADS / 32; ++w) total += s_red[w];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { const int i = tid * PER + q; if (i < n) s[i] = run; run += v[q]; }
+    if (tid == 0) s[n] = total;
+    __syncthreads();
+}
+
+// Sort m <= SORT_CAP distinct non-negative keys src[0..m) into s_key[0..m) (shared), block-wide.
+// Ob indices reaching a cell are spread evenly over the slab, so: bucket by value (about 8
+// keys per bucket, a monotone map, O(m) with shared-memory atomics), then one thread finishes
+// each bucket by insertion.  A lopsided key distribution falls back to a bitonic network.
+__device__ void block_sort_to_smem(const int* __restrict__ src, int m, int* __restrict__ s_key,
+                                   int* __restrict__ s_bkt, int* __restrict__ s_red)
+{
     const int tid = threadIdx.x;
-    extern __shared__ int s_key[];
-    if (L <= SORT_CAP) {
-        int P = 1;
-        while (P < L) P <<= 1;
-        for (int t = tid; t < P; t += BIN_THREADS) s_key[t] = (t < L) ? in[t] : 0x7fffffff;
-        __syncthreads();
-        if (L <= 2 * BIN_THREADS) {
-            // rank by counting (keys are distinct)
-            for (int t = tid; t < L; t += BIN_THREADS) {
-                const int key = s_key[t];
-                int rank = 0;
-                for (int j = 0; j < L; ++j) rank += (s_key[j] < key) ? 1 : 0;
-                out[rank] = key;
-            }
-            return;
+    if (m <= 96) {       // rank by counting
+        for (int t = tid; t < m; t += BIN_THREADS) {
+            const int key = src[t];
+            int rank = 0;
+            for (int j = 0; j < m; ++j) rank += (src[j] < key) ? 1 : 0;
+            s_key[rank] = key;
         }
+        __syncthreads();
+        return;
+    }
+    int kmax = 0, kminn = 0;       // max of key and of -key
+    for (int t = tid; t < m; t += BIN_THREADS) { const int k = src[t]; kmax = max(kmax, k); kminn = max(kminn, 0x7fffffff - k); }
+    kmax = block_max(kmax, s_red);
+    const int kmin = 0x7fffffff - block_max(kminn, s_red);
+    const int nb = min(NB_IN, max(1, m / 8));
+    const float scale = (float)nb / ((float)(kmax - kmin) + 1.0f);
+    auto bucket = [&](int key) { return min(nb - 1, (int)((float)(key - kmin) * scale)); };
+    for (int q = tid; q <= nb; q += BIN_THREADS) s_bkt[q] = 0;
+    __syncthreads();
+    for (int t = tid; t < m; t += BIN_THREADS) atomicAdd(&s_bkt[bucket(src[t])], 1);
+    __syncthreads();
+    block_exclusive_prefix<NB_IN / BIN_THREADS>(s_bkt, nb, s_red);
+    for (int t = tid; t < m; t += BIN_THREADS) {
+        const int key = src[t];
+        s_key[atomicAdd(&s_bkt[bucket(key)], 1)] = key;
+    }
+    __syncthreads();
+    // s_bkt[b] is now the end of bucket b
+    bool lopsided = false;
+    for (int bk = tid; bk < nb; bk += BIN_THREADS) {
+        const int lo = bk ? s_bkt[bk - 1] : 0, hi = s_bkt[bk];
+        if (hi - lo > 64) { lopsided = true; continue; }
+        for (int i = lo + 1; i < hi; ++i) {
+            const int key = s_key[i];
+            int j = i - 1;
+            while (j >= lo && s_key[j] > key) { s_key[j + 1] = s_key[j]; --j; }
+            s_key[j + 1] = key;
+        }
+    }
+    if (__syncthreads_or(lopsided ? 1 : 0)) {
+        int P = 1;
+        while (P < m) P <<= 1;
+        for (int t = m + tid; t < P; t += BIN_THREADS) s_key[t] = 0x7fffffff;
+        __syncthreads();
         for (int k = 2; k <= P; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int t = tid; t < (P >> 1); t += BIN_THREADS) {
@@ -185,96 +252,102 @@ __global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A, int nc
                 __syncthreads();
             }
         }
-        for (int t = tid; t < L; t += BIN_THREADS) out[t] = s_key[t];
-    } else {
-        // Longer than the shared-memory sorter: bucket the keys by value (ob indices are spread
-        // evenly, whatever the stations' positions), then sort every bucket in shared memory.
-        __shared__ int s_hist[NB_MAX + 1];
-        __shared__ int s_red[BIN_THREADS / 32];
-        int kmax = 0;
-        for (int t = tid; t < L; t += BIN_THREADS) kmax = max(kmax, in[t]);
-        for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-        if ((tid & 31) == 0) s_red[tid >> 5] = kmax;
-        __syncthreads();
-        kmax = 0;
-        for (int w = 0; w < BIN_THREADS / 32; ++w) kmax = max(kmax, s_red[w]);
-        const int nb = min(NB_MAX, max(1, L / 1024));
-        const long long span = (long long)kmax + 1;
-        for (int q = tid; q <= nb; q += BIN_THREADS) s_hist[q] = 0;
-        __syncthreads();
-        for (int t = tid; t < L; t += BIN_THREADS)
-            atomicAdd(&s_hist[(int)(((long long)in[t] * nb) / span)], 1);
-        __syncthreads();
-        // exclusive prefix over the nb bucket counts (nb <= 4096: 16 per thread)
-        {
-            constexpr int PER = NB_MAX / BIN_THREADS;
-            int v[PER], sum = 0;
-#pragma unroll
-            for (int q = 0; q < PER; ++q) { int i = tid * PER + q; v[q] = (i < nb) ? s_hist[i] : 0; sum += v[q]; }
-            int inc = sum;
-            const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            __syncthreads();
-            if (lane == 31) s_red[warp] = inc;
-            __syncthreads();
-            int woff = 0;
-            for (int w = 0; w < warp; ++w) woff += s_red[w];
-            int run = woff + inc - sum;
-            __syncthreads();
-#pragma unroll
-            for (int q = 0; q < PER; ++q) { int i = tid * PER + q; if (i < nb) s_hist[i] = run; run += v[q]; }
-            if (tid == BIN_THREADS - 1) s_hist[nb] = L;
-        }
-        __syncthreads();
-        // scatter into the buckets (any order inside a bucket); s_key doubles as the cursors
-        for (int q = tid; q < nb; q += BIN_THREADS) s_key[q] = 0;
-        __syncthreads();
-        for (int t = tid; t < L; t += BIN_THREADS) {
-            const int key = in[t];
-            const int bk = (int)(((long long)key * nb) / span);
-            out[s_hist[bk] + atomicAdd(&s_key[bk], 1)] = key;
-        }
-        __syncthreads();
-        // sort each bucket in place
-        for (int bk = 0; bk < nb; ++bk) {
-            const int b0 = s_hist[bk], m = s_hist[bk + 1] - b0;
-            if (m <= 1) continue;
-            if (m > SORT_CAP) {
-                // cannot happen for evenly spread indices; kept correct: rank by counting into
-                // the (now free) input list, then copy back
-                int* tmp = const_cast<int*>(in) + b0;
-                for (int t = tid; t < m; t += BIN_THREADS) {
-                    const int key = out[b0 + t];
-                    int rank = 0;
-                    for (int j = 0; j < m; ++j) rank += (out[b0 + j] < key) ? 1 : 0;
-                    tmp[rank] = key;
-                }
-                __syncthreads();
-                for (int t = tid; t < m; t += BIN_THREADS) out[b0 + t] = tmp[t];
-                __syncthreads();
-                continue;
-            }
-            int P = 1;
-            while (P < m) P <<= 1;
-            __syncthreads();
-            for (int t = tid; t < P; t += BIN_THREADS) s_key[t] = (t < m) ? out[b0 + t] : 0x7fffffff;
-            __syncthreads();
-            for (int k = 2; k <= P; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int t = tid; t < (P >> 1); t += BIN_THREADS) {
-                        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                        const int hi = lo | j;
-                        const bool up = ((lo & k) == 0);
-                        const int a = s_key[lo], b = s_key[hi];
-                        if ((a > b) == up) { s_key[lo] = b; s_key[hi] = a; }
-                    }
-                    __syncthreads();
-                }
-            }
-            for (int t = tid; t < m; t += BIN_THREADS) out[b0 + t] = s_key[t];
-        }
     }
+}
+
+// Every cell list into ascending ob index -- the reference's summation order.  Most lists are
+// short (tens of obs): one warp ranks one of those by counting; the long ones are queued for
+// the block-wide sorter below.
+constexpr int SMALL_LIST = 256;
+__global__ void __launch_bounds__(BIN_THREADS) cell_sort_small_kernel(BinDev A, int ncells)
+{
+    __shared__ int s_k[BIN_THREADS / 32][SMALL_LIST];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * (BIN_THREADS / 32) + warp;
+    if (c >= ncells) return;
+    const int L = A.cell_count[c];
+    if (L == 0) return;
+    if (L > SMALL_LIST) {
+        if (lane == 0) A.big_cells[atomicAdd(A.n_big, 1)] = c;
+        return;
+    }
+    const int* __restrict__ in = A.cell_list + A.cell_start[c];
+    int* __restrict__ out = A.cell_sorted + A.cell_start[c];
+    int* k = s_k[warp];
+    for (int t = lane; t < L; t += 32) k[t] = in[t];
+    __syncwarp();
+    for (int t = lane; t < L; t += 32) {
+        const int key = k[t];
+        int rank = 0;
+#pragma unroll 4
+        for (int j = 0; j < L; ++j) rank += (k[j] < key) ? 1 : 0;
+        out[rank] = key;
+    }
+}
+
+__global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A)
+{
+  for (int w = blockIdx.x; w < *A.n_big; w += gridDim.x) {
+    __syncthreads();
+    const int c = A.big_cells[w];
+    const int L = A.cell_count[c];
+    const int* __restrict__ in = A.cell_list + A.cell_start[c];
+    int* __restrict__ out = A.cell_sorted + A.cell_start[c];
+    const int tid = threadIdx.x;
+    extern __shared__ int s_key[];
+    __shared__ int s_bkt[NB_IN + 1];
+    __shared__ int s_red[BIN_THREADS / 32];
+    if (L <= SORT_CAP) {
+        block_sort_to_smem(in, L, s_key, s_bkt, s_red);
+        for (int t = tid; t < L; t += BIN_THREADS) out[t] = s_key[t];
+        continue;
+    }
+    // Longer than the shared-memory sorter: bucket the keys by value in global memory first
+    // (about 1024 per bucket), then sort every bucket in shared memory.
+    __shared__ int s_hist[NB_MAX + 1];
+    int kmax = 0;
+    for (int t = tid; t < L; t += BIN_THREADS) kmax = max(kmax, in[t]);
+    kmax = block_max(kmax, s_red);
+    const int nb = min(NB_MAX, max(1, L / 1024));
+    const float scale = (float)nb / ((float)kmax + 1.0f);
+    auto bucket = [&](int key) { return min(nb - 1, (int)((float)key * scale)); };
+    for (int q = tid; q <= nb; q += BIN_THREADS) s_hist[q] = 0;
+    __syncthreads();
+    for (int t = tid; t < L; t += BIN_THREADS) atomicAdd(&s_hist[bucket(in[t])], 1);
+    __syncthreads();
+    block_exclusive_prefix<NB_MAX / BIN_THREADS>(s_hist, nb, s_red);
+    // scatter into the buckets (any order inside a bucket); s_key doubles as the cursors
+    for (int q = tid; q < nb; q += BIN_THREADS) s_key[q] = 0;
+    __syncthreads();
+    for (int t = tid; t < L; t += BIN_THREADS) {
+        const int key = in[t];
+        const int bk = bucket(key);
+        out[s_hist[bk] + atomicAdd(&s_key[bk], 1)] = key;
+    }
+    __syncthreads();
+    int* tmp = const_cast<int*>(in);      // the fill-order list is free from here on
+    for (int bk = 0; bk < nb; ++bk) {
+        const int b0 = s_hist[bk], m = s_hist[bk + 1] - b0;
+        if (m <= 1) continue;
+        __syncthreads();
+        if (m > SORT_CAP) {
+            // cannot happen for evenly spread indices; kept correct: rank by counting
+            for (int t = tid; t < m; t += BIN_THREADS) {
+                const int key = out[b0 + t];
+                int rank = 0;
+                for (int j = 0; j < m; ++j) rank += (out[b0 + j] < key) ? 1 : 0;
+                tmp[b0 + rank] = key;
+            }
+            __syncthreads();
+            for (int t = tid; t < m; t += BIN_THREADS) out[b0 + t] = tmp[b0 + t];
+            continue;
+        }
+        for (int t = tid; t < m; t += BIN_THREADS) tmp[b0 + t] = out[b0 + t];
+        __syncthreads();
+        block_sort_to_smem(tmp + b0, m, s_key, s_bkt, s_red);
+        for (int t = tid; t < m; t += BIN_THREADS) out[b0 + t] = s_key[t];
+    }
+  }
 }
 
 } // namespace
@@ -325,11 +398,16 @@ int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, c
         bin_fill_kernel<<<g_ob, 256, 0, st>>>(A);
         ctx->count_launch();
         if (sorted) {
-            // static (bucket table) + dynamic (sort buffer) shared memory exceed the 48 KB default
+            OG_TRY(ctx->reserve_t((t + ".big").c_str(), (size_t)ncells + 1, &A.big_cells));
+            A.n_big = ctx->d_flag + 4;
+            OG_CUDA(cudaMemsetAsync(A.n_big, 0, sizeof(int), st));
+            cell_sort_small_kernel<<<(unsigned)((ncells + BIN_THREADS / 32 - 1) / (BIN_THREADS / 32)), BIN_THREADS, 0, st>>>(A, (int)ncells);
+            // static (bucket tables) + dynamic (sort buffer) shared memory exceed the 48 KB default
             OG_CUDA(cudaFuncSetAttribute(cell_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SORT_CAP * (int)sizeof(int)));
-            cell_sort_kernel<<<(unsigned)ncells, BIN_THREADS, SORT_CAP * sizeof(int), st>>>(A, (int)ncells);
-            ctx->count_launch();
+            const unsigned nblk = (unsigned)std::min<long long>(ncells, (long long)ctx->sm_count * 4);
+            cell_sort_kernel<<<nblk, BIN_THREADS, SORT_CAP * sizeof(int), st>>>(A);
+            ctx->count_launch(2);
         }
         OG_CUDA(cudaGetLastError());
     }
