@@ -1,0 +1,192 @@
+"""A second, independent restatement of the two hot loops -- numpy, written from the Fortran
+source (not from oracle/og_oracle.c) -- used only to cross-check the C oracle
+(tests/test_oracle_vs_numpy.py).  Every scalar is np.float32 so that each operation is one
+IEEE-754 binary32 operation in source order; windows are vectorised per observation, which
+does not change any result (points are independent; obs are applied in index order).
+
+    cressman     src/oa_module.F90:25-218 (+ dist_uu_vv_rh :229-574, dist_not_uu_vv_rh :577-627)
+    buddy_check  src/qc2_module.F90:111-337 (+ modify_qc_flag / add_to_qc_flag, qc0_module.F90:9-76)
+"""
+import math
+
+import numpy as np
+
+F = np.float32
+NO_BUDDIES, FAILS_BUDDY = 1 << 14, 1 << 17
+
+
+def nint(x):          # Fortran NINT: half away from zero
+    x = float(x)
+    return int(math.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)
+
+
+def fint(x):          # Fortran INT / real -> integer assignment: truncate
+    return int(float(x))
+
+
+def add_flag(q, t):   # qc0_module.F90:27-31 / :55-72
+    small = q % t if q >= 0 else -((-q) % t)
+    large = int(q / (t * 2)) * 2
+    return large * t + small + t
+
+
+def cressman(obs, xob, yob, gridded, name, R, dxd, u_b=None, v_b=None, pressure=1001.0,
+             use_first_guess=True, fg_value=None, scale_rh=False, crsdot=1):
+    """gridded: (jns, iew) C-order array == Fortran gridded(iew,jns); returns the analysed copy."""
+    g = np.array(gridded, np.float32)
+    jns, iew = g.shape
+    num = np.zeros_like(g); den = np.zeros_like(g)
+    rc2 = F(crsdot) / F(2.0)
+    r2 = F(R * R)
+    pi = F(3.14159265358); twopi = F(2.0) * F(3.14159265358)
+    dxd = F(dxd); pressure = F(pressure)
+    shapes = [0, 0, 0]
+    for n in range(len(obs)):
+        x, y, ob = F(xob[n]), F(yob[n]), F(obs[n])
+        if x <= F(1) + rc2 or y <= F(1) + rc2 or x >= F(iew) - rc2 or y >= F(jns) - rc2:
+            continue
+        i0 = max(nint(x - rc2) - 4 * R - 1, 1); j0 = max(nint(y - rc2) - 4 * R - 1, 1)
+        i1 = min(nint(x - rc2) + 4 * R + 1, iew - crsdot); j1 = min(nint(y - rc2) + 4 * R + 1, jns - crsdot)
+        if i1 < i0 or j1 < j0:
+            continue
+        ri = np.arange(i0, i1 + 1, dtype=np.float32)[None, :]
+        rj = np.arange(j0, j1 + 1, dtype=np.float32)[:, None]
+        sl = (slice(j0 - 1, j1), slice(i0 - 1, i1))
+        kind = "circle"
+        if name in ("UU", "VV", "RH"):
+            vcrit = F(15.0) if pressure < F(500.0) else F(25.0) - F(0.02) * pressure
+            u_ob = F(u_b[nint(y) - 1, nint(x) - 1]); v_ob = F(v_b[nint(y) - 1, nint(x) - 1])
+            speed = np.sqrt(u_ob * u_ob + v_ob * v_ob)
+            if speed >= vcrit:
+                dydx = v_ob / u_ob if abs(u_ob) >= F(1.0e-5) else F(1000.0)
+                x1 = x + F(3.0) * (u_ob / speed); y1 = y + F(3.0) * (v_ob / speed)
+                x2 = x - F(3.0) * (u_ob / speed); y2 = y - F(3.0) * (v_ob / speed)
+                a1 = max(min(nint(x1), iew), 1); b1 = max(min(nint(y1), jns), 1)
+                a2 = max(min(nint(x2), iew), 1); b2 = max(min(nint(y2), jns), 1)
+                d12 = np.sqrt((F(a1) - F(a2)) * (F(a1) - F(a2)) + (F(b1) - F(b2)) * (F(b1) - F(b2)))
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    dudx = (F(u_b[b1 - 1, a1 - 1]) - F(u_b[b2 - 1, a2 - 1])) / (d12 * dxd)
+                    dvdx = (F(v_b[b1 - 1, a1 - 1]) - F(v_b[b2 - 1, a2 - 1])) / (d12 * dxd)
+                    numc = abs(u_ob * dvdx - v_ob * dudx) / (u_ob * u_ob)
+                s = np.sqrt(F(1.0) + dydx * dydx)
+                denc = (s * s) * s
+                if abs(u_ob) < F(1.0e-5) or abs(v_ob) < F(1.0e-5) or abs(numc) < F(1.0e-5):
+                    roc = F(1000.0)
+                else:
+                    roc = denc / numc
+                elong = F(1.0) + F(0.7778) / vcrit * speed
+                if abs(roc) < (F(3.0) * F(R)) * dxd:
+                    kind = "banana"
+                    ia = max(nint(x) - 3, 1); ja = fint(y); ib = fint(x); jb = max(nint(y) - 3, 1)
+                    ic = min(nint(x) + 3, iew); jc = fint(y); idd = fint(x); jd = min(nint(y) + 3, jns)
+                    vor = (F(v_b[jc - 1, ic - 1]) - F(v_b[ja - 1, ia - 1])) - (F(u_b[jd - 1, idd - 1]) - F(u_b[jb - 1, ib - 1]))
+                    roc = roc * F(math.copysign(1.0, float(vor)))
+                    i_c = fint(F(nint(x)) - roc * v_ob / speed)
+                    j_c = fint(F(nint(y)) + roc * u_ob / speed)
+                    theta_ob = np.arctan2(F(j_c) - y, F(i_c) - x)
+                else:
+                    kind = "ellipse"
+        shapes[("circle", "ellipse", "banana").index(kind)] += 1
+        if kind == "circle":
+            d2 = ((x - rc2 - ri) * (x - rc2 - ri)) + ((y - rc2 - rj) * (y - rc2 - rj))
+        elif kind == "banana":
+            theta = np.arctan2(F(j_c) - rj + F(0) * ri, F(i_c) - ri + F(0) * rj).astype(np.float32)
+            rij = np.sqrt((F(i_c) - ri) * (F(i_c) - ri) + (F(j_c) - rj) * (F(j_c) - rj))
+            td = (theta_ob - theta).astype(np.float32)
+            inv2pi = F(1.0) / twopi; invpi = F(1.0) / pi
+            big = td > twopi
+            td = np.where(big, td - np.trunc(td * inv2pi).astype(np.float32) * twopi, td).astype(np.float32)
+            sml = td < -twopi
+            td = np.where(sml, td + np.trunc(td * inv2pi).astype(np.float32) * twopi, td).astype(np.float32)
+            td = np.where(td > pi, td - twopi, td).astype(np.float32)
+            td = np.where(td < -pi, td + twopi, td).astype(np.float32)
+            xx = roc * td * invpi
+            yy = abs(roc) - rij
+            d2 = xx * xx / elong + yy * yy
+        else:
+            xx = (u_ob * (ri - x) + v_ob * (rj - y)) / speed
+            yy = (v_ob * (ri - x) - u_ob * (rj - y)) / speed
+            d2 = xx * xx / elong + yy * yy
+        d2 = d2.astype(np.float32)
+        hit = d2 < r2
+        w = ((r2 - d2) / (r2 + d2)).astype(np.float32)
+        sf = np.ones_like(w)
+        if scale_rh and name == "RH" and use_first_guess and ob < F(0.0):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sf = np.minimum(F(1.0), g[sl] / F(fg_value[n])).astype(np.float32)
+        num[sl] = np.where(hit, num[sl] + w * w * ob * sf, num[sl])
+        den[sl] = np.where(hit, den[sl] + w, den[sl])
+    pert = np.zeros_like(g)
+    pos = den > 0
+    pert[pos] = num[pos] / den[pos]
+    out = (g + pert) if use_first_guess else pert
+    return out.astype(np.float32), shapes
+
+
+def bilinear(g, x, y):
+    iob, job = fint(x), fint(y)
+    dx, dy = F(x) - F(iob), F(y) - F(job)
+    G = lambda i, j: F(g[j - 1, i - 1])   # noqa: E731
+    return (F(1) - dx) * ((F(1) - dy) * G(iob, job) + dy * G(iob, job + 1)) + \
+        dx * ((F(1) - dy) * G(iob + 1, job) + dy * G(iob + 1, job + 1))
+
+
+def buddy_check(obs, xob, yob, qc_flag, elev, gridded, name, pressure, dx, buddy_weight, buddy_difference):
+    n = len(obs)
+    p = F(pressure); bd = F(buddy_difference)
+    rng = F(650.0) if p <= F(201.0) else (F(300.0) if p <= F(1000.1) else F(500.0))
+    difmax = np.full(n, bd, np.float32)
+    if name in ("UU", "VV"):
+        f = F(1.7) if p < F(401.0) else (F(1.4) if p < F(701.0) else (F(1.1) if p < F(851.0) else None))
+        if f is not None:
+            difmax[:] = bd * f
+    elif name == "PMSLPSFC":
+        for k in range(n):
+            difmax[k] = bd * (F(1.0) + (F(elev[k]) / F(2000.0)))
+    elif name == "TT":
+        f = F(0.6) if p < F(401.0) else (F(0.8) if p < F(701.0) else None)
+        if f is not None:
+            difmax[:] = bd * f
+    elif name == "DEWPOINT":
+        for k in range(n):
+            o = F(obs[k])
+            fac = F(1.25) if (o < F(255.0) and o >= F(235.0)) else (F(1.5) if (o < F(235.0) and o >= F(215.0)) else (F(1.75) if o < F(215.0) else F(1.0)))
+            difmax[k] = bd * fac
+    difmax = (difmax * F(buddy_weight)).astype(np.float32)
+    aob = np.array([bilinear(gridded, xob[k], yob[k]) for k in range(n)], np.float32)
+    obs = np.asarray(obs, np.float32); xob = np.asarray(xob, np.float32); yob = np.asarray(yob, np.float32)
+    qc = np.array(qc_flag, np.int64)
+    err = np.zeros(n, np.float32); bnf = np.zeros(n, np.int32)
+    dxf = F(dx)
+    for k in range(n):
+        x = xob[k] - xob; y = yob[k] - yob
+        dist = (np.sqrt((x * x + y * y).astype(np.float32)) * dxf).astype(np.float32)
+        m = (dist <= rng) & (dist >= F(0.1))
+        m[k] = False
+        idx = np.nonzero(m)[0]
+        diff = (obs[idx] - aob[idx]).astype(np.float32)
+        s = F(0.0)
+        for d in diff:
+            s = s + d
+        e = F(0.0)
+        if len(idx) >= 2:
+            avg = s / F(len(idx))
+            kob = len(idx)
+            for d, j in zip(diff, idx):
+                if d > difmax[j] * F(1.25) and abs(d - avg) > difmax[j]:
+                    kob -= 1
+                    s = s - d
+            bnf[k] = kob
+            if kob >= 2:
+                e = (obs[k] - aob[k]) - s / F(kob)
+            else:
+                qc[k] = add_flag(int(qc[k]), NO_BUDDIES)
+        else:
+            qc[k] = add_flag(int(qc[k]), NO_BUDDIES)
+        err[k] = e
+        if bnf[k] == 2:
+            difmax[k] = F(1.2) * difmax[k]
+    for k in range(n):
+        if abs(err[k]) > difmax[k]:
+            qc[k] = add_flag(int(qc[k]), FAILS_BUDDY)
+    return qc.astype(np.int32), aob, err, difmax, bnf

@@ -1,0 +1,77 @@
+"""The C oracle against a second, independent restatement (tests/ref_numpy.py, written from the
+Fortran source).  With no Fortran toolchain the reference itself cannot run here; two
+independent transcriptions agreeing bit for bit is the strongest pin available."""
+import numpy as np
+import pytest
+
+from tests import ref_numpy as R
+
+NAMES = {1: "UU", 2: "VV", 3: "TT", 4: "RH", 5: "PMSL", 6: "PMSLPSFC", 7: "DEWPOINT"}
+
+
+def wavy(iew, jns, a=10.0, b=280.0):
+    i = np.arange(iew)[None, :]; j = np.arange(jns)[:, None]
+    return (b + a * np.sin(i / 7.0) * np.cos(j / 5.0)).astype(np.float32)
+
+
+def winds(iew, jns, jet=40.0, curl=True):
+    i = np.arange(1, iew + 1, dtype=np.float64)[None, :]
+    j = np.arange(1, jns + 1, dtype=np.float64)[:, None]
+    yc = jns / 2 + 0.15 * jns * np.sin(2 * np.pi * i / iew * 1.5)
+    core = np.exp(-((j - yc) / (0.12 * jns)) ** 2)
+    u = 3.0 + jet * core
+    v = jet * core * (0.15 * jns * 2 * np.pi * 1.5 / iew) * np.cos(2 * np.pi * i / iew * 1.5) if curl else 0 * u
+    return u.astype(np.float32), (v + 0 * u).astype(np.float32)
+
+
+@pytest.mark.parametrize("var,R_,ufg", [(3, 5, True), (5, 3, False), (3, 9, True)])
+def test_cressman_isotropic(oracle, var, R_, ufg):
+    rng = np.random.default_rng(var * 10 + R_)
+    iew, jns, n = 44, 37, 120
+    g = wavy(iew, jns)
+    x = rng.uniform(1.0, iew - 0.2, n).astype(np.float32); y = rng.uniform(1.0, jns - 0.2, n).astype(np.float32)
+    d = rng.normal(0, 3, n).astype(np.float32)
+    a = oracle.cressman(d, x, y, g, var, R_, 12.0, use_first_guess=ufg)
+    b, _ = R.cressman(d, x, y, g, NAMES[var], R_, 12.0, use_first_guess=ufg)
+    np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("var,pressure,curl", [(1, 300.0, False), (2, 850.0, True), (4, 700.0, True), (4, 1001.0, True)])
+def test_cressman_anisotropic(oracle, var, pressure, curl):
+    rng = np.random.default_rng(int(pressure) + var)
+    iew, jns, n, R_ = 64, 52, 90, 4
+    g = wavy(iew, jns, 20.0, 50.0)
+    ub, vb = winds(iew, jns, curl=curl)
+    x = rng.uniform(1.0, iew - 0.2, n).astype(np.float32); y = rng.uniform(1.0, jns - 0.2, n).astype(np.float32)
+    d = rng.normal(0, 5, n).astype(np.float32)
+    fg = (np.abs(rng.normal(50, 20, n)) + 1).astype(np.float32)
+    oracle.reset_stats()
+    a = oracle.cressman(d, x, y, g, var, R_, 12.0, ub, vb, pressure, fg_value=fg, scale_rh=True)
+    st = oracle.get_stats()
+    b, shapes = R.cressman(d, x, y, g, NAMES[var], R_, 12.0, ub, vb, pressure, fg_value=fg, scale_rh=True)
+    assert shapes == [st["n_circle"], st["n_ellipse"], st["n_banana"]]
+    assert shapes[1] + shapes[2] > 0
+    if shapes[2] == 0:
+        np.testing.assert_array_equal(a, b)
+    else:   # numpy's float32 arctan2 need not be glibc's atan2f to the last bit
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-3)
+        assert np.mean(a != b) < 0.2 and np.max(np.abs(a - b)) < 1e-4
+
+
+@pytest.mark.parametrize("var,pressure,n,dx", [(1, 850.0, 150, 30.0), (3, 300.0, 200, 60.0), (6, 1001.0, 120, 30.0),
+                                               (7, 500.0, 100, 90.0), (5, 1001.0, 60, 150.0)])
+def test_buddy_check(oracle, var, pressure, n, dx):
+    rng = np.random.default_rng(var + n)
+    iew, jns = 70, 60
+    g = wavy(iew, jns, 6.0, 260.0 if var in (3, 7) else 10.0)
+    x = rng.uniform(2.0, iew - 1.0, n).astype(np.float32); y = rng.uniform(2.0, jns - 1.0, n).astype(np.float32)
+    x[1], y[1] = x[0], y[0]
+    ob = (g.mean() + rng.normal(0, 5, n)).astype(np.float32)
+    ob[rng.random(n) < 0.08] += 40.0
+    elev = rng.uniform(-3000, 3000, n).astype(np.float32)
+    q0 = (rng.integers(0, 2, n) * (1 << 16)).astype(np.int32)
+    a = oracle.buddy_check(ob, x, y, q0, elev, g, var, pressure, dx, 1.0, 8.0)
+    b = R.buddy_check(ob, x, y, q0, elev, g, NAMES[var], pressure, dx, 1.0, 8.0)
+    for nm, u, v in zip(("qc", "aob", "err", "difmax", "buddy_num_final"), a, b):
+        np.testing.assert_array_equal(u, v, err_msg=nm)
+    assert np.count_nonzero(a[0] & (1 << 17)) > 0
