@@ -345,8 +345,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         blocking.append((time.perf_counter() - t0) * 1e3)
     e2e_blocking_ms = float(np.mean(blocking[1:]))
     restore_host()
-    run_e2e(2)
-    same = all(np.array_equal(work[nm].cpu().numpy(), getattr(ocase[1], nm)) for nm in FIELD_NAMES + FLAG_NAMES)
+    run_e2e(NS + 1)          # touches every slot: no allocation is left for the timed steps
+    same = all(np.array_equal(work[nm].cpu().numpy(), getattr(ocase[s_], nm))
+               for nm in FIELD_NAMES + FLAG_NAMES for s_ in range(NS))
     assert same, "resident and asynchronous host-pointer paths disagree"
     ctx.reset_stats()
     barrier()
