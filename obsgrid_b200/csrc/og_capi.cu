@@ -41,6 +41,7 @@ extern "C" int og_init(og_ctx** out, int device)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->stream_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream_aux, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_a) != cudaSuccess || cudaEventCreate(&c->ev_b) != cudaSuccess ||
         cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&c->d_flag, 64 * sizeof(int)) != cudaSuccess ||
@@ -72,6 +73,7 @@ extern "C" int og_finalize(og_ctx* c)
     }
     if (c->stream_in) cudaStreamDestroy(c->stream_in);
     if (c->stream_out) cudaStreamDestroy(c->stream_out);
+    if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
     cudaStreamDestroy(c->stream);
     delete c;
     return OG_OK;

@@ -41,6 +41,7 @@ struct og_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_in = nullptr, stream_out = nullptr;   // copy streams of og_qc_oa_time
+    cudaStream_t stream_aux = nullptr;                        // second compute stream (scan kernels)
     std::vector<cudaEvent_t> pipe_events;
     struct Slot { cudaEvent_t up = nullptr, comp = nullptr, down = nullptr; bool down_pending = false; };
     Slot slots[OG_SLOTS];
