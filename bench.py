@@ -47,6 +47,19 @@ FLAG_NAMES = ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp")
 TABLE_NAMES = ("xob", "yob", "lon", "elev", "ob_u", "ob_v", "ob_t", "ob_rh", "ob_slp")
 
 
+def measured_traffic(cfg: int):
+    """dram bytes per scan launch from the newest committed ncu capture of this config."""
+    best = None
+    for f in sorted(ROOT.glob(f"profiles/r*/traffic_cfg{cfg}.json")):
+        best = f
+    if best is None:
+        return None, None
+    try:
+        return float(json.loads(best.read_text())["bytes_per_scan"]), str(best.relative_to(ROOT))
+    except Exception:      # noqa: BLE001
+        return None, None
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -371,6 +384,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     if rank == 0:
         hbm_peak, peak_src = peaks()
         fp32_peak_ops = ctx.fp32_peak()                     # lane-instructions/s, FADD/FMUL no FMA
+        traffic_bytes, traffic_src = measured_traffic(args.config)
         n_scan_launch = sum(1 for r in case.oa_params.radius_influence if r >= 0)
         per_launch_ms = scan_ms_step / max(n_scan_launch, 1)
         flops_per_launch = ALGO_FLOP_PER_UPDATE * updates / max(n_scan_launch, 1)
@@ -385,7 +399,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                            "parity build has -fmad=false, 1 lane-instruction = 1 FLOP)",
             "algorithmic_flop_per_update": ALGO_FLOP_PER_UPDATE,
             "avg_launch_ms": per_launch_ms, "launches_per_step": n_scan_launch,
-            "traffic": None,
+            "traffic": traffic_bytes, "traffic_source": traffic_src,
             "hbm": {"achieved": hbm_bytes_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0,
                     "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": hbm_bytes_launch},
