@@ -73,6 +73,26 @@ def test_cressman_dense_cluster_overflows_staging(ctx, oracle):
                                   ctx.cressman(d, x, y, g, 3, 9, 12.0))
 
 
+def test_spatially_sorted_obs_exercise_the_sorter_fallback(ctx, oracle):
+    """Obs whose index follows their position (sorted by column band): the indices reaching a
+    cell then sit in a few narrow ranges, the value buckets of the list sorter are lopsided and
+    its bitonic fallback has to produce the reference's order."""
+    rng = np.random.default_rng(77)
+    iew, jns, n = 96, 64, 9000
+    g = wavy(iew, jns)
+    x, y = rng_obs(rng, n, iew, jns)
+    order = np.lexsort((rng.random(n), (x // 6).astype(np.int64) % 4, (y // 16).astype(np.int64)))
+    x, y = x[order], y[order]
+    d = rng.normal(0, 3, n).astype(np.float32)
+    np.testing.assert_array_equal(oracle.cressman(d, x, y, g, 3, 8, 12.0), ctx.cressman(d, x, y, g, 3, 8, 12.0))
+    ob = (280 + rng.normal(0, 5, n)).astype(np.float32)
+    z = np.zeros(n, np.float32)
+    a = oracle.buddy_check(ob, x, y, np.zeros(n, np.int32), z, g, 3, 850.0, 40.0, 1.0, 8.0)
+    b = ctx.buddy_check(ob, x, y, np.zeros(n, np.int32), z, g, 3, 850.0, 40.0, 1.0, 8.0)
+    for nm, u, v in zip(("qc", "aob", "err", "difmax", "buddy_num_final"), a, b):
+        np.testing.assert_array_equal(u, v, err_msg=nm)
+
+
 def wind_fields(iew, jns, jet=40.0, curl=True):
     i = np.arange(1, iew + 1, dtype=np.float64)[None, :]
     j = np.arange(1, jns + 1, dtype=np.float64)[:, None]
