@@ -116,7 +116,8 @@ class ClockSampler:
 
 def build_case(args, rank: int):
     cfg = args.config
-    case = synth.make_case(cfg, time_index=rank)
+    # weak scaling: every rank analyses its own time period; strong: all ranks share time 0
+    case = synth.make_case(cfg, time_index=0 if args.scaling == "strong" else rank)
     if args.scale_rh:
         case.oa_params.scale_cressman_rh_decreases = 1
     return case
@@ -240,6 +241,13 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     case = build_case(args, rank)
     K = case.kbu
     KR = 1 if case.oa_params.surface_only else K      # FDDA surface analyses touch level 0 only
+    K0 = 0
+    if args.scaling == "strong" and world > 1:
+        # one time period, its levels cut into contiguous ranges balanced on a cost estimate
+        # (obsgrid_b200/shard.py); no exchange between ranks, the host writer gathers afterwards
+        from obsgrid_b200 import shard
+        rng_ = shard.plan_levels(shard.level_costs(case)[:KR], world)
+        K0, KR = rng_[rank]
 
     # ---- resident copy: pristine inputs + working set in HBM ---------------------------------
     pristine, work = {}, {}
@@ -258,8 +266,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize(dev)
 
     def step_resident():
-        ctx.dev_proc_qc(ddesc, case.qc_params, 0, KR, True)
-        ctx.dev_proc_oa(ddesc, case.oa_params, 0, KR)
+        ctx.dev_proc_qc(ddesc, case.qc_params, K0, KR, True)
+        ctx.dev_proc_oa(ddesc, case.oa_params, K0, KR)
 
     # ---- e2e: pinned host arrays through the host-pointer C ABI -----------------------------
     host0 = {nm: getattr(case, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
@@ -278,7 +286,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     def step_e2e():
         # the reference's driver calls proc_qc then proc_oa for a time period; og_qc_oa_time is
         # that pair in one call, levels pipelined through the copy engines
-        ctx.proc_qc_oa(hcase, 0, KR, pipeline_groups=args.pipeline_groups)
+        ctx.proc_qc_oa(hcase, K0, KR, pipeline_groups=args.pipeline_groups)
 
     def barrier():
         if dist is not None:
@@ -313,9 +321,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     for i in range(args.steps):
         restore_resident()
         ev[i][0].record(lib_stream)
-        ctx.dev_proc_qc(ddesc, case.qc_params, 0, KR, True)
+        ctx.dev_proc_qc(ddesc, case.qc_params, K0, KR, True)
         ev[i][1].record(lib_stream)
-        ctx.dev_proc_oa(ddesc, case.oa_params, 0, KR)
+        ctx.dev_proc_oa(ddesc, case.oa_params, K0, KR)
         ev[i][2].record(lib_stream)
     ctx.sync()
     barrier()
@@ -341,13 +349,13 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     restore_host()
 
     def run_e2e(nsteps):
-        ctx.time_upload(hcase, 0, 0, KR)
+        ctx.time_upload(hcase, 0, K0, KR)
         for i in range(nsteps):
             s_ = i % NS
             if i + 1 < nsteps:
-                ctx.time_upload(hcase, (i + 1) % NS, 0, KR)
-            ctx.time_compute(hcase, s_, 0, KR)
-            ctx.time_download(ocase[s_], s_, 0, KR)
+                ctx.time_upload(hcase, (i + 1) % NS, K0, KR)
+            ctx.time_compute(hcase, s_, K0, KR)
+            ctx.time_download(ocase[s_], s_, K0, KR)
         for s_ in range(NS):
             ctx.time_wait(s_)
 
@@ -389,7 +397,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         per_launch_ms = scan_ms_step / max(n_scan_launch, 1)
         flops_per_launch = ALGO_FLOP_PER_UPDATE * updates / max(n_scan_launch, 1)
         achieved_tf = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
-        n_oa_slabs = 5 + 4 * (KR - 1)
+        n_oa_slabs = (5 if K0 == 0 else 0) + 4 * (KR - max(K0, 1))
         hbm_bytes_launch = n_oa_slabs * 8.0 * case.iew * case.jns
         roofline = {
             "kernel": "cressman_scan_kernel", "bound": "fp32",
@@ -410,15 +418,16 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         line = {
             "metric": METRIC, "value": g_updates / (step_ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": case.label, "times_per_step": world,
+            "config": {"workload": case.label, "times_per_step": 1 if args.scaling == "strong" else world,
                        "grid": [case.iew, case.jns], "levels": K, "reports": case.nrep,
                        "scans": [int(r) for r in case.oa_params.radius_influence if r >= 0],
                        "scale_cressman_rh_decreases": bool(case.oa_params.scale_cressman_rh_decreases),
                        "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
                              "pristine copy before every step",
-                       "parallelism": f"{world} x independent analysis time",
+                       "parallelism": (f"1 analysis time, levels sharded over {world} ranks" if args.scaling == "strong"
+                                       else f"{world} x independent analysis time"),
                        "cpu_affinity": affinity},
             "e2e": {"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "api": "og_time_upload/_compute/_download/_wait, 3 time periods in flight, pinned host arrays",
@@ -454,6 +463,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs[config-1]")
     ap.add_argument("--scale-rh", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one analysis time per rank; strong: one time, levels sharded over the ranks")
     ap.add_argument("--pipeline-groups", type=int, default=0,
                     help="level groups of the pipelined e2e call (0: library default)")
     ap.add_argument("--ref-levels", type=int, default=64,

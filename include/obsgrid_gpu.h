@@ -170,6 +170,15 @@ int og_buddy_check(og_ctx* ctx, const float* obs, int n, const float* xob, const
                    float dx_km, float buddy_weight, float buddy_difference,
                    float* aob, float* err, float* difmax, int* buddy_num_final);
 
+/* GET_FG_T_AT_POINT (get_fg_at_point_module.F90:7-116, reached from query_ob,
+ * ob_access_module.F90:257, when qc_psfc is on), batched over n points already projected to
+ * grid coordinates (latlon_to_ij stays on the caller's side): first-guess temperature at
+ * (x, y, height_msl) from the 3-D first-guess temperature and height fields
+ * ((jns,iew,kbu) y fastest), OG_MISSING_R where the reference returns missing_r. */
+int og_fg_t_at_point(og_ctx* ctx, const float* fg_3d_t, const float* fg_3d_h, int jns, int iew,
+                     int kbu, const float* x_location, const float* y_location,
+                     const float* height_msl, int n, float* fg_t);
+
 /* error_max followed by buddy_check on one slab in one upload (proc_qc.F90:371-392). */
 int og_qc_slab(og_ctx* ctx, int do_error_max, int do_buddy, const float* gridded, int iew,
                int jns, int var, float pressure_hpa, const float* obs, const float* xob,

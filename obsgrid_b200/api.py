@@ -122,6 +122,16 @@ class Context:
               "og_local_time")
         return out
 
+    def fg_t_at_point(self, t3d, h3d, x, y, height):
+        """GET_FG_T_AT_POINT batched; t3d/h3d: (kbu, iew, jns) C order == Fortran (jns,iew,kbu)."""
+        t3d, h3d = f32(t3d), f32(h3d)
+        kbu, iew, jns = t3d.shape
+        x, y, height = f32(x), f32(y), f32(height)
+        out = np.zeros(x.size, np.float32)
+        check(self._lib.og_fg_t_at_point(self._h, ptr(t3d), ptr(h3d), jns, iew, kbu, ptr(x), ptr(y),
+                                         ptr(height), x.size, ptr(out)), "og_fg_t_at_point")
+        return out
+
     def error_max(self, obs, xob, yob, elev, qc_flag, gridded, var, max_difference, pressure,
                   local_t):
         g = f32(gridded); jns, iew = g.shape

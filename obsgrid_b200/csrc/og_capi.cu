@@ -311,6 +311,27 @@ extern "C" int og_local_time(og_ctx* c, int time_hhmm, const float* lonob, int n
     return OG_OK;
 }
 
+extern "C" int og_fg_t_at_point(og_ctx* c, const float* fg_3d_t, const float* fg_3d_h, int jns,
+                                int iew, int kbu, const float* x_location, const float* y_location,
+                                const float* height_msl, int n, float* fg_t)
+{
+    REQUIRE(c && fg_3d_t && fg_3d_h && n >= 0 && iew > 2 && jns > 2 && kbu >= 3, "bad argument");
+    if (n == 0) return OG_OK;
+    REQUIRE(x_location && y_location && height_msl && fg_t, "null point array");
+    const size_t vol = (size_t)iew * jns * kbu;
+    float *d_t, *d_h, *d_x, *d_y, *d_z, *d_o;
+    OG_TRY(upload(c, "io.t3", fg_3d_t, vol, &d_t));
+    OG_TRY(upload(c, "io.h3", fg_3d_h, vol, &d_h));
+    OG_TRY(upload(c, "io.x", x_location, (size_t)n, &d_x));
+    OG_TRY(upload(c, "io.y", y_location, (size_t)n, &d_y));
+    OG_TRY(upload(c, "io.z", height_msl, (size_t)n, &d_z));
+    OG_TRY(c->reserve_t("io.fgt", (size_t)n, &d_o));
+    OG_TRY(fg_t_at_point_device(c, d_t, d_h, jns, iew, kbu, d_x, d_y, d_z, n, d_o));
+    OG_TRY(download(c, fg_t, d_o, (size_t)n));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
 // shared body of og_error_max / og_buddy_check / og_qc_slab
 static int qc_slab_common(og_ctx* c, int do_emax, int do_buddy, const float* gridded, int iew,
                           int jns, int var, float pressure, const float* obs, const float* xob,

@@ -156,6 +156,8 @@ struct QcBatch {
 
 int qc_run_batch(og_ctx* ctx, QcBatch& b);
 int local_time_device(og_ctx* ctx, int time_hhmm, const float* lon, int n, int* out);
+int fg_t_at_point_device(og_ctx* ctx, const float* t3, const float* h3, int jns, int iew, int kbu,
+                         const float* x, const float* y, const float* h, int n, float* out);
 
 // ---- stable binning (og_bin.cu) --------------------------------------------------------
 struct BinSlab {

@@ -344,6 +344,59 @@ __global__ void local_time_kernel(int hh, const float* __restrict__ lon, int n, 
     out[q] = (lt % 24) * 100;
 }
 
+// GET_FG_T_AT_POINT, get_fg_at_point_module.F90:36-114 (after latlon_to_ij): one thread per point.
+__global__ void fg_t_at_point_kernel(const float* __restrict__ t3, const float* __restrict__ h3,
+                                     int jns, int iew, int kbu, const float* __restrict__ xs,
+                                     const float* __restrict__ ys, const float* __restrict__ hs,
+                                     int n, float* __restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float x = xs[q], y = ys[q], height = hs[q];
+    const float dTdz = -0.0065f;            // constants.inc: dTdz_std_atm_lt_11000m
+    if ((x < 1.f) || (x > (float)(iew - 1)) || (y < 1.f) || (y > (float)(jns - 1))) { out[q] = OG_MISSING_R; return; }
+    const int fx = (int)floorf(x), cx = (int)ceilf(x), fy = (int)floorf(y), cy = (int)ceilf(y);
+    const int nx[4] = {fx, fx, cx, cx}, ny[4] = {fy, cy, fy, cy};
+    float tn[4];
+    const size_t lev = (size_t)iew * jns;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const size_t col = (size_t)(nx[c] - 1) * jns + (size_t)(ny[c] - 1);   // (j,i,k): j fastest
+        bool found = false;
+        float hb = 0.f, ha = 0.f, tb = 0.f, ta = 0.f;
+        for (int k = 2; k <= kbu - 1; ++k) {
+            const float h0 = h3[col + (size_t)(k - 1) * lev], h1 = h3[col + (size_t)k * lev];
+            if ((height >= h0) && (height <= h1)) {
+                found = true; hb = h0; ha = h1;
+                tb = t3[col + (size_t)(k - 1) * lev]; ta = t3[col + (size_t)k * lev];
+                break;
+            }
+        }
+        if (found) {
+            const float w = fdiv(fsub(ha, height), fsub(ha, hb));
+            tn[c] = fadd(fmul(w, tb), fmul(fsub(1.f, w), ta));
+        } else if (height < h3[col + lev]) {
+            tn[c] = fsub(t3[col + lev], fmul(dTdz, fsub(h3[col + lev], height)));
+        } else {
+            out[q] = OG_MISSING_R;          // above the top level (:93-96); the reference STOPs otherwise
+            return;
+        }
+    }
+    const float xn = fsub(x, floorf(x)), yn = fsub(y, floorf(y));
+    out[q] = fadd(fmul(fsub(1.f, xn), fadd(fmul(fsub(1.f, yn), tn[0]), fmul(yn, tn[1]))),
+                  fmul(xn, fadd(fmul(fsub(1.f, yn), tn[2]), fmul(yn, tn[3]))));
+}
+
+int fg_t_at_point_device(og_ctx* ctx, const float* t3, const float* h3, int jns, int iew, int kbu,
+                         const float* x, const float* y, const float* h, int n, float* out)
+{
+    if (n <= 0) return OG_OK;
+    fg_t_at_point_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(t3, h3, jns, iew, kbu, x, y, h, n, out);
+    ctx->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
 int local_time_device(og_ctx* ctx, int time_hhmm, const float* lon, int n, int* out)
 {
     if (n <= 0) return OG_OK;

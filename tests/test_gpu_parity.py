@@ -177,6 +177,29 @@ def test_oa_slab_multi_scan(ctx, oracle):
     np.testing.assert_array_equal(a, b)
 
 
+def test_fg_t_at_point_bit_exact(ctx, oracle):
+    """GET_FG_T_AT_POINT: trapping levels, extrapolation below level 2, missing above
+    the top and outside the domain."""
+    import ctypes as C
+    rng = np.random.default_rng(14)
+    kbu, iew, jns, n = 9, 30, 26, 2000
+    base = np.linspace(0.0, 12000.0, kbu, dtype=np.float32)[:, None, None]
+    h = (base + rng.uniform(-150, 150, (kbu, iew, jns))).astype(np.float32)
+    h = np.sort(h, axis=0)
+    t = (288.0 - 0.0065 * h + rng.normal(0, 1.0, h.shape)).astype(np.float32)
+    x = rng.uniform(0.2, iew - 0.2, n).astype(np.float32)
+    y = rng.uniform(0.2, jns - 0.2, n).astype(np.float32)
+    z = rng.uniform(-500.0, 13500.0, n).astype(np.float32)
+    x[:10] = np.arange(1, 11); y[:10] = np.arange(1, 11)          # exactly on grid points
+    got = ctx.fg_t_at_point(t, h, x, y, z)
+    L = oracle.lib()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
+    want = np.array([L.ogo_fg_t_at_point(p(t), p(h), jns, iew, kbu, float(x[k]), float(y[k]), float(z[k]))
+                     for k in range(n)], np.float32)
+    np.testing.assert_array_equal(got, want)
+    assert 50 < np.count_nonzero(want == np.float32(-888888.0)) < n - 50
+
+
 def test_local_time_bit_exact(ctx, oracle):
     rng = np.random.default_rng(2)
     lon = rng.uniform(-180, 180, 5000).astype(np.float32)
