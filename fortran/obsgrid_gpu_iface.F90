@@ -96,9 +96,30 @@ MODULE obsgrid_gpu
          TYPE ( C_PTR ) , VALUE :: aob , err , difmax , buddy_num_final   ! nullable diagnostics
       END FUNCTION og_buddy_check
 
+      INTEGER ( C_INT ) FUNCTION og_ob_density ( ctx , xob , yob , grid_dist , numobs , tobbox , &
+      iew , jns ) BIND ( C , NAME = 'og_ob_density' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: xob ( * ) , yob ( * )
+         REAL ( C_FLOAT ) , VALUE :: grid_dist
+         INTEGER ( C_INT ) , VALUE :: numobs
+         REAL ( C_FLOAT ) , INTENT ( INOUT ) :: tobbox ( * )
+         INTEGER ( C_INT ) , VALUE :: iew , jns
+      END FUNCTION og_ob_density
+
+      INTEGER ( C_INT ) FUNCTION og_obs_distance ( ctx , tobbox , distance , iew , jns , dx ) &
+      BIND ( C , NAME = 'og_obs_distance' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: tobbox ( * )
+         REAL ( C_FLOAT ) , INTENT ( OUT ) :: distance ( * )
+         INTEGER ( C_INT ) , VALUE :: iew , jns
+         REAL ( C_FLOAT ) , VALUE :: dx
+      END FUNCTION og_obs_distance
+
    END INTERFACE
 
-   PUBLIC :: og_cressman , og_error_max , og_buddy_check , og_fail
+   PUBLIC :: og_cressman , og_error_max , og_buddy_check , og_ob_density , og_obs_distance , og_fail
 
 CONTAINS
 
@@ -304,3 +325,38 @@ pressure , local_time , dx , buddy_weight , buddy_difference , print_buddy )
    END IF
 
 END SUBROUTINE buddy_check
+
+!  MODULE qc0 :: ob_density / obs_distance   (replace src/qc0_module.F90:81-119 and :123-232)
+SUBROUTINE ob_density ( xob , yob , grid_dist , numobs , tobbox , iew , jns )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   REAL    , DIMENSION ( : )      :: xob , yob
+   REAL                           :: grid_dist
+   INTEGER                        :: numobs
+   REAL    , DIMENSION ( : , : )  :: tobbox
+   INTEGER                        :: iew , jns
+
+   IF ( og_ob_density ( og_handle , xob ( 1 : numobs ) , yob ( 1 : numobs ) , grid_dist , &
+                        INT ( numobs , C_INT ) , tobbox ( 1 : jns , 1 : iew ) , &
+                        INT ( iew , C_INT ) , INT ( jns , C_INT ) ) .NE. 0 ) CALL og_fail ( 'ob_density' )
+
+END SUBROUTINE ob_density
+
+SUBROUTINE obs_distance ( tobbox , distance , iew , jns , dx )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER                                 :: jns , iew
+   REAL , INTENT ( IN )                    :: dx
+   REAL , DIMENSION ( : , : ) , INTENT ( IN )  :: tobbox
+   REAL , DIMENSION ( : , : ) , INTENT ( OUT ) :: distance
+
+   IF ( og_obs_distance ( og_handle , tobbox ( 1 : jns , 1 : iew ) , distance ( 1 : jns , 1 : iew ) , &
+                          INT ( iew , C_INT ) , INT ( jns , C_INT ) , dx ) .NE. 0 ) CALL og_fail ( 'obs_distance' )
+
+END SUBROUTINE obs_distance

@@ -179,6 +179,16 @@ int og_fg_t_at_point(og_ctx* ctx, const float* fg_3d_t, const float* fg_3d_h, in
                      int kbu, const float* x_location, const float* y_location,
                      const float* height_msl, int n, float* fg_t);
 
+/* ob_density (qc0_module.F90:81-119): tobbox(j,i) += 1 for every ob within 250 km
+ * (250./grid_dist cells) of grid point (i,j); tobbox is (jns,iew), j fastest, in/out --
+ * proc_qc.F90:350 accumulates it over the surface variables.
+ * obs_distance (qc0_module.F90:123-232): distance (same layout, same unit as dx) from every
+ * grid box to the nearest box with tobbox > 0.5; an exact Euclidean distance transform
+ * instead of the reference's O((iew*jns)^2) search. */
+int og_ob_density(og_ctx* ctx, const float* xob, const float* yob, float grid_dist, int numobs,
+                  float* tobbox, int iew, int jns);
+int og_obs_distance(og_ctx* ctx, const float* tobbox, float* distance, int iew, int jns, float dx);
+
 /* error_max followed by buddy_check on one slab in one upload (proc_qc.F90:371-392). */
 int og_qc_slab(og_ctx* ctx, int do_error_max, int do_buddy, const float* gridded, int iew,
                int jns, int var, float pressure_hpa, const float* obs, const float* xob,

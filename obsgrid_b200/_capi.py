@@ -106,6 +106,8 @@ SIGNATURES = {
                              _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, C.c_float,
                              C.c_float, _vp]),
     "og_fg_t_at_point": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
+    "og_ob_density": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, _vp, C.c_int, C.c_int]),
+    "og_obs_distance": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float]),
     "og_qc_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams)]),
     "og_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgOaParams), C.c_int, C.c_int]),
     "og_qc_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.POINTER(OgOaParams),

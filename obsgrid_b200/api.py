@@ -132,6 +132,20 @@ class Context:
                                          ptr(height), x.size, ptr(out)), "og_fg_t_at_point")
         return out
 
+    def ob_density(self, xob, yob, grid_dist, tobbox):
+        """tobbox: (iew, jns) C order == Fortran tobbox(jns,iew); returns the accumulated copy."""
+        tb = f32(tobbox).copy(); iew, jns = tb.shape
+        xob, yob = f32(xob), f32(yob)
+        check(self._lib.og_ob_density(self._h, ptr(xob), ptr(yob), grid_dist, xob.size, ptr(tb), iew, jns),
+              "og_ob_density")
+        return tb
+
+    def obs_distance(self, tobbox, dx):
+        tb = f32(tobbox); iew, jns = tb.shape
+        out = np.zeros_like(tb)
+        check(self._lib.og_obs_distance(self._h, ptr(tb), ptr(out), iew, jns, dx), "og_obs_distance")
+        return out
+
     def error_max(self, obs, xob, yob, elev, qc_flag, gridded, var, max_difference, pressure,
                   local_t):
         g = f32(gridded); jns, iew = g.shape

@@ -332,6 +332,37 @@ extern "C" int og_fg_t_at_point(og_ctx* c, const float* fg_3d_t, const float* fg
     return OG_OK;
 }
 
+extern "C" int og_ob_density(og_ctx* c, const float* xob, const float* yob, float grid_dist, int n,
+                             float* tobbox, int iew, int jns)
+{
+    REQUIRE(c && tobbox && n >= 0 && iew > 2 && jns > 2 && iew <= 32000 && jns <= 32000, "bad argument");
+    REQUIRE(grid_dist > 0.f, "grid_dist must be positive");
+    if (n == 0) return OG_OK;
+    REQUIRE(xob && yob, "null observation array");
+    const size_t npts = (size_t)iew * jns;
+    float *d_x, *d_y, *d_t;
+    OG_TRY(upload(c, "io.x", xob, (size_t)n, &d_x));
+    OG_TRY(upload(c, "io.y", yob, (size_t)n, &d_y));
+    OG_TRY(upload(c, "io.tobbox", tobbox, npts, &d_t));
+    OG_TRY(ob_density_device(c, d_x, d_y, grid_dist, n, d_t, iew, jns));
+    OG_TRY(download(c, tobbox, d_t, npts));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
+extern "C" int og_obs_distance(og_ctx* c, const float* tobbox, float* distance, int iew, int jns, float dx)
+{
+    REQUIRE(c && tobbox && distance && iew > 0 && jns > 0 && iew <= 32000 && jns <= 32000, "bad argument");
+    const size_t npts = (size_t)iew * jns;
+    float *d_t, *d_d;
+    OG_TRY(upload(c, "io.tobbox", tobbox, npts, &d_t));
+    OG_TRY(c->reserve_t("io.odis", npts, &d_d));
+    OG_TRY(obs_distance_device(c, d_t, d_d, iew, jns, dx));
+    OG_TRY(download(c, distance, d_d, npts));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
 // shared body of og_error_max / og_buddy_check / og_qc_slab
 static int qc_slab_common(og_ctx* c, int do_emax, int do_buddy, const float* gridded, int iew,
                           int jns, int var, float pressure, const float* obs, const float* xob,

@@ -179,6 +179,11 @@ struct BinLists {
 int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, const short4* d_box,
               bool sorted, BinLists* out);
 
+// ---- density / distance (og_density.cu) -------------------------------------------------
+int ob_density_device(og_ctx* ctx, const float* d_x, const float* d_y, float grid_dist, int n,
+                      float* d_tobbox, int iew, int jns);
+int obs_distance_device(og_ctx* ctx, const float* d_tobbox, float* d_distance, int iew, int jns, float dx);
+
 // ---- misc (og_misc.cu) ---------------------------------------------------------------
 const char* last_error();
 int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches);

@@ -626,6 +626,49 @@ void ogo_buddy_check(const float* obs, int numobs, const float* xob, const float
     free(buddy_num); free(buddy_num_final); free(buddy_num_index);
 }
 
+/* qc0_module.F90:81-119 */
+void ogo_ob_density(const float* xob, const float* yob, float grid_dist, int numobs,
+                    float* tobbox, int iew, int jns)
+{
+#define TB(j, i) tobbox[(size_t)((i)-1) * jns + (size_t)((j)-1)]
+    for (int num = 0; num < numobs; ++num) {
+        int iob = (int)xob[num], job = (int)yob[num];
+        int rr = f_nint(250.f / grid_dist);
+        int jobs = imax(job - rr - 1, 1), jobe = imin(job + rr + 1, jns - 1);
+        int iobs = imax(iob - rr - 1, 1), iobe = imin(iob + rr + 1, iew - 1);
+        for (int j = jobs; j <= jobe; ++j)
+            for (int i = iobs; i <= iobe; ++i) {
+                float dist = sqrtf(((float)i - xob[num]) * ((float)i - xob[num]) +
+                                   ((float)j - yob[num]) * ((float)j - yob[num]));
+                if (dist < 250.f / grid_dist) TB(j, i) = TB(j, i) + 1.f;
+            }
+    }
+#undef TB
+}
+
+/* qc0_module.F90:123-232 */
+void ogo_obs_distance(const float* tobbox, float* distance, int iew, int jns, float dx)
+{
+#define IX(j, i) ((size_t)((i)-1) * jns + (size_t)((j)-1))
+    float domain_diagonal_m = sqrtf((float)(iew - 1) * dx * (float)(iew - 1) * dx +
+                                    (float)(jns - 1) * dx * (float)(jns - 1) * dx);
+    float domain_diagonal_grid_cells = domain_diagonal_m / dx;
+    for (int i = 1; i <= iew; ++i)
+        for (int j = 1; j <= jns; ++j) {
+            if (tobbox[IX(j, i)] > 0.5f) { distance[IX(j, i)] = 0.0f; continue; }
+            float dijmin = domain_diagonal_grid_cells;
+            for (int ii = 1; ii <= iew; ++ii)
+                for (int jj = 1; jj <= jns; ++jj)
+                    if (tobbox[IX(jj, ii)] > 0.5f) {
+                        int di = abs(ii - i), dj = abs(jj - j);
+                        float dij = sqrtf((float)dj * (float)dj + (float)di * (float)di); /* dij_lookup */
+                        if (dij < dijmin) dijmin = dij;
+                    }
+            distance[IX(j, i)] = dijmin * dx;
+        }
+#undef IX
+}
+
 /* get_fg_at_point_module.F90:36-114 (after latlon_to_ij) */
 float ogo_fg_t_at_point(const float* t3d, const float* h3d, int jns, int iew, int kbu,
                         float x_location, float y_location, float height_msl)

@@ -74,6 +74,12 @@ void ogo_buddy_check(const float* obs, int n, const float* xob, const float* yob
                      float buddy_weight, float buddy_difference,
                      float* aob, float* err, float* difmax, int* buddy_num_final);
 
+/* ob_density / obs_distance (qc0_module.F90:81-232): observation density and distance to the
+ * nearest observed grid box for the surface FDDA.  tobbox / distance are (jns,iew), j fastest. */
+void ogo_ob_density(const float* xob, const float* yob, float grid_dist, int numobs,
+                    float* tobbox, int iew, int jns);
+void ogo_obs_distance(const float* tobbox, float* distance, int iew, int jns, float dx);
+
 /* DEWPOINT first-guess field of proc_qc.F90:315-319 and dewpoint ob of
  * ob_access_module.F90:476-486 (same formula). */
 float ogo_dewpoint(float t, float rh);

@@ -44,6 +44,8 @@ def lib():
         l.ogo_fg_t_at_point.restype = C.c_float
         l.ogo_fg_t_at_point.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float,
                                         C.c_float, C.c_float]
+        l.ogo_ob_density.argtypes = [_vp, _vp, C.c_float, C.c_int, _vp, C.c_int, C.c_int]
+        l.ogo_obs_distance.argtypes = [_vp, _vp, C.c_int, C.c_int, C.c_float]
         l.ogo_innovation.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_float,
                                      C.c_int, _vp, _vp]
         l.ogo_cressman.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int,
@@ -185,6 +187,21 @@ def add_to_qc_flag(q, add):
     v = C.c_int(int(q))
     lib().ogo_add_to_qc_flag(C.byref(v), add)
     return v.value
+
+
+def ob_density(xob, yob, grid_dist, tobbox):
+    """tobbox: (iew, jns) C order == Fortran tobbox(jns,iew); returns the accumulated copy."""
+    tb = f32(tobbox).copy(); iew, jns = tb.shape
+    xob, yob = f32(xob), f32(yob)
+    lib().ogo_ob_density(ptr(xob), ptr(yob), C.c_float(grid_dist), xob.size, ptr(tb), iew, jns)
+    return tb
+
+
+def obs_distance(tobbox, dx):
+    tb = f32(tobbox); iew, jns = tb.shape
+    out = np.zeros_like(tb)
+    lib().ogo_obs_distance(ptr(tb), ptr(out), iew, jns, C.c_float(dx))
+    return out
 
 
 def dewpoint(t, rh):

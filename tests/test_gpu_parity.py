@@ -200,6 +200,23 @@ def test_fg_t_at_point_bit_exact(ctx, oracle):
     assert 50 < np.count_nonzero(want == np.float32(-888888.0)) < n - 50
 
 
+@pytest.mark.parametrize("iew,jns,n,gd", [(60, 45, 300, 30.0), (33, 70, 40, 12.0), (40, 40, 0, 30.0), (90, 64, 2500, 50.0)])
+def test_ob_density_and_obs_distance_bit_exact(ctx, oracle, iew, jns, n, gd):
+    """qc0_module.F90:81-232; the distance is an exact EDT on the device."""
+    rng = np.random.default_rng(iew + n)
+    x = rng.uniform(-3.0, iew + 3.0, n).astype(np.float32)      # some obs outside the domain
+    y = rng.uniform(-3.0, jns + 3.0, n).astype(np.float32)
+    tb0 = (rng.random((iew, jns)) < 0.02).astype(np.float32) * 3.0
+    a = oracle.ob_density(x, y, gd, tb0)
+    b = ctx.ob_density(x, y, gd, tb0)
+    np.testing.assert_array_equal(a, b)
+    # sparse occupancy for the distance: a handful of observed boxes, then none, then the density field
+    for tb in ((rng.random((iew, jns)) < 0.004).astype(np.float32), np.zeros((iew, jns), np.float32),
+               np.where(a / 5.0 < 1.0, 0.0, a / 5.0).astype(np.float32)):
+        for dx in (gd, 1.0, 3000.0):
+            np.testing.assert_array_equal(oracle.obs_distance(tb, dx), ctx.obs_distance(tb, dx))
+
+
 def test_local_time_bit_exact(ctx, oracle):
     rng = np.random.default_rng(2)
     lon = rng.uniform(-180, 180, 5000).astype(np.float32)

@@ -379,3 +379,32 @@ def test_fg_t_at_point(oracle):
     # above the top or outside the domain: missing
     assert L.ogo_fg_t_at_point(ptr(t), ptr(h), jns, iew, kbu, 3.5, 2.25, 9000.0) == f(-888888.0)
     assert L.ogo_fg_t_at_point(ptr(t), ptr(h), jns, iew, kbu, 0.5, 2.25, 2500.0) == f(-888888.0)
+
+
+def test_ob_density_and_obs_distance_by_hand(oracle):
+    """qc0_module.F90:81-232 on a case small enough to do by hand."""
+    iew, jns = 12, 9
+    tb = np.zeros((iew, jns), np.float32)               # Fortran tobbox(jns,iew)
+    # one ob at (x,y) = (4.3, 5.6), grid_dist 100 km -> radius 2.5 cells, window INT() +- 4
+    out = oracle.ob_density([4.3], [5.6], 100.0, tb)
+    want = np.zeros_like(tb)
+    for i in range(1, iew):            # i <= iew-1
+        for j in range(1, jns):        # j <= jns-1
+            if np.sqrt(np.float32((i - 4.3) ** 2 + (j - 5.6) ** 2)) < 2.5:
+                want[i - 1, j - 1] = 1.0
+    assert want.sum() == 19 or want.sum() == 20 or want.sum() == 21   # a disc of radius 2.5 cells
+    np.testing.assert_array_equal(out, want)
+    # accumulation: a second call adds on top
+    out2 = oracle.ob_density([4.3, 11.9], [5.6, 8.9], 100.0, out)
+    assert out2[3, 5] == 2.0 and out2[iew - 1].sum() == 0 and out2[:, jns - 1].sum() == 0
+    # distance: boxes (i,j) = (2,3) and (10,7) observed, dx = 3
+    tb = np.zeros((iew, jns), np.float32)
+    tb[1, 2] = 1.0; tb[9, 6] = 0.6; tb[5, 5] = 0.5        # 0.5 is not > 0.5
+    d = oracle.obs_distance(tb, 3.0)
+    assert d[1, 2] == 0.0 and d[9, 6] == 0.0
+    assert d[5, 5] == np.float32(np.sqrt(np.float32(16 + 1))) * np.float32(3.0)     # nearest: (10,7)
+    assert d[0, 0] == np.float32(np.sqrt(np.float32(1 + 4))) * np.float32(3.0)
+    # no observed box at all: the domain diagonal (in cells) times dx
+    d0 = oracle.obs_distance(np.zeros((iew, jns), np.float32), 3.0)
+    diag = np.sqrt(np.float32(np.float32(11 * 3.0) * 11 * 3.0 + np.float32(8 * 3.0) * 8 * 3.0)) / np.float32(3.0)
+    assert np.all(d0 == np.float32(diag) * np.float32(3.0))
