@@ -61,6 +61,23 @@ def test_cressman_circle_bit_exact(ctx, oracle, var, iew, jns, n, R):
     np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize("var", [3, 1])
+def test_cressman_crsdot_zero_and_odd_grids(ctx, oracle, var):
+    """crsdot = 0 (dot-point variables update the last row / column too) and grids that are not
+    a multiple of the 32-point cell."""
+    rng = np.random.default_rng(var)
+    for iew, jns in ((33, 31), (65, 97), (5, 7)):
+        n = max(4, iew * jns // 20)
+        g = wavy(iew, jns)
+        ub, vb = wind_fields(iew, jns, jet=45.0, curl=False)
+        x, y = rng_obs(rng, n, iew, jns, lo=1.0)
+        d = rng.normal(0, 3, n).astype(np.float32)
+        for crsdot in (0, 1):
+            a = oracle.cressman(d, x, y, g, var, 4, 12.0, ub, vb, 300.0, crsdot=crsdot)
+            b = ctx.cressman(d, x, y, g, var, 4, 12.0, ub, vb, 300.0, crsdot=crsdot)
+            np.testing.assert_array_equal(a, b, err_msg=f"{iew}x{jns} crsdot={crsdot}")
+
+
 def test_cressman_dense_cluster_overflows_staging(ctx, oracle):
     """More candidates per tile than the shared-memory staging holds (batched consumption)."""
     rng = np.random.default_rng(5)
