@@ -274,15 +274,35 @@ __global__ void __launch_bounds__(BIN_THREADS) cell_sort_small_kernel(BinDev A, 
     const int* __restrict__ in = A.cell_list + A.cell_start[c];
     int* __restrict__ out = A.cell_sorted + A.cell_start[c];
     int* k = s_k[warp];
-    for (int t = lane; t < L; t += 32) k[t] = in[t];
-    __syncwarp();
-    for (int t = lane; t < L; t += 32) {
-        const int key = k[t];
-        int rank = 0;
-#pragma unroll 4
-        for (int j = 0; j < L; ++j) rank += (k[j] < key) ? 1 : 0;
-        out[rank] = key;
+    if (L <= 24) {          // rank by counting
+        for (int t = lane; t < L; t += 32) k[t] = in[t];
+        __syncwarp();
+        for (int t = lane; t < L; t += 32) {
+            const int key = k[t];
+            int rank = 0;
+            for (int j = 0; j < L; ++j) rank += (k[j] < key) ? 1 : 0;
+            out[rank] = key;
+        }
+        return;
     }
+    // bitonic network over the warp's shared-memory row, padded to a power of two
+    int P = 32;
+    while (P < L) P <<= 1;
+    for (int t = lane; t < P; t += 32) k[t] = (t < L) ? in[t] : 0x7fffffff;
+    __syncwarp();
+    for (int kk = 2; kk <= P; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int hi = lo | j;
+                const bool up = ((lo & kk) == 0);
+                const int a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+            }
+            __syncwarp();
+        }
+    }
+    for (int t = lane; t < L; t += 32) out[t] = k[t];
 }
 
 __global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A)

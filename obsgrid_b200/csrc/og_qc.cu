@@ -224,27 +224,33 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
 // Per cell, the index-ordered sub-list of its candidates that can ever be removed from a
 // buddy set: diff > 1.25*difmax with either the plain or the relaxed difmax
 // (qc2_module.F90:277-282; flagged per ob by qc_prep_kernel).
-__global__ void __launch_bounds__(256) suspect_kernel(QcDev A)
+__global__ void __launch_bounds__(128) suspect_kernel(QcDev A)
 {
     const QcSlabDev& S = A.slabs[blockIdx.y];
-    const int lane = threadIdx.x & 31;
-    const int lc = blockIdx.x * 8 + (threadIdx.x >> 5);      // one warp per cell
-    if (lc >= S.ncx * S.ncy) return;
-    const int c = S.cell_off + lc;
+    if ((int)blockIdx.x >= S.ncx * S.ncy) return;
+    const int c = S.cell_off + blockIdx.x;
     const int L = (A.home_count[c] > 0) ? A.range_count[c] : 0;   // cells without targets are never read
     const int* __restrict__ cl = A.range_list + A.range_start[c];
     int* __restrict__ out = A.susp_list + A.range_start[c];
+    __shared__ int s_w[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int done = 0;
-    for (int base = 0; base < L; base += 32) {
-        const int k = base + lane;
+    for (int base = 0; base < L; base += 128) {
+        const int k = base + threadIdx.x;
         int lk = 0;
         bool sp = false;
         if (k < L) { lk = cl[k]; sp = A.susp[S.ob_off + lk] != 0; }
         const unsigned m = __ballot_sync(0xffffffffu, sp);
-        if (sp) out[done + __popc(m & ((1u << lane) - 1u))] = lk;
-        done += __popc(m);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { int v = s_w[w]; woff += (w < warp) ? v : 0; tot += v; }
+        if (sp) out[done + woff + __popc(m & ((1u << lane) - 1u))] = lk;
+        done += tot;
+        __syncthreads();
     }
-    if (lane == 0) A.susp_count[c] = done;
+    if (threadIdx.x == 0) A.susp_count[c] = done;
 }
 
 // remove_bad_ob + err (qc2_module.F90:269-327) for one relaxation mask.
@@ -528,7 +534,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         const int tslot = ctx->timer_begin(1);
         buddy_pass1_kernel<<<(unsigned)max_items, BP_THREADS, 0, st>>>(A);
         ctx->timer_end(tslot);
-        suspect_kernel<<<dim3((max_cells + 7) / 8, ns), 256, 0, st>>>(A);
+        suspect_kernel<<<dim3(max_cells, ns), 128, 0, st>>>(A);
         ctx->count_launch(3);
         int iters = 0;
         for (;;) {
