@@ -42,10 +42,48 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
     }
 }
 
+// 64x64 tiles, 128-bit global accesses on both sides (both extents a multiple of 4).
+__global__ void __launch_bounds__(256) transpose4_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                         float* __restrict__ dst2, int nfast, int nslow)
+{
+    __shared__ float tile[64][65];
+    const size_t lev = (size_t)blockIdx.z * (size_t)nfast * (size_t)nslow;
+    const int f0 = blockIdx.x * 64, s0 = blockIdx.y * 64;
+    const int c4 = (threadIdx.x & 15) * 4, r = threadIdx.x >> 4;        // 16 float4 per row, 16 rows per pass
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int s = s0 + r + 16 * p, f = f0 + c4;
+        if (s < nslow && f < nfast) {
+            const float4 v = *reinterpret_cast<const float4*>(src + lev + (size_t)s * nfast + f);
+            tile[r + 16 * p][c4] = v.x; tile[r + 16 * p][c4 + 1] = v.y;
+            tile[r + 16 * p][c4 + 2] = v.z; tile[r + 16 * p][c4 + 3] = v.w;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int f = f0 + r + 16 * p, s = s0 + c4;
+        if (f < nfast && s < nslow) {
+            const float4 v = make_float4(tile[c4][r + 16 * p], tile[c4 + 1][r + 16 * p],
+                                         tile[c4 + 2][r + 16 * p], tile[c4 + 3][r + 16 * p]);
+            *reinterpret_cast<float4*>(dst + lev + (size_t)f * nslow + s) = v;
+            if (dst2) *reinterpret_cast<float4*>(dst2 + lev + (size_t)f * nslow + s) = v;
+        }
+    }
+}
+
 int transpose_levels(og_ctx* ctx, const float* src, float* dst, int nfast, int nslow, int nlev,
                      float* dst2)
 {
     if (nlev <= 0) return OG_OK;
+    const bool aligned = ((nfast | nslow) & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst | (uintptr_t)dst2) & 15) == 0;
+    if (aligned) {
+        dim3 grd((nfast + 63) / 64, (nslow + 63) / 64, nlev);
+        transpose4_kernel<<<grd, 256, 0, ctx->stream>>>(src, dst, dst2, nfast, nslow);
+        ctx->count_launch();
+        OG_CUDA(cudaGetLastError());
+        return OG_OK;
+    }
     dim3 blk(32, 8), grd((nfast + 31) / 32, (nslow + 31) / 32, nlev);
     transpose_kernel<<<grd, blk, 0, ctx->stream>>>(src, dst, dst2, nfast, nslow);
     ctx->count_launch();
