@@ -31,7 +31,7 @@ def add_flag(q, t):   # qc0_module.F90:27-31 / :55-72
 
 
 def cressman(obs, xob, yob, gridded, name, R, dxd, u_b=None, v_b=None, pressure=1001.0,
-             use_first_guess=True, fg_value=None, scale_rh=False, crsdot=1):
+             use_first_guess=True, fg_value=None, scale_rh=False, crsdot=1, stats=None):
     """gridded: (jns, iew) C-order array == Fortran gridded(iew,jns); returns the analysed copy."""
     g = np.array(gridded, np.float32)
     jns, iew = g.shape
@@ -109,6 +109,9 @@ def cressman(obs, xob, yob, gridded, name, R, dxd, u_b=None, v_b=None, pressure=
             d2 = xx * xx / elong + yy * yy
         d2 = d2.astype(np.float32)
         hit = d2 < r2
+        if stats is not None:
+            st = stats.setdefault(kind, [0, 0, 0])
+            st[0] += 1; st[1] += hit.size; st[2] += int(np.count_nonzero(hit))
         w = ((r2 - d2) / (r2 + d2)).astype(np.float32)
         sf = np.ones_like(w)
         if scale_rh and name == "RH" and use_first_guess and ob < F(0.0):
