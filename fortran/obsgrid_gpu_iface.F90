@@ -117,9 +117,37 @@ MODULE obsgrid_gpu
          REAL ( C_FLOAT ) , VALUE :: dx
       END FUNCTION og_obs_distance
 
+      INTEGER ( C_INT ) FUNCTION og_wind_increment_to_c_grid ( ctx , u , uA , uC , v , vA , vC , &
+      jns , iew , kbu ) BIND ( C , NAME = 'og_wind_increment_to_c_grid' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( INOUT ) :: u ( * ) , v ( * )
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: uA ( * ) , uC ( * ) , vA ( * ) , vC ( * )
+         INTEGER ( C_INT ) , VALUE :: jns , iew , kbu
+      END FUNCTION og_wind_increment_to_c_grid
+
+      INTEGER ( C_INT ) FUNCTION og_pres_sfc_from_slp ( ctx , pres_sfc , slp_C , slp_x , out , &
+      jns , iew ) BIND ( C , NAME = 'og_pres_sfc_from_slp' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: pres_sfc ( * ) , slp_C ( * ) , slp_x ( * )
+         REAL ( C_FLOAT ) , INTENT ( OUT ) :: out ( * )
+         INTEGER ( C_INT ) , VALUE :: jns , iew
+      END FUNCTION og_pres_sfc_from_slp
+
+      INTEGER ( C_INT ) FUNCTION og_mixing_ratio ( ctx , rh , t , h , terrain , slp_x , pressure , &
+      iew , jns , kbu , qv , psfc ) BIND ( C , NAME = 'og_mixing_ratio' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( INOUT ) :: rh ( * ) , qv ( * ) , psfc ( * )
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: t ( * ) , h ( * ) , terrain ( * ) , slp_x ( * ) , pressure ( * )
+         INTEGER ( C_INT ) , VALUE :: iew , jns , kbu
+      END FUNCTION og_mixing_ratio
+
    END INTERFACE
 
    PUBLIC :: og_cressman , og_error_max , og_buddy_check , og_ob_density , og_obs_distance , og_fail
+   PUBLIC :: og_wind_increment_to_c_grid , og_pres_sfc_from_slp , og_mixing_ratio
 
 CONTAINS
 
@@ -360,3 +388,62 @@ SUBROUTINE obs_distance ( tobbox , distance , iew , jns , dx )
                           INT ( iew , C_INT ) , INT ( jns , C_INT ) , dx ) .NE. 0 ) CALL og_fail ( 'obs_distance' )
 
 END SUBROUTINE obs_distance
+
+!  MODULE final_analysis :: mixing_ratio   (replaces src/final_analysis_module.F90:1026-1201,
+!  sfcprs included; called from proc_oa.F90:346)
+SUBROUTINE mixing_ratio ( rh , t , h , terrain , slp_x , pressure , iew_alloc , jns_alloc , kbu_alloc , &
+                          qv , psfc )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER , INTENT ( IN ) :: iew_alloc , jns_alloc , kbu_alloc
+   REAL , INTENT ( IN ) , DIMENSION ( kbu_alloc ) :: pressure
+   REAL , INTENT ( IN ) , DIMENSION ( jns_alloc , iew_alloc ) :: terrain , slp_x
+   REAL , INTENT ( INOUT ) , DIMENSION ( jns_alloc , iew_alloc , kbu_alloc ) :: rh
+   REAL , INTENT ( IN ) , DIMENSION ( jns_alloc , iew_alloc , kbu_alloc ) :: t , h
+   REAL , INTENT ( INOUT ) , DIMENSION ( jns_alloc , iew_alloc , kbu_alloc ) :: qv
+   REAL , INTENT ( INOUT ) , DIMENSION ( jns_alloc , iew_alloc ) :: psfc
+
+   !  a missing 850/700/500 hPa level is the reference's STOP 'No_find_levels' (:1122-1127)
+   IF ( og_mixing_ratio ( og_handle , rh , t , h , terrain , slp_x , pressure , INT ( iew_alloc , C_INT ) , &
+                          INT ( jns_alloc , C_INT ) , INT ( kbu_alloc , C_INT ) , qv , psfc ) .NE. 0 ) &
+      CALL og_fail ( 'mixing_ratio' )
+
+END SUBROUTINE mixing_ratio
+
+!  write_analysis, src/final_analysis_module.F90:316-319 and :336-339: the two statements
+!     pertubation = u - uA ; CALL crs2dot_pertU ( pertubation , ... ) ; u = uC + pertubation
+!  (and the V twin) become one call
+SUBROUTINE wind_increment_to_c_grid ( u , uA , uC , v , vA , vC , jns_alloc , iew_alloc , kbu_alloc )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER , INTENT ( IN ) :: jns_alloc , iew_alloc , kbu_alloc
+   REAL , INTENT ( INOUT ) , DIMENSION ( jns_alloc , iew_alloc , kbu_alloc ) :: u , v
+   REAL , INTENT ( IN ) , DIMENSION ( jns_alloc , iew_alloc , kbu_alloc ) :: uA , uC , vA , vC
+
+   IF ( og_wind_increment_to_c_grid ( og_handle , u , uA , uC , v , vA , vC , INT ( jns_alloc , C_INT ) , &
+                                      INT ( iew_alloc , C_INT ) , INT ( kbu_alloc , C_INT ) ) .NE. 0 ) &
+      CALL og_fail ( 'wind_increment_to_c_grid' )
+
+END SUBROUTINE wind_increment_to_c_grid
+
+!  write_analysis, src/final_analysis_module.F90:364-370 (inside IF ( .NOT. oa_psfc ))
+SUBROUTINE pres_sfc_from_slp ( pres_sfc , slp_C , slp_x , out , jns_alloc , iew_alloc )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER , INTENT ( IN ) :: jns_alloc , iew_alloc
+   REAL , INTENT ( IN ) , DIMENSION ( jns_alloc , iew_alloc ) :: pres_sfc , slp_C , slp_x
+   REAL , INTENT ( OUT ) , DIMENSION ( jns_alloc , iew_alloc ) :: out
+
+   IF ( og_pres_sfc_from_slp ( og_handle , pres_sfc , slp_C , slp_x , out , INT ( jns_alloc , C_INT ) , &
+                               INT ( iew_alloc , C_INT ) ) .NE. 0 ) CALL og_fail ( 'pres_sfc_from_slp' )
+
+END SUBROUTINE pres_sfc_from_slp

@@ -189,6 +189,30 @@ int og_ob_density(og_ctx* ctx, const float* xob, const float* yob, float grid_di
                   float* tobbox, int iew, int jns);
 int og_obs_distance(og_ctx* ctx, const float* tobbox, float* distance, int iew, int jns, float dx);
 
+/* ---- post-analysis epilogue (host arrays, blocking) ------------------
+ * 3-D arrays are the reference's (jns,iew,kbu), j fastest (first_guess.inc:1-11).
+ *
+ * write_analysis, final_analysis_module.F90:316-319 and :336-339, with crs2dot_pertU / _pertV
+ * (first_guess_module.F90:59-91): the increment the analysis made on the A grid (u - uA) is
+ * averaged onto the staggered points and added to the incoming C-grid wind; u and v are
+ * replaced by the result (in/out).  Either triple may be NULL.  Bit-identical FP32. */
+int og_wind_increment_to_c_grid(og_ctx* ctx, float* u, const float* uA, const float* uC,
+                                float* v, const float* vA, const float* vC,
+                                int jns, int iew, int kbu);
+/* final_analysis_module.F90:364-370: out = pres + (pres/slp_C)*(slp_x - slp_C) for the surface
+ * level of PRES (skipped by the caller when oa_psfc).  (jns,iew) arrays.  Bit-identical FP32. */
+int og_pres_sfc_from_slp(og_ctx* ctx, const float* pres_sfc, const float* slp_C,
+                         const float* slp_x, float* out, int jns, int iew);
+/* mixing_ratio + sfcprs, final_analysis_module.F90:1026-1201 (called from proc_oa.F90:346):
+ * clamps rh to [1,100] in place on (1:jns-1,1:iew-1,:), fills qv on those points of every
+ * level and psfc (Pa; slp_x in Pa) on the same points of the surface; other entries of qv /
+ * psfc keep the caller's values.  OG_ERR_INVALID when `pressure` lacks the 850, 700 or 500 hPa
+ * level (the reference STOPs, :1122-1127).  EXP/LOG/** are evaluated in FP64 and rounded once:
+ * results agree with the glibc-based reference to ~1 ulp, not bit for bit. */
+int og_mixing_ratio(og_ctx* ctx, float* rh, const float* t, const float* h, const float* terrain,
+                    const float* slp_x, const float* pressure, int iew, int jns, int kbu,
+                    float* qv, float* psfc);
+
 /* error_max followed by buddy_check on one slab in one upload (proc_qc.F90:371-392). */
 int og_qc_slab(og_ctx* ctx, int do_error_max, int do_buddy, const float* gridded, int iew,
                int jns, int var, float pressure_hpa, const float* obs, const float* xob,

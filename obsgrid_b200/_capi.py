@@ -108,6 +108,9 @@ SIGNATURES = {
     "og_fg_t_at_point": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "og_ob_density": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, _vp, C.c_int, C.c_int]),
     "og_obs_distance": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float]),
+    "og_wind_increment_to_c_grid": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int]),
+    "og_pres_sfc_from_slp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "og_mixing_ratio": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "og_qc_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams)]),
     "og_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgOaParams), C.c_int, C.c_int]),
     "og_qc_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.POINTER(OgOaParams),

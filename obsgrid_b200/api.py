@@ -146,6 +146,34 @@ class Context:
         check(self._lib.og_obs_distance(self._h, ptr(tb), ptr(out), iew, jns, dx), "og_obs_distance")
         return out
 
+    # ---- post-analysis epilogue (3-D arrays: (kbu, iew, jns) C order == Fortran (jns,iew,kbu)) ----
+    def wind_increment_to_c_grid(self, u, uA, uC, v, vA, vC):
+        """write_analysis :316-339: u = uC + crs2dot_pertU(u - uA), v = vC + crs2dot_pertV(v - vA)."""
+        u, v = f32(u).copy(), f32(v).copy()
+        uA, uC, vA, vC = f32(uA), f32(uC), f32(vA), f32(vC)
+        kbu, iew, jns = u.shape
+        check(self._lib.og_wind_increment_to_c_grid(self._h, ptr(u), ptr(uA), ptr(uC), ptr(v), ptr(vA),
+                                                    ptr(vC), jns, iew, kbu), "og_wind_increment_to_c_grid")
+        return u, v
+
+    def pres_sfc_from_slp(self, pres_sfc, slp_C, slp_x):
+        p, c, x = f32(pres_sfc), f32(slp_C), f32(slp_x)
+        iew, jns = p.shape
+        out = np.zeros_like(p)
+        check(self._lib.og_pres_sfc_from_slp(self._h, ptr(p), ptr(c), ptr(x), ptr(out), jns, iew),
+              "og_pres_sfc_from_slp")
+        return out
+
+    def mixing_ratio(self, rh, t, h, terrain, slp_x_pa, pressure):
+        """mixing_ratio + sfcprs; returns (rh clamped, qv, psfc)."""
+        rh = f32(rh).copy(); t, h = f32(t), f32(h)
+        terrain, slp, pressure = f32(terrain), f32(slp_x_pa), f32(pressure)
+        kbu, iew, jns = rh.shape
+        qv = np.zeros_like(rh); psfc = np.zeros((iew, jns), np.float32)
+        check(self._lib.og_mixing_ratio(self._h, ptr(rh), ptr(t), ptr(h), ptr(terrain), ptr(slp),
+                                        ptr(pressure), iew, jns, kbu, ptr(qv), ptr(psfc)), "og_mixing_ratio")
+        return rh, qv, psfc
+
     def error_max(self, obs, xob, yob, elev, qc_flag, gridded, var, max_difference, pressure,
                   local_t):
         g = f32(gridded); jns, iew = g.shape

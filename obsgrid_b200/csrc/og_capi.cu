@@ -363,6 +363,73 @@ extern "C" int og_obs_distance(og_ctx* c, const float* tobbox, float* distance, 
     return OG_OK;
 }
 
+// ---- post-analysis epilogue -------------------------------------------
+extern "C" int og_wind_increment_to_c_grid(og_ctx* c, float* u, const float* uA, const float* uC,
+                                           float* v, const float* vA, const float* vC, int jns,
+                                           int iew, int kbu)
+{
+    REQUIRE(c && jns >= 2 && iew >= 2 && kbu >= 1 && kbu <= 65535 && iew <= 65535, "bad argument");
+    REQUIRE((u && uA && uC) || (v && vA && vC), "null field");
+    const size_t n = (size_t)jns * iew * kbu;
+    for (int dir = 0; dir < 2; ++dir) {
+        float* w = dir ? v : u;
+        const float* wA = dir ? vA : uA;
+        const float* wC = dir ? vC : uC;
+        if (!w) continue;
+        REQUIRE(wA && wC, "null A-grid or C-grid wind");
+        float *d_w, *d_a, *d_c, *d_o;
+        OG_TRY(upload(c, "fin.w", w, n, &d_w));
+        OG_TRY(upload(c, "fin.wA", wA, n, &d_a));
+        OG_TRY(upload(c, "fin.wC", wC, n, &d_c));
+        OG_TRY(c->reserve_t("fin.out", n, &d_o));
+        OG_TRY(wind_increment_device(c, dir, d_w, d_a, d_c, d_o, jns, iew, kbu));
+        OG_TRY(download(c, w, d_o, n));
+        OG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return OG_OK;
+}
+
+extern "C" int og_pres_sfc_from_slp(og_ctx* c, const float* pres_sfc, const float* slp_C,
+                                    const float* slp_x, float* out, int jns, int iew)
+{
+    REQUIRE(c && pres_sfc && slp_C && slp_x && out && jns > 0 && iew > 0, "bad argument");
+    const size_t n = (size_t)jns * iew;
+    float *d_p, *d_c, *d_x, *d_o;
+    OG_TRY(upload(c, "fin.w", pres_sfc, n, &d_p));
+    OG_TRY(upload(c, "fin.wA", slp_C, n, &d_c));
+    OG_TRY(upload(c, "fin.wC", slp_x, n, &d_x));
+    OG_TRY(c->reserve_t("fin.out", n, &d_o));
+    OG_TRY(pres_sfc_device(c, d_p, d_c, d_x, d_o, n));
+    OG_TRY(download(c, out, d_o, n));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
+extern "C" int og_mixing_ratio(og_ctx* c, float* rh, const float* t, const float* h,
+                               const float* terrain, const float* slp_x, const float* pressure,
+                               int iew, int jns, int kbu, float* qv, float* psfc)
+{
+    REQUIRE(c && rh && t && h && terrain && slp_x && pressure && qv && psfc, "null argument");
+    REQUIRE(iew >= 2 && jns >= 2 && kbu >= 2 && iew <= 65535, "bad dimensions");
+    const size_t per = (size_t)jns * iew, n = per * kbu;
+    float *d_rh, *d_t, *d_h, *d_ter, *d_slp, *d_p, *d_qv, *d_ps;
+    OG_TRY(upload(c, "fin.w", rh, n, &d_rh));
+    OG_TRY(upload(c, "fin.wA", t, n, &d_t));
+    OG_TRY(upload(c, "fin.wC", h, n, &d_h));
+    OG_TRY(upload(c, "fin.ter", terrain, per, &d_ter));
+    OG_TRY(upload(c, "fin.slp", slp_x, per, &d_slp));
+    OG_TRY(upload(c, "fin.p", pressure, (size_t)kbu, &d_p));
+    // qv / psfc are only written on the cross points (1:jns-1, 1:iew-1): keep the caller's values elsewhere
+    OG_TRY(upload(c, "fin.out", qv, n, &d_qv));
+    OG_TRY(upload(c, "fin.ps", psfc, per, &d_ps));
+    OG_TRY(mixing_ratio_device(c, d_rh, d_t, d_h, d_ter, d_slp, d_p, pressure, iew, jns, kbu, d_qv, d_ps));
+    OG_TRY(download(c, rh, d_rh, n));
+    OG_TRY(download(c, qv, d_qv, n));
+    OG_TRY(download(c, psfc, d_ps, per));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
 // shared body of og_error_max / og_buddy_check / og_qc_slab
 static int qc_slab_common(og_ctx* c, int do_emax, int do_buddy, const float* gridded, int iew,
                           int jns, int var, float pressure, const float* obs, const float* xob,

@@ -184,6 +184,15 @@ int ob_density_device(og_ctx* ctx, const float* d_x, const float* d_y, float gri
                       float* d_tobbox, int iew, int jns);
 int obs_distance_device(og_ctx* ctx, const float* d_tobbox, float* d_distance, int iew, int jns, float dx);
 
+// ---- post-analysis epilogue (og_final.cu) ------------------------------------------------
+int wind_increment_device(og_ctx* ctx, int dir, const float* w, const float* wA, const float* wC,
+                          float* out, int jns, int iew, int kbu);
+int pres_sfc_device(og_ctx* ctx, const float* pres, const float* slp_C, const float* slp_x,
+                    float* out, size_t n);
+int mixing_ratio_device(og_ctx* ctx, float* rh, const float* t, const float* h, const float* terrain,
+                        const float* slp_x, const float* d_pressure, const float* h_pressure, int iew,
+                        int jns, int kbu, float* qv, float* psfc);
+
 // ---- misc (og_misc.cu) ---------------------------------------------------------------
 const char* last_error();
 int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches);

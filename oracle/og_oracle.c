@@ -1021,3 +1021,139 @@ int ogo_qc_time_mt(const og_time_desc* d, const og_qc_params* p, int k_begin, in
     if (run_consistency) qc_consistency(d, k_begin, k_end);
     return OG_OK;
 }
+
+/* ======================================================================================
+ * Post-analysis epilogue: the per-grid-point maps between proc_oa and the
+ * netCDF writer.  3-D arrays are (jns,iew,kbu), j fastest, as first_guess.inc declares them.
+ * ====================================================================================== */
+#define IX3(j, i, k, jns, iew) (((size_t)(k) * (size_t)(iew) + (size_t)(i)) * (size_t)(jns) + (size_t)(j))
+
+/* final_analysis_module.F90:316-319 with crs2dot_pertU (first_guess_module.F90:59-74):
+ * pertubation = u - uA; averaged along dim2 (iew) onto the staggered points; u = uC + pert. */
+void ogo_wind_increment_u(float* u, const float* uA, const float* uC, int jns, int iew, int kbu)
+{
+    const size_t n = (size_t)jns * iew * kbu;
+    float* pert = (float*)malloc(sizeof(float) * n);
+    float* dummy = (float*)malloc(sizeof(float) * n);
+    for (size_t q = 0; q < n; ++q) pert[q] = u[q] - uA[q];
+    for (int k = 0; k < kbu; ++k)
+        for (int i = 0; i < iew; ++i)
+            for (int j = 0; j < jns; ++j) {
+                float v;
+                if (i == 0) v = pert[IX3(j, 0, k, jns, iew)];                       /* :70 */
+                else if (i == iew - 1) v = pert[IX3(j, iew - 2, k, jns, iew)];      /* :71 */
+                else v = (pert[IX3(j, i - 1, k, jns, iew)] + pert[IX3(j, i, k, jns, iew)]) * 0.5f; /* :68-69 */
+                dummy[IX3(j, i, k, jns, iew)] = v;
+            }
+    for (size_t q = 0; q < n; ++q) u[q] = uC[q] + dummy[q];
+    free(pert); free(dummy);
+}
+
+/* final_analysis_module.F90:336-339 with crs2dot_pertV (first_guess_module.F90:76-91): along dim1 (jns). */
+void ogo_wind_increment_v(float* v, const float* vA, const float* vC, int jns, int iew, int kbu)
+{
+    const size_t n = (size_t)jns * iew * kbu;
+    float* pert = (float*)malloc(sizeof(float) * n);
+    float* dummy = (float*)malloc(sizeof(float) * n);
+    for (size_t q = 0; q < n; ++q) pert[q] = v[q] - vA[q];
+    for (int k = 0; k < kbu; ++k)
+        for (int i = 0; i < iew; ++i)
+            for (int j = 0; j < jns; ++j) {
+                float w;
+                if (j == 0) w = pert[IX3(0, i, k, jns, iew)];                       /* :87 */
+                else if (j == jns - 1) w = pert[IX3(jns - 2, i, k, jns, iew)];      /* :88 */
+                else w = (pert[IX3(j - 1, i, k, jns, iew)] + pert[IX3(j, i, k, jns, iew)]) * 0.5f; /* :85-86 */
+                dummy[IX3(j, i, k, jns, iew)] = w;
+            }
+    for (size_t q = 0; q < n; ++q) v[q] = vC[q] + dummy[q];
+    free(pert); free(dummy);
+}
+
+/* final_analysis_module.F90:364-370: surface level of PRES follows the SLP increment. */
+void ogo_pres_sfc_from_slp(const float* pres_sfc, const float* slp_C, const float* slp_x,
+                           float* out, int jns, int iew)
+{
+    const size_t n = (size_t)jns * iew;
+    for (size_t q = 0; q < n; ++q)
+        out[q] = pres_sfc[q] + (pres_sfc[q] / slp_C[q]) * (slp_x[q] - slp_C[q]);
+}
+
+/* es of mixing_ratio (:1058): svp1*10. is a PARAMETER product, folded in FP32 */
+static float sat_vapor_pressure(float t)
+{
+    const float svp1x10 = 0.6112f * 10.f, svp2 = 17.67f, svp3 = 29.65f, svpt0 = 273.15f;
+    return svp1x10 * expf(svp2 * (t - svpt0) / (t - svp3));
+}
+
+/* sfcprs, final_analysis_module.F90:1087-1201.  Returns OG_ERR_INVALID when the 850/700/500 hPa
+ * levels are missing (the reference STOPs, :1122-1127). */
+static int sfcprs(const float* t, const float* q, const float* h, const float* slp_x,
+                  const float* terrain, const float* pressure, int iew, int jns, int kbu,
+                  float* psfc)
+{
+    const float R = 287.f, g = 9.806f, gamma = 6.5e-3f;
+    const float gammarg = gamma * R / g;
+    int k850 = -1, k700 = -1, k500 = -1;
+    for (int k = 1; k < kbu; ++k) {
+        const long p = lroundf(pressure[k]);
+        if (p == 850) k850 = k; else if (p == 700) k700 = k; else if (p == 500) k500 = k;
+    }
+    if (k850 < 0 || k700 < 0 || k500 < 0) return OG_ERR_INVALID;
+    const float p78 = 1.f / logf(850.f / 700.f), p57 = 1.f / logf(700.f / 500.f);
+    for (int i = 0; i < iew - 1; ++i)
+        for (int j = 0; j < jns - 1; ++j) {
+            const size_t o = (size_t)i * jns + j;
+            const float ht = -terrain[o] / h[IX3(j, i, k850, jns, iew)];            /* :1133 */
+            const float ps0 = slp_x[o] * powf(slp_x[o] / 85000.f, ht);              /* :1134 */
+            float p1;                                                               /* :1142-1148 */
+            if (ps0 > 95000.f) p1 = 85000.f;
+            else if (ps0 > 70000.f) p1 = ps0 - 10000.f;
+            else p1 = 50000.f;
+            const float t850 = t[IX3(j, i, k850, jns, iew)] * (1.f + 0.608f * q[IX3(j, i, k850, jns, iew)]);
+            const float t700 = t[IX3(j, i, k700, jns, iew)] * (1.f + 0.608f * q[IX3(j, i, k700, jns, iew)]);
+            const float t500 = t[IX3(j, i, k500, jns, iew)] * (1.f + 0.608f * q[IX3(j, i, k500, jns, iew)]);
+            const float gamma78 = logf(t850 / t700) * p78, gamma57 = logf(t700 / t500) * p57;
+            float t1;                                                               /* :1173-1181 */
+            if (ps0 > 95000.f) t1 = t850;
+            else if (ps0 > 85000.f) t1 = t700 * powf(p1 / 70000.f, gamma78);
+            else if (ps0 > 70000.f) t1 = t500 * powf(p1 / 50000.f, gamma57);
+            else t1 = t500;
+            const float tslv = t1 * powf(slp_x[o] / p1, gammarg);                    /* :1185 */
+            const float tsfc = tslv - gamma * terrain[o];                           /* :1189 */
+            psfc[o] = slp_x[o] * expf((-terrain[o] * g) / (R / 2.f * (tsfc + tslv))); /* :1197 */
+        }
+    return OG_OK;
+}
+
+/* mixing_ratio, final_analysis_module.F90:1026-1083: clamps rh in place (:1055), fills qv on the
+ * cross points (1:jns-1, 1:iew-1) of every level and psfc (Pa) on the same points. */
+int ogo_mixing_ratio(float* rh, const float* t, const float* h, const float* terrain,
+                     const float* slp_x, const float* pressure, int iew, int jns, int kbu,
+                     float* qv, float* psfc)
+{
+    const float eps = 0.622f;
+    for (int k = 0; k < kbu; ++k)
+        for (int i = 0; i < iew - 1; ++i)
+            for (int j = 0; j < jns - 1; ++j) {
+                float* r = &rh[IX3(j, i, k, jns, iew)];
+                *r = fminf(fmaxf(*r, 1.f), 100.f);
+            }
+    for (int k = 1; k < kbu; ++k)
+        for (int i = 0; i < iew - 1; ++i)
+            for (int j = 0; j < jns - 1; ++j) {
+                const size_t o = IX3(j, i, k, jns, iew);
+                const float es = sat_vapor_pressure(t[o]);
+                const float qs = eps * es / (pressure[k] - es);
+                qv[o] = fmaxf(0.01f * rh[o] * qs, 0.0f);
+            }
+    int rc = sfcprs(t, qv, h, slp_x, terrain, pressure, iew, jns, kbu, psfc);
+    if (rc != OG_OK) return rc;
+    for (int i = 0; i < iew - 1; ++i)
+        for (int j = 0; j < jns - 1; ++j) {
+            const size_t o = IX3(j, i, 0, jns, iew);
+            const float es = sat_vapor_pressure(t[o]);
+            const float qs = eps * es / (psfc[o] / 100.f - es);
+            qv[o] = fmaxf(0.01f * rh[o] * qs, 0.0f);
+        }
+    return OG_OK;
+}

@@ -99,6 +99,18 @@ int ogo_qc_time_mt(const og_time_desc* d, const og_qc_params* p, int k_begin, in
 float ogo_fg_t_at_point(const float* t3d, const float* h3d, int jns, int iew, int kbu,
                         float x_location, float y_location, float height_msl);
 
+/* Post-analysis epilogue.  3-D arrays are (jns,iew,kbu), j fastest.
+ * final_analysis_module.F90:316-350 + first_guess_module.F90:59-91 (A-grid increments onto the
+ * C-grid winds), :364-370 (surface PRES from the SLP increment), :1026-1201 (mixing_ratio +
+ * sfcprs; expf/logf/powf are glibc's, as in the gfortran build). */
+void ogo_wind_increment_u(float* u, const float* uA, const float* uC, int jns, int iew, int kbu);
+void ogo_wind_increment_v(float* v, const float* vA, const float* vC, int jns, int iew, int kbu);
+void ogo_pres_sfc_from_slp(const float* pres_sfc, const float* slp_C, const float* slp_x,
+                           float* out, int jns, int iew);
+int ogo_mixing_ratio(float* rh, const float* t, const float* h, const float* terrain,
+                     const float* slp_x, const float* pressure, int iew, int jns, int kbu,
+                     float* qv, float* psfc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -204,6 +204,42 @@ def obs_distance(tobbox, dx):
     return out
 
 
+def wind_increment_to_c_grid(u, uA, uC, v, vA, vC):
+    """3-D arrays (kbu, iew, jns) C order == Fortran (jns,iew,kbu)."""
+    u, v = f32(u).copy(), f32(v).copy()
+    uA, uC, vA, vC = f32(uA), f32(uC), f32(vA), f32(vC)
+    kbu, iew, jns = u.shape
+    l = lib()
+    l.ogo_wind_increment_u.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int]
+    l.ogo_wind_increment_v.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int]
+    l.ogo_wind_increment_u(ptr(u), ptr(uA), ptr(uC), jns, iew, kbu)
+    l.ogo_wind_increment_v(ptr(v), ptr(vA), ptr(vC), jns, iew, kbu)
+    return u, v
+
+
+def pres_sfc_from_slp(pres_sfc, slp_C, slp_x):
+    p, c, x = f32(pres_sfc), f32(slp_C), f32(slp_x)
+    iew, jns = p.shape
+    out = np.zeros_like(p)
+    l = lib()
+    l.ogo_pres_sfc_from_slp.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_int]
+    l.ogo_pres_sfc_from_slp(ptr(p), ptr(c), ptr(x), ptr(out), jns, iew)
+    return out
+
+
+def mixing_ratio(rh, t, h, terrain, slp_x_pa, pressure):
+    rh = f32(rh).copy(); t, h = f32(t), f32(h)
+    terrain, slp, pressure = f32(terrain), f32(slp_x_pa), f32(pressure)
+    kbu, iew, jns = rh.shape
+    qv = np.zeros_like(rh); psfc = np.zeros((iew, jns), np.float32)
+    l = lib()
+    l.ogo_mixing_ratio.restype = C.c_int
+    l.ogo_mixing_ratio.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]
+    rc = l.ogo_mixing_ratio(ptr(rh), ptr(t), ptr(h), ptr(terrain), ptr(slp), ptr(pressure), iew, jns,
+                            kbu, ptr(qv), ptr(psfc))
+    return rc, rh, qv, psfc
+
+
 def dewpoint(t, rh):
     return lib().ogo_dewpoint(float(t), float(rh))
 

@@ -473,3 +473,63 @@ def test_bad_arguments_are_reported(ctx):
         ctx.cressman([1.0], [5.0], [5.0], g, 1, 5, 12.0)       # UU without banana winds
     with pytest.raises(OgError):
         ctx.cressman([1.0], [5.0], [5.0], g, 9, 5, 12.0)       # unknown variable
+
+
+# ---- post-analysis epilogue -------------------------------------------------
+@pytest.mark.parametrize("kbu,iew,jns", [(3, 7, 5), (27, 100, 100), (1, 2, 2), (5, 333, 257)])
+def test_wind_increment_to_c_grid_bit_exact(ctx, oracle, kbu, iew, jns):
+    """final_analysis_module.F90:316-339 + first_guess_module.F90:59-91."""
+    rng = np.random.default_rng(kbu * 1000 + iew)
+    mk = lambda: rng.uniform(-40, 40, (kbu, iew, jns)).astype(np.float32)
+    u, uA, uC, v, vA, vC = (mk() for _ in range(6))
+    a = oracle.wind_increment_to_c_grid(u, uA, uC, v, vA, vC)
+    b = ctx.wind_increment_to_c_grid(u, uA, uC, v, vA, vC)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_pres_sfc_from_slp_bit_exact(ctx, oracle):
+    """final_analysis_module.F90:364-370."""
+    rng = np.random.default_rng(5)
+    iew, jns = 211, 173
+    pres = rng.uniform(55000, 103000, (iew, jns)).astype(np.float32)
+    slpc = rng.uniform(98000, 104000, (iew, jns)).astype(np.float32)
+    slpx = (slpc + rng.normal(0, 300, (iew, jns))).astype(np.float32)
+    np.testing.assert_array_equal(oracle.pres_sfc_from_slp(pres, slpc, slpx), ctx.pres_sfc_from_slp(pres, slpc, slpx))
+
+
+def _epilogue_case(kbu_levels, iew, jns, seed):
+    rng = np.random.default_rng(seed)
+    press = np.array(kbu_levels, np.float32)
+    kbu = len(press)
+    t = np.empty((kbu, iew, jns), np.float32); h = np.empty_like(t)
+    for k, p in enumerate(press):
+        t[k] = 288.0 * (min(p, 1000.0) / 1000.0) ** 0.19 + rng.normal(0, 1.5, (iew, jns))
+        h[k] = 44330.0 * (1 - (min(p, 1000.0) / 1013.25) ** 0.1903) + rng.normal(0, 10, (iew, jns))
+    rh = rng.uniform(-5, 110, (kbu, iew, jns)).astype(np.float32)
+    terrain = rng.uniform(0, 5200, (iew, jns)).astype(np.float32)
+    slp = rng.uniform(99000, 103000, (iew, jns)).astype(np.float32)
+    return press, rh, t, h, terrain, slp
+
+
+@pytest.mark.parametrize("iew,jns", [(9, 8), (150, 131)])
+def test_mixing_ratio_and_sfcprs(ctx, oracle, iew, jns):
+    """final_analysis_module.F90:1026-1201.  EXP / LOG / ** are glibc's expf / logf / powf in the
+    reference build and FP64-then-round on the device: tolerance 1e-6 relative (a few FP32 ulp
+    through the chain of powers), and the clamped rh is bit-identical."""
+    press, rh, t, h, terrain, slp = _epilogue_case([1001, 1000, 925, 850, 700, 500, 400, 300], iew, jns, iew)
+    rc, rh0, qv0, ps0 = oracle.mixing_ratio(rh, t, h, terrain, slp, press)
+    assert rc == 0
+    rh1, qv1, ps1 = ctx.mixing_ratio(rh, t, h, terrain, slp, press)
+    np.testing.assert_array_equal(rh0, rh1)
+    np.testing.assert_allclose(ps1, ps0, rtol=1e-6, atol=0)
+    np.testing.assert_allclose(qv1, qv0, rtol=1e-6, atol=1e-12)
+    # almost every value is in fact identical: the differences are isolated last-bit cases
+    assert np.mean(ps1 != ps0) < 0.02 and np.mean(qv1 != qv0) < 0.02
+
+
+def test_mixing_ratio_needs_the_mandatory_levels(ctx):
+    from obsgrid_b200._capi import OgError
+    press, rh, t, h, terrain, slp = _epilogue_case([1001, 1000, 925, 850], 6, 6, 1)
+    with pytest.raises(OgError):
+        ctx.mixing_ratio(rh, t, h, terrain, slp, press)

@@ -408,3 +408,93 @@ def test_ob_density_and_obs_distance_by_hand(oracle):
     d0 = oracle.obs_distance(np.zeros((iew, jns), np.float32), 3.0)
     diag = np.sqrt(np.float32(np.float32(11 * 3.0) * 11 * 3.0 + np.float32(8 * 3.0) * 8 * 3.0)) / np.float32(3.0)
     assert np.all(d0 == np.float32(diag) * np.float32(3.0))
+
+
+# ---- post-analysis epilogue -------------------------------------------------
+def _epilogue_fields(kbu, iew, jns, seed=0):
+    rng = np.random.default_rng(seed)
+    mk = lambda lo, hi: rng.uniform(lo, hi, (kbu, iew, jns)).astype(np.float32)
+    return rng, mk
+
+
+def test_wind_increment_to_c_grid_by_hand(oracle):
+    """final_analysis_module.F90:316-339 with first_guess_module.F90:59-91, restated with numpy
+    slices exactly as the Fortran array expressions are written (arrays (kbu,iew,jns) here)."""
+    kbu, iew, jns = 3, 7, 5
+    rng, mk = _epilogue_fields(kbu, iew, jns, 3)
+    u, uA, uC, v, vA, vC = (mk(-30, 30) for _ in range(6))
+    gu, gv = oracle.wind_increment_to_c_grid(u, uA, uC, v, vA, vC)
+    half = np.float32(0.5)
+    pu = u - uA                                   # pertubation(dim1=jns, dim2=iew, dim3)
+    du = np.zeros_like(pu)
+    du[:, 1:iew - 1, :] = (pu[:, 0:iew - 2, :] + pu[:, 1:iew - 1, :]) * half     # dummy(:,2:dim2-1,:)
+    du[:, 0, :] = pu[:, 0, :]; du[:, iew - 1, :] = pu[:, iew - 2, :]
+    np.testing.assert_array_equal(gu, uC + du)
+    pv = v - vA
+    dv = np.zeros_like(pv)
+    dv[:, :, 1:jns - 1] = (pv[:, :, 0:jns - 2] + pv[:, :, 1:jns - 1]) * half     # dummy(2:dim1-1,:,:)
+    dv[:, :, 0] = pv[:, :, 0]; dv[:, :, jns - 1] = pv[:, :, jns - 2]
+    np.testing.assert_array_equal(gv, vC + dv)
+    # a single-point increment of 2 at A-grid (j,i) spreads as 1 + 1 onto the two staggered neighbours
+    u0 = np.zeros((1, 6, 4), np.float32); uA0 = u0.copy(); u0[0, 2, 1] = 2.0
+    gu, _ = oracle.wind_increment_to_c_grid(u0, uA0, np.zeros_like(u0), u0, uA0, np.zeros_like(u0))
+    assert gu[0, 2, 1] == 1.0 and gu[0, 3, 1] == 1.0 and gu.sum() == 2.0
+
+
+def test_pres_sfc_from_slp_by_hand(oracle):
+    """final_analysis_module.F90:364-370."""
+    f = np.float32
+    pres = np.array([[95000.0, 88000.5], [101300.0, 70000.0]], np.float32)
+    slpc = np.array([[101000.0, 100500.0], [101300.0, 99000.0]], np.float32)
+    slpx = np.array([[101250.0, 100100.0], [101300.0, 99900.0]], np.float32)
+    out = oracle.pres_sfc_from_slp(pres, slpc, slpx)
+    want = pres + (pres / slpc) * (slpx - slpc)          # float32 ops in source order
+    np.testing.assert_array_equal(out, want)
+    assert out[1, 0] == f(101300.0)                      # no SLP increment, no change
+
+
+def test_mixing_ratio_and_sfcprs_against_float64(oracle):
+    """final_analysis_module.F90:1026-1201: the FP32 restatement against the same formulas in
+    float64 (tolerance: FP32 rounding of a dozen operations), plus structural facts."""
+    press = np.array([1001, 1000, 925, 850, 700, 500, 300], np.float32)
+    kbu, iew, jns = len(press), 9, 8
+    rng = np.random.default_rng(11)
+    t = np.empty((kbu, iew, jns), np.float32); h = np.empty_like(t)
+    for k, p in enumerate(press):
+        t[k] = 288.0 * (min(p, 1000.0) / 1000.0) ** 0.19 + rng.normal(0, 1.5, (iew, jns))
+        h[k] = 44330.0 * (1 - (min(p, 1000.0) / 1013.25) ** 0.1903) + rng.normal(0, 10, (iew, jns))
+    rh = rng.uniform(-5, 110, (kbu, iew, jns)).astype(np.float32)
+    terrain = rng.uniform(0, 3200, (iew, jns)).astype(np.float32)   # all four branches of :1142 / :1173
+    terrain[0, 0] = 0.0; terrain[1, 1] = 5200.0
+    slp = rng.uniform(99000, 103000, (iew, jns)).astype(np.float32)
+    rc, rh1, qv, psfc = oracle.mixing_ratio(rh, t, h, terrain, slp, press)
+    assert rc == 0
+    # clamp on the cross points only; last row / column untouched
+    np.testing.assert_array_equal(rh1[:, :-1, :-1], np.clip(rh[:, :-1, :-1], 1.0, 100.0))
+    np.testing.assert_array_equal(rh1[:, -1, :], rh[:, -1, :]); np.testing.assert_array_equal(rh1[:, :, -1], rh[:, :, -1])
+    assert np.all(qv[:, -1, :] == 0) and np.all(qv[:, :, -1] == 0) and np.all(psfc[-1, :] == 0) and np.all(psfc[:, -1] == 0)
+    T, H, RH = t.astype(np.float64), h.astype(np.float64), rh1.astype(np.float64)
+    TER, SLP, P = terrain.astype(np.float64), slp.astype(np.float64), press.astype(np.float64)
+    es = 6.112 * np.exp(17.67 * (T - 273.15) / (T - 29.65))
+    qs = 0.622 * es / (P[:, None, None] - es)
+    q64 = np.maximum(0.01 * RH * qs, 0.0)
+    k850, k700, k500 = 3, 4, 5
+    R, g, gamma = 287.0, 9.806, 6.5e-3
+    ps0 = SLP * (SLP / 85000.0) ** (-TER / H[k850])
+    p1 = np.where(ps0 > 95000, 85000.0, np.where(ps0 > 70000, ps0 - 10000.0, 50000.0))
+    tv = lambda k: T[k] * (1 + 0.608 * q64[k])
+    g78 = np.log(tv(k850) / tv(k700)) / np.log(850.0 / 700.0)
+    g57 = np.log(tv(k700) / tv(k500)) / np.log(700.0 / 500.0)
+    t1 = np.where(ps0 > 95000, tv(k850), np.where(ps0 > 85000, tv(k700) * (p1 / 70000.0) ** g78,
+                  np.where(ps0 > 70000, tv(k500) * (p1 / 50000.0) ** g57, tv(k500))))
+    tslv = t1 * (SLP / p1) ** (gamma * R / g)
+    tsfc = tslv - gamma * TER
+    ps64 = SLP * np.exp(-TER * g / (R / 2.0 * (tsfc + tslv)))
+    assert {int(x) for x in np.unique(np.digitize(ps0[:-1, :-1], [70000, 85000, 95000]))} == {0, 1, 2, 3}
+    np.testing.assert_allclose(psfc[:-1, :-1], ps64[:-1, :-1], rtol=3e-6)
+    np.testing.assert_allclose(qv[1:, :-1, :-1], q64[1:, :-1, :-1], rtol=2e-5, atol=1e-9)
+    qs0 = 0.622 * es[0] / (ps64 / 100.0 - es[0])
+    np.testing.assert_allclose(qv[0, :-1, :-1], np.maximum(0.01 * RH[0] * qs0, 0)[:-1, :-1], rtol=2e-5, atol=1e-9)
+    # no 850/700/500 hPa level: the reference STOPs, the restatement reports it
+    rc, *_ = oracle.mixing_ratio(rh[:4], t[:4], h[:4], terrain, slp, np.array([1001, 1000, 925, 850], np.float32))
+    assert rc != 0
