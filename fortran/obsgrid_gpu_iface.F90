@@ -135,6 +135,15 @@ MODULE obsgrid_gpu
          INTEGER ( C_INT ) , VALUE :: jns , iew
       END FUNCTION og_pres_sfc_from_slp
 
+      INTEGER ( C_INT ) FUNCTION og_temporal_interp ( ctx , first , second , out , jns , iew , nlev , &
+      icount_fdda , icount_1 , icount_2 , cross ) BIND ( C , NAME = 'og_temporal_interp' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         REAL ( C_FLOAT ) , INTENT ( IN ) :: first ( * ) , second ( * )
+         REAL ( C_FLOAT ) , INTENT ( OUT ) :: out ( * )
+         INTEGER ( C_INT ) , VALUE :: jns , iew , nlev , icount_fdda , icount_1 , icount_2 , cross
+      END FUNCTION og_temporal_interp
+
       INTEGER ( C_INT ) FUNCTION og_mixing_ratio ( ctx , rh , t , h , terrain , slp_x , pressure , &
       iew , jns , kbu , qv , psfc ) BIND ( C , NAME = 'og_mixing_ratio' )
          IMPORT :: C_PTR , C_INT , C_FLOAT
@@ -147,7 +156,7 @@ MODULE obsgrid_gpu
    END INTERFACE
 
    PUBLIC :: og_cressman , og_error_max , og_buddy_check , og_ob_density , og_obs_distance , og_fail
-   PUBLIC :: og_wind_increment_to_c_grid , og_pres_sfc_from_slp , og_mixing_ratio
+   PUBLIC :: og_wind_increment_to_c_grid , og_pres_sfc_from_slp , og_mixing_ratio , og_temporal_interp
 
 CONTAINS
 
@@ -447,3 +456,26 @@ SUBROUTINE pres_sfc_from_slp ( pres_sfc , slp_C , slp_x , out , jns_alloc , iew_
                                INT ( iew_alloc , C_INT ) ) .NE. 0 ) CALL og_fail ( 'pres_sfc_from_slp' )
 
 END SUBROUTINE pres_sfc_from_slp
+
+!  temporal_interp, src/tinterp_module.F90:126-213: each branch of the_3d_search / the_2d_search
+!  becomes one call, e.g. for 'TT      ' (cross = 1; UU, VV, UA, VA, UC, VC pass cross = 0):
+!     CALL temporal_interp_field ( all_3d(loop_count,first_time)%array , &
+!                                  all_3d(loop_count,second_time)%array , t , jns_alloc , iew_alloc , &
+!                                  kbu_alloc , icount_fdda , icount_1 , icount_2 , 1 )
+SUBROUTINE temporal_interp_field ( first , second , out , jns_alloc , iew_alloc , nlev , &
+                                   icount_fdda , icount_1 , icount_2 , cross )
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE obsgrid_gpu
+   IMPLICIT NONE
+
+   INTEGER , INTENT ( IN ) :: jns_alloc , iew_alloc , nlev , icount_fdda , icount_1 , icount_2 , cross
+   REAL , INTENT ( IN ) , DIMENSION ( jns_alloc , iew_alloc , nlev ) :: first , second
+   REAL , INTENT ( OUT ) , DIMENSION ( jns_alloc , iew_alloc , nlev ) :: out
+
+   IF ( og_temporal_interp ( og_handle , first , second , out , INT ( jns_alloc , C_INT ) , &
+                             INT ( iew_alloc , C_INT ) , INT ( nlev , C_INT ) , INT ( icount_fdda , C_INT ) , &
+                             INT ( icount_1 , C_INT ) , INT ( icount_2 , C_INT ) , INT ( cross , C_INT ) ) .NE. 0 ) &
+      CALL og_fail ( 'temporal_interp' )
+
+END SUBROUTINE temporal_interp_field

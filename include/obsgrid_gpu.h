@@ -199,6 +199,15 @@ int og_obs_distance(og_ctx* ctx, const float* tobbox, float* distance, int iew, 
 int og_wind_increment_to_c_grid(og_ctx* ctx, float* u, const float* uA, const float* uC,
                                 float* v, const float* vA, const float* vC,
                                 int jns, int iew, int kbu);
+/* temporal_interp, tinterp_module.F90:53-215 (surface FDDA first guess between two analysed
+ * times): out = (w1*first + w2*second)/(w1+w2) with the integer weights w1 = icount_2 -
+ * icount_fdda, w2 = icount_fdda - icount_1 (both zero: w1 = 1, :106-109; sum zero:
+ * OG_ERR_INVALID, the reference STOPs :112-115).  cross != 0 (TT, GHT, RH, PRES, PMSL, PMSL_C,
+ * SNOW): computed on (1:jns-1,1:iew-1), last row and column replicated (:131-132); cross == 0
+ * (UU, VV, UA, VA, UC, VC): the whole array.  nlev = 1 for the 2-D fields.  Bit-identical FP32. */
+int og_temporal_interp(og_ctx* ctx, const float* first, const float* second, float* out,
+                       int jns, int iew, int nlev, int icount_fdda, int icount_1, int icount_2,
+                       int cross);
 /* final_analysis_module.F90:364-370: out = pres + (pres/slp_C)*(slp_x - slp_C) for the surface
  * level of PRES (skipped by the caller when oa_psfc).  (jns,iew) arrays.  Bit-identical FP32. */
 int og_pres_sfc_from_slp(og_ctx* ctx, const float* pres_sfc, const float* slp_C,
@@ -207,7 +216,7 @@ int og_pres_sfc_from_slp(og_ctx* ctx, const float* pres_sfc, const float* slp_C,
  * clamps rh to [1,100] in place on (1:jns-1,1:iew-1,:), fills qv on those points of every
  * level and psfc (Pa; slp_x in Pa) on the same points of the surface; other entries of qv /
  * psfc keep the caller's values.  OG_ERR_INVALID when `pressure` lacks the 850, 700 or 500 hPa
- * level (the reference STOPs, :1122-1127).  EXP/LOG/** are evaluated in FP64 and rounded once:
+ * level (the reference STOPs, :1122-1127).  EXP, LOG and the power operator are evaluated in FP64 and rounded once:
  * results agree with the glibc-based reference to ~1 ulp, not bit for bit. */
 int og_mixing_ratio(og_ctx* ctx, float* rh, const float* t, const float* h, const float* terrain,
                     const float* slp_x, const float* pressure, int iew, int jns, int kbu,
@@ -269,6 +278,12 @@ typedef struct og_time_desc {
 
 /* proc_qc level x variable loop + qc_consistency.  Flags are updated in place. */
 int og_qc_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p);
+/* proc_qc of a surface-FDDA time (proc_qc.F90:243-420): og_qc_time plus the observation
+ * density.  tobbox (jns,iew; in/out) receives +1 per surface ob of every checked variable within
+ * 250 km (ob_density at kp = 1, :349-351), is divided by 5 and zeroed below 1 (:416-417); odis
+ * (jns,iew; out) is obs_distance of the result (:420), in the unit of d->dx_km. */
+int og_qc_time_fdda(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p, float* tobbox,
+                    float* odis);
 /* proc_oa level x variable loop.  Fields are updated in place.  Observations whose flag is
  * >= min(fails_error_max, fails_buddy_check) are not used (proc_oa.F90:462).
  * k_begin/k_end select a half-open level range [k_begin,k_end) -- the unit by which the

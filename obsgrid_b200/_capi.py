@@ -110,8 +110,10 @@ SIGNATURES = {
     "og_obs_distance": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_float]),
     "og_wind_increment_to_c_grid": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int]),
     "og_pres_sfc_from_slp": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int]),
+    "og_temporal_interp": (C.c_int, [_vp, _vp, _vp, _vp] + [C.c_int] * 7),
     "og_mixing_ratio": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "og_qc_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams)]),
+    "og_qc_time_fdda": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), _vp, _vp]),
     "og_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgOaParams), C.c_int, C.c_int]),
     "og_qc_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.POINTER(OgOaParams),
                                 C.c_int, C.c_int, C.c_int]),

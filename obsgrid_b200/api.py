@@ -156,6 +156,17 @@ class Context:
                                                     ptr(vC), jns, iew, kbu), "og_wind_increment_to_c_grid")
         return u, v
 
+    def temporal_interp(self, first, second, icount_fdda, icount_1, icount_2, cross):
+        """tinterp_module.F90:53-215 for one field; arrays (nlev, iew, jns) or (iew, jns)."""
+        a, b = f32(first), f32(second)
+        shp = a.shape
+        nlev = shp[0] if a.ndim == 3 else 1
+        iew, jns = shp[-2], shp[-1]
+        out = np.zeros_like(a)
+        check(self._lib.og_temporal_interp(self._h, ptr(a), ptr(b), ptr(out), jns, iew, nlev,
+                                           icount_fdda, icount_1, icount_2, int(cross)), "og_temporal_interp")
+        return out
+
     def pres_sfc_from_slp(self, pres_sfc, slp_C, slp_x):
         p, c, x = f32(pres_sfc), f32(slp_C), f32(slp_x)
         iew, jns = p.shape
@@ -215,6 +226,14 @@ class Context:
         k_end = case.kbu if k_end is None else k_end
         check(self._lib.og_qc_time_levels(self._h, C.byref(d), C.byref(case.qc_params), k_begin,
                                           k_end, int(run_consistency)), "og_qc_time_levels")
+
+    def proc_qc_fdda(self, case, tobbox):
+        """proc_qc of a surface-FDDA time: flags in place; returns (tobbox, odis), (iew, jns) C order."""
+        d = case.desc()
+        tb = f32(tobbox).copy(); od = np.zeros_like(tb)
+        check(self._lib.og_qc_time_fdda(self._h, C.byref(d), C.byref(case.qc_params), ptr(tb), ptr(od)),
+              "og_qc_time_fdda")
+        return tb, od
 
     def proc_oa(self, case, k_begin=0, k_end=None):
         d = case.desc()

@@ -389,6 +389,27 @@ extern "C" int og_wind_increment_to_c_grid(og_ctx* c, float* u, const float* uA,
     return OG_OK;
 }
 
+extern "C" int og_temporal_interp(og_ctx* c, const float* first, const float* second, float* out,
+                                  int jns, int iew, int nlev, int icount_fdda, int icount_1,
+                                  int icount_2, int cross)
+{
+    REQUIRE(c && first && second && out && jns >= 2 && iew >= 2 && nlev >= 1, "bad argument");
+    REQUIRE(iew <= 65535 && nlev <= 65535, "too many columns or levels");
+    // tinterp_module.F90:98-121: integer weights, the both-zero special case, the divide check
+    int w1 = icount_2 - icount_fdda, w2 = icount_fdda - icount_1;
+    if (w1 == 0 && w2 == 0) w1 = 1;
+    if (w1 + w2 == 0) { set_error("temporal_interp: weights sum to zero (tinterp_module.F90:112)"); return OG_ERR_INVALID; }
+    const size_t n = (size_t)jns * iew * nlev;
+    float *d_a, *d_b, *d_o;
+    OG_TRY(upload(c, "fin.w", first, n, &d_a));
+    OG_TRY(upload(c, "fin.wA", second, n, &d_b));
+    OG_TRY(c->reserve_t("fin.out", n, &d_o));
+    OG_TRY(temporal_interp_device(c, d_a, d_b, d_o, jns, iew, nlev, (float)w1, (float)w2, (float)(w1 + w2), cross));
+    OG_TRY(download(c, out, d_o, n));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
 extern "C" int og_pres_sfc_from_slp(og_ctx* c, const float* pres_sfc, const float* slp_C,
                                     const float* slp_x, float* out, int jns, int iew)
 {
@@ -681,7 +702,18 @@ struct TimeDev {
     const float *xob, *yob, *lon, *elev;
     const float *ob_u, *ob_v, *ob_t, *ob_rh, *ob_slp;
     int *qc_u, *qc_v, *qc_t, *qc_rh, *qc_slp;
+    float* tobbox = nullptr;   // optional (surface FDDA): (jns,iew) observation density, in/out
+    float* odis = nullptr;     //                          (jns,iew) distance to the nearest observed box
 };
+
+// proc_qc.F90:416-417: tobbox = tobbox / 5. ; WHERE ( tobbox .LT. 1 ) tobbox = 0
+__global__ void tobbox_average_kernel(float* __restrict__ tb, size_t n)
+{
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const float v = fdiv(tb[q], 5.f);
+    tb[q] = (v < 1.f) ? 0.f : v;
+}
 
 // Run the three selection kernels for `sel` and return per-slab counts / offsets on the host.
 int run_selection(og_ctx* c, const TimeDev& T, std::vector<SelSlab>& sel, bool qc_outputs,
@@ -847,6 +879,7 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
         b.iew = iew; b.jns = jns; b.dx_km = T.dx_km; b.buddy_weight = p->buddy_weight;
         b.do_error_max = p->qc_test_error_max; b.do_buddy = p->qc_test_buddy;
         std::vector<PutSlab> puts;
+        std::vector<int> slab_level;
         for (int k = k0; k < k1; ++k) {
             const size_t row = (size_t)k * T.nrep, lev = per * (size_t)(k - k0);
             const float pk = T.pressure[k];
@@ -876,7 +909,7 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
                         q.ob_t = T.ob_t + row; q.qc_t = T.qc_t + row; pt.qc = T.qc_rh + row;
                         s.max_error = p->max_error_dewpoint; s.max_buddy = p->max_buddy_dewpoint; break;
                 }
-                b.slabs.push_back(s); sel.push_back(q); puts.push_back(pt);
+                b.slabs.push_back(s); sel.push_back(q); puts.push_back(pt); slab_level.push_back(k);
             }
         }
         if (b.slabs.empty()) continue;
@@ -891,6 +924,11 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
         }
         b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval; b.elev = SA.oelev;
         b.local_time = SA.olt; b.qc = SA.oqc;
+        if (T.tobbox)   // proc_qc.F90:349-351: every surface variable's obs add to the density
+            for (size_t s = 0; s < b.slabs.size(); ++s)
+                if (slab_level[s] == 0)
+                    OG_TRY(ob_density_device(c, SA.ox + sel[s].ob_off, SA.oy + sel[s].ob_off, T.dx_km,
+                                             ncount[s], T.tobbox, iew, jns));
         OG_TRY(qc_run_batch(c, b));
         if (max_n > 0) {
             PutSlab* d_put;
@@ -900,6 +938,11 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
             put_kernel<<<g, 256, 0, c->stream>>>(d_put, SA.oqc, SA.oidx);
             c->count_launch();
         }
+    }
+    if (T.tobbox && T.odis && has_sfc) {   // proc_qc.F90:412-420
+        tobbox_average_kernel<<<nblk(per), 256, 0, c->stream>>>(T.tobbox, per);
+        c->count_launch();
+        OG_TRY(obs_distance_device(c, T.tobbox, T.odis, iew, jns, T.dx_km));
     }
     if (run_consistency && T.nrep > 0) {
         const size_t n = (size_t)nlev * T.nrep, off = (size_t)k0 * T.nrep;
@@ -1268,6 +1311,30 @@ extern "C" int og_time_wait(og_ctx* c, int slot)
     REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
     og_ctx::Slot& s = c->slots[slot];
     if (s.down_pending) { OG_CUDA(cudaEventSynchronize(s.down)); s.down_pending = false; }
+    return OG_OK;
+}
+
+extern "C" int og_qc_time_fdda(og_ctx* c, const og_time_desc* d, const og_qc_params* p, float* tobbox,
+                               float* odis)
+{
+    REQUIRE(c && p && tobbox && odis, "null argument");
+    OG_TRY(check_desc(d, 0, d ? d->kbu : 0, true));
+    REQUIRE(d->iew <= 32000 && d->jns <= 32000, "grid larger than 32000 points per edge");
+    TimeDev T;
+    OG_TRY(mirror_in(c, d, 0, d->kbu, true, T));
+    const size_t per = (size_t)d->iew * d->jns;
+    OG_TRY(upload(c, "m.tobbox", tobbox, per, &T.tobbox));
+    OG_TRY(c->reserve_t("m.odis", per, &T.odis));
+    OG_TRY(qc_time_core(c, T, p, 0, d->kbu, 1));
+    const size_t n = (size_t)d->nrep * d->kbu;
+    OG_TRY(download(c, d->qc_u, T.qc_u, n));
+    OG_TRY(download(c, d->qc_v, T.qc_v, n));
+    OG_TRY(download(c, d->qc_t, T.qc_t, n));
+    OG_TRY(download(c, d->qc_rh, T.qc_rh, n));
+    OG_TRY(download(c, d->qc_slp, T.qc_slp, (size_t)d->nrep));
+    OG_TRY(download(c, tobbox, T.tobbox, per));
+    OG_TRY(download(c, odis, T.odis, per));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
     return OG_OK;
 }
 

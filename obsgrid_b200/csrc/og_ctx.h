@@ -187,6 +187,8 @@ int obs_distance_device(og_ctx* ctx, const float* d_tobbox, float* d_distance, i
 // ---- post-analysis epilogue (og_final.cu) ------------------------------------------------
 int wind_increment_device(og_ctx* ctx, int dir, const float* w, const float* wA, const float* wC,
                           float* out, int jns, int iew, int kbu);
+int temporal_interp_device(og_ctx* ctx, const float* a, const float* b, float* out, int jns, int iew,
+                           int nlev, float w1, float w2, float wd, int cross);
 int pres_sfc_device(og_ctx* ctx, const float* pres, const float* slp_C, const float* slp_x,
                     float* out, size_t n);
 int mixing_ratio_device(og_ctx* ctx, float* rh, const float* t, const float* h, const float* terrain,

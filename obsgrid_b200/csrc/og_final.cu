@@ -51,6 +51,21 @@ __global__ void pres_sfc_kernel(const float* __restrict__ pres, const float* __r
     out[q] = fadd(pres[q], fmul(fdiv(pres[q], slp_C[q]), fsub(slp_x[q], slp_C[q])));
 }
 
+// temporal_interp (tinterp_module.F90:126-213): (w1*a + w2*b)/wd; cross-point fields are computed on
+// (1:jns-1, 1:iew-1) and their last row / column replicated (:131-132), i.e. read from the
+// clamped source point.
+__global__ void __launch_bounds__(256) temporal_interp_kernel(const float* __restrict__ a,
+                                                              const float* __restrict__ b,
+                                                              float* __restrict__ out, int jns, int iew,
+                                                              float w1, float w2, float wd, int cross)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y, k = blockIdx.z;
+    if (j >= jns) return;
+    const int js = cross ? min(j, jns - 2) : j, is = cross ? min(i, iew - 2) : i;
+    const size_t o = ix3(js, is, k, jns, iew);
+    out[ix3(j, i, k, jns, iew)] = fdiv(fadd(fmul(w1, a[o]), fmul(w2, b[o])), wd);
+}
+
 __device__ __forceinline__ float exp_rn(float x) { return (float)exp((double)x); }
 __device__ __forceinline__ float log_rn(float x) { return (float)log((double)x); }
 __device__ __forceinline__ float pow_rn(float x, float y) { return (float)pow((double)x, (double)y); }
@@ -130,6 +145,16 @@ int wind_increment_device(og_ctx* ctx, int dir, const float* w, const float* wA,
     dim3 grid((jns + 255) / 256, iew, kbu);
     if (dir == 0) wind_increment_kernel<0><<<grid, 256, 0, ctx->stream>>>(w, wA, wC, out, jns, iew);
     else wind_increment_kernel<1><<<grid, 256, 0, ctx->stream>>>(w, wA, wC, out, jns, iew);
+    ctx->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+int temporal_interp_device(og_ctx* ctx, const float* a, const float* b, float* out, int jns, int iew,
+                           int nlev, float w1, float w2, float wd, int cross)
+{
+    dim3 grid((jns + 255) / 256, iew, nlev);
+    temporal_interp_kernel<<<grid, 256, 0, ctx->stream>>>(a, b, out, jns, iew, w1, w2, wd, cross);
     ctx->count_launch();
     OG_CUDA(cudaGetLastError());
     return OG_OK;

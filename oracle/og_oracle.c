@@ -742,7 +742,8 @@ typedef struct {
 } qc_level_job;
 
 /* proc_qc.F90:247-406 for one level kp (0-based k). */
-static void qc_level(const og_time_desc* d, const og_qc_params* p, int k, int job_mask)
+static void qc_level_density(const og_time_desc* d, const og_qc_params* p, int k, int job_mask,
+                             float* tobbox)
 {
     const int iew = d->iew, jns = d->jns, nrep = d->nrep;
     const size_t npts = (size_t)iew * jns;
@@ -811,6 +812,7 @@ static void qc_level(const og_time_desc* d, const og_qc_params* p, int k, int jo
             elev[n] = d->elev[r]; qc[n] = q; idx[n] = r; ++n;
         }
         ogo_local_time(p->time_hhmmss / 100, lon, n, lt);  /* proc_qc.F90:344 */
+        if (tobbox && k == 0) ogo_ob_density(x, y, d->dx_km, n, tobbox, iew, jns);   /* :349-351 */
         if (p->qc_test_error_max)
             ogo_error_max(val, x, y, elev, qc, n, gridded, iew, jns, ivar, error_difference, pk,
                           lt, NULL, NULL, NULL);
@@ -840,6 +842,26 @@ static void qc_consistency(const og_time_desc* d, int k_begin, int k_end)
             if (contains_2n(qc_t, OG_FAILS_BUDDY_CHECK) && !contains_2n(qc_rh, OG_FAILS_BUDDY_CHECK))
                 ogo_add_to_qc_flag(&d->qc_rh[q], OG_FAILS_BUDDY_CHECK);
         }
+}
+
+static void qc_level(const og_time_desc* d, const og_qc_params* p, int k, int job_mask)
+{
+    qc_level_density(d, p, k, job_mask, NULL);
+}
+
+/* proc_qc.F90:243-420 for a surface-FDDA time: the level x variable loop with the observation
+ * density accumulated at kp = 1, then :416-420. */
+int ogo_qc_time_fdda(const og_time_desc* d, const og_qc_params* p, float* tobbox, float* odis)
+{
+    for (int k = 0; k < d->kbu; ++k) qc_level_density(d, p, k, 0, tobbox);
+    const size_t npts = (size_t)d->iew * d->jns;
+    for (size_t q = 0; q < npts; ++q) {
+        tobbox[q] = tobbox[q] / 5.f;
+        if (tobbox[q] < 1.f) tobbox[q] = 0.f;
+    }
+    ogo_obs_distance(tobbox, odis, d->iew, d->jns, d->dx_km);
+    qc_consistency(d, 0, d->kbu);
+    return OG_OK;
 }
 
 int ogo_qc_time(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
@@ -1155,5 +1177,31 @@ int ogo_mixing_ratio(float* rh, const float* t, const float* h, const float* ter
             const float qs = eps * es / (psfc[o] / 100.f - es);
             qv[o] = fmaxf(0.01f * rh[o] * qs, 0.0f);
         }
+    return OG_OK;
+}
+
+/* temporal_interp, tinterp_module.F90:53-215, for one field.  Returns OG_ERR_INVALID where the
+ * reference STOPs on a zero weight sum (:112-115). */
+int ogo_temporal_interp(const float* first, const float* second, float* out, int jns, int iew,
+                        int nlev, int icount_fdda, int icount_1, int icount_2, int cross)
+{
+    int w1i = icount_2 - icount_fdda, w2i = icount_fdda - icount_1;      /* :98-104 */
+    if (w1i == 0 && w2i == 0) w1i = 1;                                    /* :106-109 */
+    if (w1i + w2i == 0) return OG_ERR_INVALID;
+    const float w1 = (float)w1i, w2 = (float)w2i, wd = (float)(w1i + w2i);
+    const int je = cross ? jns - 1 : jns, ie = cross ? iew - 1 : iew;
+    for (int k = 0; k < nlev; ++k) {
+        for (int i = 0; i < ie; ++i)
+            for (int j = 0; j < je; ++j) {
+                const size_t o = IX3(j, i, k, jns, iew);
+                out[o] = (w1 * first[o] + w2 * second[o]) / wd;          /* :128-130 */
+            }
+        if (cross) {
+            for (int i = 0; i < iew - 1; ++i)                             /* t(jns,:iew-1,:) = t(jns-1,:iew-1,:) */
+                out[IX3(jns - 1, i, k, jns, iew)] = out[IX3(jns - 2, i, k, jns, iew)];
+            for (int j = 0; j < jns; ++j)                                 /* t(:jns,iew,:) = t(:jns,iew-1,:) */
+                out[IX3(j, iew - 1, k, jns, iew)] = out[IX3(j, iew - 2, k, jns, iew)];
+        }
+    }
     return OG_OK;
 }

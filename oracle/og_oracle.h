@@ -88,6 +88,9 @@ float ogo_dewpoint(float t, float rh);
 int ogo_qc_time(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
                 int run_consistency);
 int ogo_oa_time(const og_time_desc* d, const og_oa_params* p, int k_begin, int k_end);
+/* proc_qc of a surface-FDDA time: ogo_qc_time over every level + ob_density at kp = 1,
+ * tobbox / 5 thresholded at 1, obs_distance (proc_qc.F90:349-351, :412-420). */
+int ogo_qc_time_fdda(const og_time_desc* d, const og_qc_params* p, float* tobbox, float* odis);
 /* Same as ogo_oa_time but slabs are distributed over `threads` pthreads (slabs of one
  * level are independent) -- the "all host cores" CPU baseline. */
 int ogo_oa_time_mt(const og_time_desc* d, const og_oa_params* p, int k_begin, int k_end,
@@ -107,6 +110,8 @@ void ogo_wind_increment_u(float* u, const float* uA, const float* uC, int jns, i
 void ogo_wind_increment_v(float* v, const float* vA, const float* vC, int jns, int iew, int kbu);
 void ogo_pres_sfc_from_slp(const float* pres_sfc, const float* slp_C, const float* slp_x,
                            float* out, int jns, int iew);
+int ogo_temporal_interp(const float* first, const float* second, float* out, int jns, int iew,
+                        int nlev, int icount_fdda, int icount_1, int icount_2, int cross);
 int ogo_mixing_ratio(float* rh, const float* t, const float* h, const float* terrain,
                      const float* slp_x, const float* pressure, int iew, int jns, int kbu,
                      float* qv, float* psfc);

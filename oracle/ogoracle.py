@@ -227,6 +227,19 @@ def pres_sfc_from_slp(pres_sfc, slp_C, slp_x):
     return out
 
 
+def temporal_interp(first, second, icount_fdda, icount_1, icount_2, cross):
+    a, b = f32(first), f32(second)
+    nlev = a.shape[0] if a.ndim == 3 else 1
+    iew, jns = a.shape[-2], a.shape[-1]
+    out = np.zeros_like(a)
+    l = lib()
+    l.ogo_temporal_interp.restype = C.c_int
+    l.ogo_temporal_interp.argtypes = [_vp, _vp, _vp] + [C.c_int] * 7
+    rc = l.ogo_temporal_interp(ptr(a), ptr(b), ptr(out), jns, iew, nlev, icount_fdda, icount_1,
+                               icount_2, int(cross))
+    return rc, out
+
+
 def mixing_ratio(rh, t, h, terrain, slp_x_pa, pressure):
     rh = f32(rh).copy(); t, h = f32(t), f32(h)
     terrain, slp, pressure = f32(terrain), f32(slp_x_pa), f32(pressure)
@@ -250,6 +263,17 @@ def qc_time(case, k_begin=0, k_end=None, run_consistency=True, threads=1):
     k_end = case.kbu if k_end is None else k_end
     return lib().ogo_qc_time_mt(C.byref(d), C.byref(case.qc_params), k_begin, k_end,
                                 int(run_consistency), threads)
+
+
+def qc_time_fdda(case, tobbox):
+    """proc_qc of a surface-FDDA time; returns (tobbox, odis), (iew, jns) C order."""
+    d = case.desc()
+    tb = f32(tobbox).copy(); od = np.zeros_like(tb)
+    l = lib()
+    l.ogo_qc_time_fdda.restype = C.c_int
+    l.ogo_qc_time_fdda.argtypes = [C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), _vp, _vp]
+    l.ogo_qc_time_fdda(C.byref(d), C.byref(case.qc_params), ptr(tb), ptr(od))
+    return tb, od
 
 
 def oa_time(case, k_begin=0, k_end=None, threads=1):

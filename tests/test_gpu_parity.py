@@ -533,3 +533,37 @@ def test_mixing_ratio_needs_the_mandatory_levels(ctx):
     press, rh, t, h, terrain, slp = _epilogue_case([1001, 1000, 925, 850], 6, 6, 1)
     with pytest.raises(OgError):
         ctx.mixing_ratio(rh, t, h, terrain, slp, press)
+
+
+def test_qc_time_fdda_density_bit_exact(ctx, oracle):
+    """proc_qc of a surface-FDDA time (proc_qc.F90:243-420): flags as og_qc_time, tobbox and odis
+    bit-identical (counts are exact in FP32; the distance is an exact EDT)."""
+    base = synth.small_case(iew=90, jns=70, kbu=5, n_sfc=60, n_snd=10, radii=(6, 4), seed=23,
+                            dx_m=60000.0)      # 250 km = 4.2 cells: boxes with and without obs
+    rng = np.random.default_rng(2)
+    tb0 = rng.integers(0, 3, (base.iew, base.jns)).astype(np.float32)   # the driver hands in the previous tobbox
+    for tb_in in (np.zeros_like(tb0), tb0):
+        cpu, gpu = base.copy(), base.copy()
+        tb_c, od_c = oracle.qc_time_fdda(cpu, tb_in)
+        tb_g, od_g = ctx.proc_qc_fdda(gpu, tb_in)
+        np.testing.assert_array_equal(tb_c, tb_g)
+        np.testing.assert_array_equal(od_c, od_g)
+        assert tb_c.max() >= 1.0 and od_c.max() > 0.0 and (tb_c == 0).any()
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_slp"):
+            np.testing.assert_array_equal(getattr(cpu, nm), getattr(gpu, nm))
+        assert len(_rh_flag_mismatches(cpu, gpu)) <= 2
+
+
+@pytest.mark.parametrize("shape", [(3, 6, 5), (27, 120, 97), (64, 51)])
+def test_temporal_interp_bit_exact(ctx, oracle, shape):
+    """tinterp_module.F90:53-215, every weight pattern of a 6-hour bracket, both grid kinds."""
+    rng = np.random.default_rng(len(shape) * 17 + shape[-1])
+    a = rng.normal(280, 5, shape).astype(np.float32); b = rng.normal(282, 5, shape).astype(np.float32)
+    for (cf, c1, c2) in ((1, 0, 6), (2, 0, 6), (5, 0, 6), (0, 0, 6), (6, 0, 6), (3, 3, 3)):
+        for cross in (False, True):
+            rc, want = oracle.temporal_interp(a, b, cf, c1, c2, cross)
+            assert rc == 0
+            np.testing.assert_array_equal(ctx.temporal_interp(a, b, cf, c1, c2, cross), want)
+    from obsgrid_b200._capi import OgError
+    with pytest.raises(OgError):
+        ctx.temporal_interp(a, b, 4, 2, 2, False)

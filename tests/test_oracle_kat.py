@@ -498,3 +498,53 @@ def test_mixing_ratio_and_sfcprs_against_float64(oracle):
     # no 850/700/500 hPa level: the reference STOPs, the restatement reports it
     rc, *_ = oracle.mixing_ratio(rh[:4], t[:4], h[:4], terrain, slp, np.array([1001, 1000, 925, 850], np.float32))
     assert rc != 0
+
+
+def test_qc_time_fdda_is_qc_time_plus_density(oracle):
+    """proc_qc.F90:349-351, :412-420: the FDDA variant leaves the flags of ogo_qc_time and adds
+    tobbox = (sum over the six checked surface variables of ob_density) / 5, zeroed below 1."""
+    from obsgrid_b200 import synth
+    base = synth.small_case(iew=50, jns=44, kbu=4, n_sfc=30, n_snd=6, radii=(6, 4), seed=5, dx_m=60000.0)
+    a, b = base.copy(), base.copy()
+    oracle.qc_time(a)
+    tb, od = oracle.qc_time_fdda(b, np.zeros((base.iew, base.jns), np.float32))
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp"):
+        np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm))
+    want = np.zeros((base.iew, base.jns), np.float32)
+    ok_xy = (base.xob >= 2) & (base.xob <= base.iew - 1) & (base.yob >= 2) & (base.yob <= base.jns - 1)
+    miss = lambda v: np.abs(v - np.float32(-888888.0)) <= 1
+    for ob in (base.ob_u[0], base.ob_v[0], base.ob_t[0], base.ob_rh[0], base.ob_slp):
+        m = ok_xy & ~miss(ob)
+        want = oracle.ob_density(base.xob[m], base.yob[m], float(base.dx_km), want)
+    m = ok_xy & ~miss(base.ob_rh[0]) & ~miss(base.ob_t[0])          # DEWPOINT: the sixth surface slab
+    want = oracle.ob_density(base.xob[m], base.yob[m], float(base.dx_km), want)
+    want = want / np.float32(5.0); want[want < 1] = 0
+    np.testing.assert_array_equal(tb, want)
+    np.testing.assert_array_equal(od, oracle.obs_distance(want, float(base.dx_km)))
+    assert (tb > 0).any() and (tb == 0).any()
+
+
+def test_temporal_interp_by_hand(oracle):
+    """tinterp_module.F90:98-132: integer weights, cross-point edge replication."""
+    rng = np.random.default_rng(4)
+    a = rng.normal(280, 5, (3, 6, 5)).astype(np.float32); b = rng.normal(282, 5, (3, 6, 5)).astype(np.float32)
+    f = np.float32
+    # FDDA hour 2 of a 6-hour bracket: w1 = 6-2 = 4, w2 = 2-0 = 2
+    rc, o = oracle.temporal_interp(a, b, 2, 0, 6, cross=False)
+    assert rc == 0
+    np.testing.assert_array_equal(o, (f(4) * a + f(2) * b) / f(6))
+    rc, o = oracle.temporal_interp(a, b, 2, 0, 6, cross=True)
+    want = (f(4) * a + f(2) * b) / f(6)
+    want[:, :-1, -1] = want[:, :-1, -2]         # t(jns,:iew-1,:) = t(jns-1,:iew-1,:)
+    want[:, -1, :] = want[:, -2, :]             # t(:jns,iew,:)   = t(:jns,iew-1,:)
+    np.testing.assert_array_equal(o, want)
+    # both bracketing times at the FDDA time: the first time is used as is (:106-109)
+    rc, o = oracle.temporal_interp(a, b, 3, 3, 3, cross=False)
+    np.testing.assert_array_equal(o, a)
+    # weights summing to zero: the reference STOPs
+    rc, _ = oracle.temporal_interp(a, b, 5, 7, 3, cross=False)      # w1 = -2, w2 = -2 ... sum -4: fine
+    assert rc == 0
+    rc, _ = oracle.temporal_interp(a, b, 4, 6, 2, cross=False)      # w1 = -2, w2 = -2
+    assert rc == 0
+    rc, _ = oracle.temporal_interp(a, b, 4, 2, 2, cross=False)      # w1 = -2, w2 = 2 -> 0
+    assert rc != 0
