@@ -84,6 +84,8 @@ SIGNATURES = {
     "og_get_stats": (C.c_int, [_vp, C.POINTER(OgStats)]),
     "og_reset_stats": (C.c_int, [_vp]),
     "og_set_counting": (C.c_int, [_vp, C.c_int]),
+    "og_set_arithmetic": (C.c_int, [_vp, C.c_int]),
+    "og_get_arithmetic": (C.c_int, [_vp]),
     "og_set_timing": (C.c_int, [_vp, C.c_int]),
     "og_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "og_host_free": (C.c_int, [_vp]),

@@ -50,6 +50,13 @@ class Context:
     def set_counting(self, on: bool):
         check(self._lib.og_set_counting(self._h, int(on)), "og_set_counting")
 
+    def set_arithmetic(self, mode: str):
+        """'exact' (reference arithmetic, bit-identical) or 'contracted' (FMA + hardware reciprocal)."""
+        check(self._lib.og_set_arithmetic(self._h, {"exact": 0, "contracted": 1}[mode]), "og_set_arithmetic")
+
+    def arithmetic(self) -> str:
+        return ("exact", "contracted")[self._lib.og_get_arithmetic(self._h)]
+
     def set_timing(self, on: bool):
         check(self._lib.og_set_timing(self._h, int(on)), "og_set_timing")
 

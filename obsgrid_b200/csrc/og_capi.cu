@@ -105,6 +105,13 @@ extern "C" int og_reset_stats(og_ctx* c)
     return OG_OK;
 }
 extern "C" int og_set_counting(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->counting = on; return OG_OK; }
+extern "C" int og_set_arithmetic(og_ctx* c, int mode)
+{
+    if (!c || (mode != OG_ARITH_EXACT && mode != OG_ARITH_CONTRACTED)) { set_error("og_set_arithmetic: bad argument"); return OG_ERR_INVALID; }
+    c->arithmetic = mode;
+    return OG_OK;
+}
+extern "C" int og_get_arithmetic(og_ctx* c) { return c ? c->arithmetic : OG_ERR_INVALID; }
 extern "C" int og_set_timing(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->time_kernels = on != 0; c->timers_used = 0; return OG_OK; }
 extern "C" void* og_stream(og_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" int og_sync(og_ctx* c) { if (!c) return OG_ERR_INVALID; OG_CUDA(cudaStreamSynchronize(c->stream)); return OG_OK; }

@@ -47,6 +47,7 @@ struct og_ctx {
     Slot slots[OG_SLOTS];
     og_stats stats{};
     int counting = 0;
+    int arithmetic = OG_ARITH_EXACT;            // og_set_arithmetic
     unsigned long long* d_counters = nullptr;   // [0] updates, [1] candidates
     int* d_flag = nullptr;                      // small device scratch (changed flags)
     int* h_pinned_small = nullptr;              // pinned host scratch (>= 4 KiB)

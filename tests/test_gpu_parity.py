@@ -567,3 +567,50 @@ def test_temporal_interp_bit_exact(ctx, oracle, shape):
     from obsgrid_b200._capi import OgError
     with pytest.raises(OgError):
         ctx.temporal_interp(a, b, 4, 2, 2, False)
+
+
+# ---- OG_ARITH_CONTRACTED: the opt-in scan arithmetic (FMA contraction, hardware reciprocal) --------
+@pytest.fixture
+def contracted(ctx):
+    ctx.set_arithmetic("contracted")
+    assert ctx.arithmetic() == "contracted"
+    yield ctx
+    ctx.set_arithmetic("exact")
+
+
+@pytest.mark.parametrize("var,pressure", [(3, 500.0), (5, 1001.0), (1, 300.0), (2, 850.0), (4, 1001.0)])
+def test_contracted_cressman_within_north_star_tolerance(contracted, oracle, var, pressure):
+    """Every shape (circles for TT/PMSL; circles, ellipses and bananas for UU/VV/RH, with RH
+    scaling) against the oracle at 1e-5 relative / 1e-3 absolute, the north-star bar; the
+    observed deviation is two orders of magnitude smaller, which the test also pins."""
+    rng = np.random.default_rng(int(pressure) * 7 + var)
+    iew, jns, n, R = 140, 110, 2500, 7
+    g = wavy(iew, jns, 20.0, 50.0)
+    ub, vb = wind_fields(iew, jns)
+    x, y = rng_obs(rng, n, iew, jns, lo=1.0)
+    d = rng.normal(0, 5, n).astype(np.float32)
+    fg = np.abs(rng.normal(50, 20, n)).astype(np.float32) + 1
+    a = oracle.cressman(d, x, y, g, var, R, 12.0, ub, vb, pressure, fg_value=fg, scale_rh=True)
+    b = contracted.cressman(d, x, y, g, var, R, 12.0, ub, vb, pressure, fg_value=fg, scale_rh=True)
+    np.testing.assert_allclose(b, a, rtol=RTOL, atol=ATOL)
+    assert np.max(np.abs(b.astype(np.float64) - a)) < 1e-4
+    assert np.any(a != g)
+
+
+def test_contracted_time_small(contracted, oracle):
+    """A whole analysis time: flags are untouched by the mode (QC is always exact); all five
+    analysed fields within the north-star tolerance of the oracle."""
+    base = synth.small_case(iew=60, jns=52, kbu=6, n_sfc=500, n_snd=120, radii=(6, 4, 2), scale_rh=True)
+    cpu, gpu = base.copy(), base.copy()
+    oracle.qc_time(cpu); contracted.proc_qc(gpu)
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_slp"):
+        np.testing.assert_array_equal(getattr(cpu, nm), getattr(gpu, nm), err_msg=nm)
+    gpu.qc_rh[...] = cpu.qc_rh
+    assert oracle.oa_time(cpu) == contracted.proc_oa(gpu) == 0
+    for nm in ("t", "u", "v", "rh", "slp"):
+        np.testing.assert_allclose(getattr(gpu, nm), getattr(cpu, nm), rtol=RTOL, atol=ATOL, err_msg=nm)
+
+
+def test_arithmetic_mode_is_validated(ctx):
+    from obsgrid_b200._capi import lib
+    assert lib().og_set_arithmetic(ctx._h, 7) == -2 and ctx.arithmetic() == "exact"
