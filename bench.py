@@ -41,7 +41,12 @@ from obsgrid_b200._capi import OgTimeDesc  # noqa: E402
 
 METRIC = "cressman_gridpoint_x_obs_updates_per_s"
 UNIT = "updates/s"
-ALGO_FLOP_PER_UPDATE = 11          # circle update = 11 FP32 ops (divide counted once)
+# SURVEY 8d, algorithmic FP32 operations per contributing (grid point, ob) update, the divide counted
+# once: circle 11; ellipse +9 (stream coordinates, division by the elongation); banana about +25
+# (atan2, sqrt, angle wrap).  The kernels count the updates per shape (og_stats).
+ALGO_FLOP_PER_UPDATE = 11
+ALGO_FLOP_ELLIPSE = 20
+ALGO_FLOP_BANANA = 36
 FIELD_NAMES = ("t", "u", "v", "rh", "slp")
 FLAG_NAMES = ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp")
 TABLE_NAMES = ("xob", "yob", "lon", "elev", "ob_u", "ob_v", "ob_t", "ob_rh", "ob_slp")
@@ -236,6 +241,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     ctx = Context(local_rank)
+    ctx.set_arithmetic(args.arith)
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     case = build_case(args, rank)
@@ -300,6 +306,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     st = ctx.stats()
     ctx.set_counting(False)
     updates, candidates = st["cressman_updates"], st["cressman_candidates"]
+    upd_ell, upd_ban = st["cressman_updates_ellipse"], st["cressman_updates_banana"]
     buddy_obs, pair_tests = st["buddy_obs"], st["buddy_pair_tests"]
     restore_host(); step_e2e()
     same = all(np.array_equal(work[nm].cpu().numpy(), getattr(hcase, nm)) for nm in FIELD_NAMES + FLAG_NAMES)
@@ -382,12 +389,13 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
 
     # ---- reduce over ranks: max time, summed work ------------------------------------------------
     vec = torch.tensor([step_ms, e2e_ms, qc_ms, oa_ms, scan_ms / args.steps], device=dev, dtype=torch.float64)
-    tot = torch.tensor([updates, buddy_obs, pair_tests, candidates, launches], device=dev, dtype=torch.float64)
+    tot = torch.tensor([updates, buddy_obs, pair_tests, candidates, launches, upd_ell, upd_ban], device=dev,
+                       dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(vec, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     step_ms, e2e_ms, qc_ms, oa_ms, scan_ms_step = [float(x) for x in vec.tolist()]
-    g_updates, g_bobs, g_pairs, g_cands, g_launch = [float(x) for x in tot.tolist()]
+    g_updates, g_bobs, g_pairs, g_cands, g_launch, g_ell, g_ban = [float(x) for x in tot.tolist()]
 
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -395,7 +403,10 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         traffic_bytes, traffic_src = measured_traffic(args.config)
         n_scan_launch = sum(1 for r in case.oa_params.radius_influence if r >= 0)
         per_launch_ms = scan_ms_step / max(n_scan_launch, 1)
-        flops_per_launch = ALGO_FLOP_PER_UPDATE * updates / max(n_scan_launch, 1)
+        # rank 0's own kernels against rank 0's own peak
+        algo_flops = (ALGO_FLOP_PER_UPDATE * (updates - upd_ell - upd_ban) + ALGO_FLOP_ELLIPSE * upd_ell +
+                      ALGO_FLOP_BANANA * upd_ban)
+        flops_per_launch = algo_flops / max(n_scan_launch, 1)
         achieved_tf = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
         n_oa_slabs = (5 if K0 == 0 else 0) + 4 * (KR - max(K0, 1))
         hbm_bytes_launch = n_oa_slabs * 8.0 * case.iew * case.jns
@@ -405,7 +416,12 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "frac": achieved_tf / (fp32_peak_ops / 1e12) if fp32_peak_ops else None,
             "peak_source": "measured in this run: og_fp32_peak (FMUL+FADD chains, no FMA: the "
                            "parity build has -fmad=false, 1 lane-instruction = 1 FLOP)",
-            "algorithmic_flop_per_update": ALGO_FLOP_PER_UPDATE,
+            "algorithmic_flop_per_update": {"circle": ALGO_FLOP_PER_UPDATE, "ellipse": ALGO_FLOP_ELLIPSE,
+                                            "banana": ALGO_FLOP_BANANA,
+                                            "mean_over_this_workload": algo_flops / max(updates, 1)},
+            "updates_by_shape": {"circle": updates - upd_ell - upd_ban, "ellipse": upd_ell, "banana": upd_ban},
+            "frac_if_every_update_were_a_circle": (ALGO_FLOP_PER_UPDATE * updates / max(n_scan_launch, 1) /
+                                                   (per_launch_ms * 1e-3) / fp32_peak_ops) if per_launch_ms > 0 and fp32_peak_ops else None,
             "avg_launch_ms": per_launch_ms, "launches_per_step": n_scan_launch,
             "traffic": traffic_bytes, "traffic_source": traffic_src,
             "hbm": {"achieved": hbm_bytes_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0,
@@ -424,6 +440,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                        "grid": [case.iew, case.jns], "levels": K, "reports": case.nrep,
                        "scans": [int(r) for r in case.oa_params.radius_influence if r >= 0],
                        "scale_cressman_rh_decreases": bool(case.oa_params.scale_cressman_rh_decreases),
+                       "scan_arithmetic": ctx.arithmetic(),
                        "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
                              "pristine copy before every step",
                        "parallelism": (f"1 analysis time, levels sharded over {world} ranks" if args.scaling == "strong"
@@ -462,6 +479,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json configs[config-1]")
     ap.add_argument("--scale-rh", action="store_true")
+    ap.add_argument("--arith", default="exact", choices=["exact", "contracted"],
+                    help="scan-kernel arithmetic (og_set_arithmetic); exact = bit-identical to the reference's")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one analysis time per rank; strong: one time, levels sharded over the ranks")

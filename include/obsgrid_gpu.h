@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define OG_ABI_VERSION 1
+#define OG_ABI_VERSION 2
 
 typedef enum og_status {
     OG_OK = 0,
@@ -104,6 +104,8 @@ typedef struct og_stats {
     int64_t buddy_fixpoint_iters;
     int64_t buddy_pairs_examined;   /* pair tests the binned kernel actually ran; buddy_pair_tests
                                        is the reference's N*(N-1) for the same slabs */
+    int64_t cressman_updates_ellipse;   /* of cressman_updates: pairs of an ellipse-shaped ob     */
+    int64_t cressman_updates_banana;    /* ... of a banana-shaped ob (oa_module.F90:505-542)      */
 } og_stats;
 int  og_get_stats(og_ctx* ctx, og_stats* out);
 int  og_reset_stats(og_ctx* ctx);

@@ -33,7 +33,7 @@ class OgStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "kernel_launches", "cressman_updates", "cressman_candidates", "buddy_pair_tests",
         "buddy_obs", "h2d_bytes", "d2h_bytes", "buddy_fixpoint_iters",
-        "buddy_pairs_examined")]
+        "buddy_pairs_examined", "cressman_updates_ellipse", "cressman_updates_banana")]
 
 
 class OgQcParams(C.Structure):

@@ -81,12 +81,14 @@ extern "C" int og_finalize(og_ctx* c)
 
 static int fetch_counters(og_ctx* c)
 {
-    unsigned long long h[4];
+    unsigned long long h[6];
     OG_CUDA(cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     OG_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.cressman_updates = (int64_t)h[0];
     c->stats.cressman_candidates = (int64_t)h[1];
     c->stats.buddy_pairs_examined = (int64_t)h[3];
+    c->stats.cressman_updates_ellipse = (int64_t)h[4];
+    c->stats.cressman_updates_banana = (int64_t)h[5];
     return OG_OK;
 }
 
@@ -101,7 +103,7 @@ extern "C" int og_reset_stats(og_ctx* c)
 {
     if (!c) return OG_ERR_INVALID;
     c->stats = og_stats{};
-    OG_CUDA(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream));
+    OG_CUDA(cudaMemsetAsync(c->d_counters, 0, 6 * sizeof(unsigned long long), c->stream));
     return OG_OK;
 }
 extern "C" int og_set_counting(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->counting = on; return OG_OK; }

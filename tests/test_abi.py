@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(str(_capi.LIB_PATH))
     missing = [n for n in declared_functions() if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.og_abi_version() == 1
+    assert lib.og_abi_version() == 2
 
 
 def test_ctypes_binding_covers_the_header():
