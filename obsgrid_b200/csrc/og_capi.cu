@@ -658,7 +658,8 @@ __global__ void put_kernel(const PutSlab* slabs, const int* oqc, const int* oidx
     const PutSlab S = slabs[blockIdx.y];
     int li = blockIdx.x * blockDim.x + threadIdx.x;
     if (li >= S.n) return;
-    S.qc[oidx[S.ob_off + li]] = oqc[S.ob_off + li];
+    // the RH row is written by two slabs (RH and DEWPOINT): each ORs its bits in
+    atomicOr(&S.qc[oidx[S.ob_off + li]], oqc[S.ob_off + li]);
 }
 
 // qc_consistency (qc0_module.F90:371-404) on the table rows of the levels in range;
@@ -876,9 +877,14 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
     OG_TRY(c->reserve_t("qc.lt_rep", (size_t)std::max(T.nrep, 1), &lt_rep));
     OG_TRY(local_time_device(c, p->time_hhmmss / 100, T.lon, T.nrep, lt_rep)); // proc_qc.F90:344
 
-    for (int phase = 0; phase < 2; ++phase) { // 0: UU VV TT RH PMSL, 1: DEWPOINT (reads RH flags)
-        if (phase == 1) {
-            if (!p->qc_dewpoint) break;
+    // One batch for every slab of the level range.  The reference runs DEWPOINT (ivar 7) after RH
+    // (ivar 4) of the same level and hands it RH's output flags (ob_access_module.F90:466-487,
+    // :771-774); here both slabs start from the incoming flags and 'put' ORs their results into the
+    // row.  That is the same value: selection only asks qc < 2**20, which no flag set here can
+    // change, no test reads the flags, and modify_qc_flag / add_to_qc_flag set one bit of a
+    // non-negative integer (qc0_module.F90:27-31, :55-72), so (q | rh_bits) | dew_bits either way.
+    {
+        if (p->qc_dewpoint) {
             OG_TRY(c->reserve_t("qc.w_dew", per * nlev, &w_dew));
             dewfield_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_t, w_rh, w_dew, per * nlev);
             c->count_launch();
@@ -893,7 +899,7 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
             const size_t row = (size_t)k * T.nrep, lev = per * (size_t)(k - k0);
             const float pk = T.pressure[k];
             for (int ivar = 1; ivar <= 7; ++ivar) {
-                if ((phase == 0) == (ivar == 7)) continue;
+                if (ivar == 7 && !p->qc_dewpoint) continue;
                 if (ivar == 6) continue;                      // qc_psfc = .FALSE.
                 if (k > 0 && ivar == 5) continue;             // proc_qc.F90:255
                 if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
@@ -921,31 +927,32 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
                 b.slabs.push_back(s); sel.push_back(q); puts.push_back(pt); slab_level.push_back(k);
             }
         }
-        if (b.slabs.empty()) continue;
-        SelDev SA;
-        std::vector<int> ncount;
-        int total = 0, max_n = 0;
-        OG_TRY(run_selection(c, T, sel, true, lt_rep, SA, ncount, total));
-        for (size_t s = 0; s < b.slabs.size(); ++s) {
-            b.slabs[s].n = ncount[s]; b.slabs[s].ob_off = sel[s].ob_off;
-            puts[s].n = ncount[s]; puts[s].ob_off = sel[s].ob_off;
-            max_n = std::max(max_n, ncount[s]);
-        }
-        b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval; b.elev = SA.oelev;
-        b.local_time = SA.olt; b.qc = SA.oqc;
-        if (T.tobbox)   // proc_qc.F90:349-351: every surface variable's obs add to the density
-            for (size_t s = 0; s < b.slabs.size(); ++s)
-                if (slab_level[s] == 0)
-                    OG_TRY(ob_density_device(c, SA.ox + sel[s].ob_off, SA.oy + sel[s].ob_off, T.dx_km,
-                                             ncount[s], T.tobbox, iew, jns));
-        OG_TRY(qc_run_batch(c, b));
-        if (max_n > 0) {
-            PutSlab* d_put;
-            OG_TRY(c->reserve_t("qc.put", puts.size(), &d_put));
-            OG_TRY(c->put_small(d_put, puts.data(), sizeof(PutSlab) * puts.size()));
-            dim3 g(nblk((size_t)max_n), (unsigned)puts.size());
-            put_kernel<<<g, 256, 0, c->stream>>>(d_put, SA.oqc, SA.oidx);
-            c->count_launch();
+        if (!b.slabs.empty()) {
+            SelDev SA;
+            std::vector<int> ncount;
+            int total = 0, max_n = 0;
+            OG_TRY(run_selection(c, T, sel, true, lt_rep, SA, ncount, total));
+            for (size_t s = 0; s < b.slabs.size(); ++s) {
+                b.slabs[s].n = ncount[s]; b.slabs[s].ob_off = sel[s].ob_off;
+                puts[s].n = ncount[s]; puts[s].ob_off = sel[s].ob_off;
+                max_n = std::max(max_n, ncount[s]);
+            }
+            b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval; b.elev = SA.oelev;
+            b.local_time = SA.olt; b.qc = SA.oqc;
+            if (T.tobbox)   // proc_qc.F90:349-351: every surface variable's obs add to the density
+                for (size_t s = 0; s < b.slabs.size(); ++s)
+                    if (slab_level[s] == 0)
+                        OG_TRY(ob_density_device(c, SA.ox + sel[s].ob_off, SA.oy + sel[s].ob_off, T.dx_km,
+                                                 ncount[s], T.tobbox, iew, jns));
+            OG_TRY(qc_run_batch(c, b));
+            if (max_n > 0) {
+                PutSlab* d_put;
+                OG_TRY(c->reserve_t("qc.put", puts.size(), &d_put));
+                OG_TRY(c->put_small(d_put, puts.data(), sizeof(PutSlab) * puts.size()));
+                dim3 g(nblk((size_t)max_n), (unsigned)puts.size());
+                put_kernel<<<g, 256, 0, c->stream>>>(d_put, SA.oqc, SA.oidx);
+                c->count_launch();
+            }
         }
     }
     if (T.tobbox && T.odis && has_sfc) {   // proc_qc.F90:412-420
