@@ -23,6 +23,7 @@ constexpr int NB_MAX = 4096;         // value buckets of the long-list sorter
 
 struct BinDev {
     const BinSlab* slabs;
+    int ns;
     const short4* box;
     int* cell_count;
     int* cell_cursor;
@@ -50,9 +51,8 @@ constexpr int HCAP = 4096;
 
 __global__ void __launch_bounds__(256) bin_count_kernel(BinDev A)
 {
-    const BinSlab S = A.slabs[blockIdx.y];
-    if ((int)(blockIdx.x * blockDim.x) >= S.n) return;
-    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    const BinSlab S = A.slabs[slab_of_block(A.slabs, A.ns, (int)blockIdx.x)];
+    const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
     const int nc = S.ncx * S.ncy;
     const short4 box = (li < S.n) ? A.box[S.ob_off + li] : make_short4(1, 0, 1, 0);
     if (nc > HCAP) {
@@ -119,9 +119,8 @@ __global__ void __launch_bounds__(1024) cell_prefix_kernel(const int* __restrict
 
 __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
 {
-    const BinSlab S = A.slabs[blockIdx.y];
-    if ((int)(blockIdx.x * blockDim.x) >= S.n) return;
-    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    const BinSlab S = A.slabs[slab_of_block(A.slabs, A.ns, (int)blockIdx.x)];
+    const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
     const int nc = S.ncx * S.ncy;
     const short4 box = (li < S.n) ? A.box[S.ob_off + li] : make_short4(1, 0, 1, 0);
     if (nc > HCAP) {
@@ -392,15 +391,17 @@ int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, c
     OG_TRY(ctx->reserve_t((t + ".count").c_str(), (size_t)ncells + 1, &A.cell_count));
     OG_TRY(ctx->reserve_t((t + ".cursor").c_str(), (size_t)ncells + 1, &A.cell_cursor));
     OG_TRY(ctx->reserve_t((t + ".start").c_str(), (size_t)ncells + 1, &A.cell_start));
-    A.slabs = d_slabs; A.box = d_box;
+    A.slabs = d_slabs; A.ns = ns; A.box = d_box;
+    std::vector<BinSlab> hs(slabs);
+    int nblk = 0;
+    for (BinSlab& q : hs) { q.blk_off = nblk; nblk += (q.n + 255) / 256; }
     OG_CUDA(cudaMemsetAsync(A.cell_count, 0, sizeof(int) * ((size_t)ncells + 1), st));
     OG_CUDA(cudaMemsetAsync(A.cell_start, 0, sizeof(int) * ((size_t)ncells + 1), st));
     int list_total = 0;
     if (ns > 0 && max_n > 0 && ncells > 0) {
-        OG_TRY(ctx->put_small(d_slabs, slabs.data(), sizeof(BinSlab) * ns));
+        OG_TRY(ctx->put_small(d_slabs, hs.data(), sizeof(BinSlab) * ns));
         OG_CUDA(cudaMemsetAsync(A.cell_cursor, 0, sizeof(int) * ((size_t)ncells + 1), st));
-        dim3 g_ob((max_n + 255) / 256, ns);
-        bin_count_kernel<<<g_ob, 256, 0, st>>>(A);
+        bin_count_kernel<<<nblk, 256, 0, st>>>(A);
         cell_prefix_kernel<<<1, 1024, 0, st>>>(A.cell_count, A.cell_start, (int)ncells, ctx->d_flag);
         ctx->count_launch(2);
         void* h_total = nullptr;
@@ -414,8 +415,7 @@ int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, c
     A.cell_sorted = A.cell_list;
     if (sorted) OG_TRY(ctx->reserve_t((t + ".sorted").c_str(), nlist, &A.cell_sorted));
     if (list_total > 0) {
-        dim3 g_ob((max_n + 255) / 256, ns);
-        bin_fill_kernel<<<g_ob, 256, 0, st>>>(A);
+        bin_fill_kernel<<<nblk, 256, 0, st>>>(A);
         ctx->count_launch();
         if (sorted) {
             OG_TRY(ctx->reserve_t((t + ".big").c_str(), (size_t)ncells + 1, &A.big_cells));

@@ -652,11 +652,11 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_scatter_kernel(SelDev A)
 }
 
 // 'put' (proc_ob_access.F90:381-403): flags back into the table rows
-struct PutSlab { int* qc; int ob_off; int n; };
-__global__ void put_kernel(const PutSlab* slabs, const int* oqc, const int* oidx)
+struct PutSlab { int* qc; int ob_off; int n; int blk_off; };
+__global__ void put_kernel(const PutSlab* slabs, int ns, const int* oqc, const int* oidx)
 {
-    const PutSlab S = slabs[blockIdx.y];
-    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    const PutSlab S = slabs[slab_of_block(slabs, ns, (int)blockIdx.x)];
+    const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
     if (li >= S.n) return;
     // the RH row is written by two slabs (RH and DEWPOINT): each ORs its bits in
     atomicOr(&S.qc[oidx[S.ob_off + li]], oqc[S.ob_off + li]);
@@ -930,11 +930,12 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
         if (!b.slabs.empty()) {
             SelDev SA;
             std::vector<int> ncount;
-            int total = 0, max_n = 0;
+            int total = 0, max_n = 0, nblk_ob = 0;
             OG_TRY(run_selection(c, T, sel, true, lt_rep, SA, ncount, total));
             for (size_t s = 0; s < b.slabs.size(); ++s) {
                 b.slabs[s].n = ncount[s]; b.slabs[s].ob_off = sel[s].ob_off;
                 puts[s].n = ncount[s]; puts[s].ob_off = sel[s].ob_off;
+                puts[s].blk_off = nblk_ob; nblk_ob += (ncount[s] + 255) / 256;
                 max_n = std::max(max_n, ncount[s]);
             }
             b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval; b.elev = SA.oelev;
@@ -949,8 +950,7 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
                 PutSlab* d_put;
                 OG_TRY(c->reserve_t("qc.put", puts.size(), &d_put));
                 OG_TRY(c->put_small(d_put, puts.data(), sizeof(PutSlab) * puts.size()));
-                dim3 g(nblk((size_t)max_n), (unsigned)puts.size());
-                put_kernel<<<g, 256, 0, c->stream>>>(d_put, SA.oqc, SA.oidx);
+                put_kernel<<<nblk_ob, 256, 0, c->stream>>>(d_put, (int)puts.size(), SA.oqc, SA.oidx);
                 c->count_launch();
             }
         }

@@ -166,6 +166,7 @@ struct BinSlab {
     int cell;           // cell edge in grid points
     int ncx, ncy;       // cells per row / column
     int cell_off;       // first cell of the slab in the per-cell arrays (cumulative)
+    int blk_off;        // first 256-ob block of the slab in the flat per-ob grids (filled by bin_build)
 };
 struct BinLists {
     const BinSlab* slabs = nullptr;   // device copy of the slab table

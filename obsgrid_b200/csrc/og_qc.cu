@@ -36,10 +36,12 @@ struct QcSlabDev {
     float t_lo, t_hi;   // buddy iff t_lo <= dx*dx+dy*dy <= t_hi
     float reach;        // >= the largest |dx| or |dy| (grid cells) a buddy pair can have
     int ncx, ncy, cell_off;   // cells of the slab (edge ~ reach), first cell in the per-cell arrays
+    int blk_off;              // first 256-ob block of the slab in the flat per-ob grids
 };
 
 struct QcDev {
     const QcSlabDev* slabs;
+    int nslab;
     int iew, jns;
     float buddy_weight;
     int do_error_max, do_buddy;
@@ -84,8 +86,8 @@ __device__ __forceinline__ float dewpoint_factor(float ob)
 // error_max (qc1_module.F90:102-249) and the per-ob set-up of buddy_check (:121-213).
 __global__ void __launch_bounds__(256) qc_prep_kernel(QcDev A)
 {
-    const QcSlabDev& S = A.slabs[blockIdx.y];
-    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    const QcSlabDev& S = A.slabs[slab_of_block(A.slabs, A.nslab, (int)blockIdx.x)];
+    const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
     if (li >= S.n) return;
     const int gi = S.ob_off + li;
     const float x = A.xob[gi], y = A.yob[gi], ob = A.val[gi];
@@ -320,8 +322,8 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass2_kernel(QcDev A)
 // Flags: error_max (2**16), no_buddies (2**14), buddy (2**17), in the reference's order.
 __global__ void __launch_bounds__(256) qc_flag_kernel(QcDev A)
 {
-    const QcSlabDev& S = A.slabs[blockIdx.y];
-    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    const QcSlabDev& S = A.slabs[slab_of_block(A.slabs, A.nslab, (int)blockIdx.x)];
+    const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
     if (li >= S.n) return;
     const int gi = S.ob_off + li;
     int q = A.qc[gi];
@@ -451,7 +453,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     if (ns == 0) return OG_OK;
     cudaStream_t st = ctx->stream;
     std::vector<QcSlabDev> hs(ns);
-    int max_n = 0, ncells_all = 0, max_cells = 0;
+    int max_n = 0, ncells_all = 0, max_cells = 0, nblk_ob = 0;
     std::vector<BinSlab> bslabs(ns);
     int64_t pair_tests = 0, nobs = 0;
     // thresholds depend on the range class only: cache the three
@@ -475,6 +477,8 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         const int cell = std::max(8, (int)ceilf(edge));
         d.ncx = (b.iew + cell - 1) / cell; d.ncy = (b.jns + cell - 1) / cell;
         d.cell_off = ncells_all;
+        d.blk_off = nblk_ob;
+        nblk_ob += (h.n + 255) / 256;
         bslabs[s] = BinSlab{h.n, h.ob_off, cell, d.ncx, d.ncy, d.cell_off};
         ncells_all += d.ncx * d.ncy;
         max_cells = std::max(max_cells, d.ncx * d.ncy);
@@ -487,7 +491,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     QcSlabDev* d_slabs = nullptr;
     OG_TRY(ctx->reserve_t("qc.slabs", (size_t)ns, &d_slabs));
     QcDev A{};
-    A.slabs = d_slabs; A.iew = b.iew; A.jns = b.jns; A.buddy_weight = b.buddy_weight;
+    A.slabs = d_slabs; A.nslab = ns; A.iew = b.iew; A.jns = b.jns; A.buddy_weight = b.buddy_weight;
     A.do_error_max = b.do_error_max; A.do_buddy = b.do_buddy;
     A.xob = b.xob; A.yob = b.yob; A.val = b.val; A.elev = b.elev; A.local_time = b.local_time;
     A.qc = b.qc;
@@ -510,8 +514,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     A.d_err_buddy = b.err_buddy; A.d_difmax = b.difmax; A.d_bnf = b.buddy_num_final;
 
     OG_TRY(ctx->put_small(d_slabs, hs.data(), sizeof(QcSlabDev) * ns));
-    dim3 g_ob((max_n + 255) / 256, ns);
-    qc_prep_kernel<<<g_ob, 256, 0, st>>>(A);
+    qc_prep_kernel<<<nblk_ob, 256, 0, st>>>(A);
     ctx->count_launch();
     if (b.do_buddy) {
         // targets of a cell: the obs sitting in it (any order); candidates: the obs within reach
@@ -553,7 +556,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         ctx->stats.buddy_pair_tests += pair_tests;
         ctx->stats.buddy_obs += nobs;
     }
-    qc_flag_kernel<<<g_ob, 256, 0, st>>>(A);
+    qc_flag_kernel<<<nblk_ob, 256, 0, st>>>(A);
     ctx->count_launch();
     OG_CUDA(cudaGetLastError());
     return OG_OK;

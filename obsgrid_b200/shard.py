@@ -24,8 +24,18 @@ FIELDS3 = ("t", "u", "v", "rh")
 FLAGS3 = ("qc_u", "qc_v", "qc_t", "qc_rh")
 
 
+# Relative cost of the two kernels that dominate a level, calibrated on B200 (profiles/exp_levels.py,
+# bench breakdowns of cfg2 / cfg3): a Cressman (grid point, ob) update costs ~4.3e-9 ms, a buddy
+# pair examined by the binned kernel ~5e-10 ms, and every level carries ~0.05 ms of fixed work
+# (transposes, selection, list building, launches).
+PAIR_PER_UPDATE = 0.12
+LEVEL_FIXED_UPDATES = 1.2e7
+
+
 def level_costs(case) -> np.ndarray:
-    """Relative cost of each level: obs at the level x (Cressman reach + buddy reach)."""
+    """Relative cost of each level, in units of one Cressman update: obs x Cressman reach, plus
+    the pairs the binned buddy check examines (candidates within a 3 x 3 block of range-wide
+    cells), plus the per-level fixed work."""
     radii = [int(r) for r in case.oa_params.radius_influence if r >= 0]
     r2 = float(sum(r * r for r in radii)) or 1.0
     cost = np.zeros(case.kbu, np.float64)
@@ -40,20 +50,17 @@ def level_costs(case) -> np.ndarray:
         rng_km = 650.0 if p <= 201.0 else (300.0 if p <= 1000.1 else 500.0)
         rc = rng_km / float(case.dx_km)
         per_var = n / 4.0
-        cost[k] = n * np.pi * r2 + 4.0 * per_var * per_var * min(9.0 * rc * rc / area, 1.0)
-    return cost + 1.0
+        pairs = 4.0 * per_var * per_var * min(9.0 * rc * rc / area, 1.0)
+        cost[k] = n * np.pi * r2 + PAIR_PER_UPDATE * pairs + LEVEL_FIXED_UPDATES
+    return cost
 
 
-def plan_levels(costs: Sequence[float], world: int) -> list[tuple[int, int]]:
-    """Contiguous level ranges, one per rank, minimising the heaviest range (linear-partition
-    DP).  Ranks beyond the number of levels get empty ranges."""
-    c = np.asarray(costs, np.float64)
+def _bottleneck(c: np.ndarray, parts: int) -> float:
+    """Smallest possible heaviest-part cost when c is cut into `parts` contiguous parts."""
     K = len(c)
-    world = max(int(world), 1)
-    parts = min(world, K)
+    parts = min(parts, K)
     pre = np.concatenate([[0.0], np.cumsum(c)])
     best = np.full((parts + 1, K + 1), np.inf)
-    cut = np.zeros((parts + 1, K + 1), np.int64)
     best[0, 0] = 0.0
     for p in range(1, parts + 1):
         for k in range(p, K + 1):
@@ -61,14 +68,32 @@ def plan_levels(costs: Sequence[float], world: int) -> list[tuple[int, int]]:
                 v = max(best[p - 1, j], pre[k] - pre[j])
                 if v < best[p, k]:
                     best[p, k] = v
-                    cut[p, k] = j
-    bounds = [K]
-    k = K
-    for p in range(parts, 0, -1):
-        k = int(cut[p, k])
-        bounds.append(k)
-    bounds = bounds[::-1]
-    ranges = [(bounds[i], bounds[i + 1]) for i in range(parts)]
+    return float(best[parts, K])
+
+
+def plan_levels(costs: Sequence[float], world: int) -> list[tuple[int, int]]:
+    """Contiguous level ranges, one per rank.  The heaviest range is minimal (linear-partition DP),
+    and so is, in turn, the heaviest of the ranges after the first, and so on: a rank that cannot
+    be helped (the surface level on its own) does not leave the others lumped together.  Ranks
+    beyond the number of levels get empty ranges."""
+    c = np.asarray(costs, np.float64)
+    K = len(c)
+    world = max(int(world), 1)
+    parts = min(world, K)
+    ranges, start = [], 0
+    for r in range(parts):
+        left = parts - r
+        if left == 1:
+            end = K
+        else:
+            limit = _bottleneck(c[start:], left) * (1.0 + 1e-12)
+            end, acc = start, 0.0
+            # as many levels as fit under the optimal bottleneck, leaving one per remaining rank
+            while end < K - (left - 1) and (end == start or acc + c[end] <= limit):
+                acc += c[end]
+                end += 1
+        ranges.append((start, end))
+        start = end
     ranges += [(K, K)] * (world - parts)
     return ranges
 
