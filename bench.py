@@ -248,12 +248,17 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     K = case.kbu
     KR = 1 if case.oa_params.surface_only else K      # FDDA surface analyses touch level 0 only
     K0 = 0
+    slab_plan = None
     if args.scaling == "strong" and world > 1:
         # one time period, its levels cut into contiguous ranges balanced on a cost estimate
         # (obsgrid_b200/shard.py); no exchange between ranks, the host writer gathers afterwards
         from obsgrid_b200 import shard
         rng_ = shard.plan_levels(shard.level_costs(case)[:KR], world)
         K0, KR = rng_[rank]
+        if args.shard == "slabs" and not case.oa_params.surface_only:
+            # resident path: the surface level's variable slabs are dealt out on their own
+            # (shard.plan_slabs); the flags of the surface level are combined between the phases
+            slab_plan = shard.plan_slabs(case, world)[rank]
 
     # ---- resident copy: pristine inputs + working set in HBM ---------------------------------
     pristine, work = {}, {}
@@ -271,9 +276,43 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             work[nm].copy_(pristine[nm])
         torch.cuda.synchronize(dev)
 
+    def resident_qc():
+        if slab_plan is None:
+            ctx.dev_proc_qc(ddesc, case.qc_params, K0, KR, True)
+            return
+        qp = case.qc_params
+        if slab_plan["sfc_mask"]:
+            qp.var_mask = slab_plan["sfc_mask"]
+            ctx.dev_proc_qc(ddesc, qp, 0, 1, False)
+            qp.var_mask = 0
+        if slab_plan["k1"] > slab_plan["k0"]:
+            ctx.dev_proc_qc(ddesc, qp, slab_plan["k0"], slab_plan["k1"], True)
+        # exchange: every surface flag row was updated by exactly one rank and flags only gain
+        # bits -> element-wise MAX over the ranks (NCCL, on the library's stream), then the
+        # consistency pass of the surface level (qc0_module.F90:371-404) on the merged rows
+        with torch.cuda.stream(lib_stream):
+            rows = torch.stack([work["qc_u"][0], work["qc_v"][0], work["qc_t"][0], work["qc_rh"][0], work["qc_slp"]])
+            dist.all_reduce(rows, op=dist.ReduceOp.MAX)
+            for i_, nm_ in enumerate(("qc_u", "qc_v", "qc_t", "qc_rh")):
+                work[nm_][0].copy_(rows[i_])
+            work["qc_slp"].copy_(rows[4])
+        ctx.dev_qc_consistency(ddesc, 0, 1)
+
+    def resident_oa():
+        if slab_plan is None:
+            ctx.dev_proc_oa(ddesc, case.oa_params, K0, KR)
+            return
+        op = case.oa_params
+        if slab_plan["sfc_mask"] & 0x1f:
+            op.var_mask = slab_plan["sfc_mask"] & 0x1f
+            ctx.dev_proc_oa(ddesc, op, 0, 1)
+            op.var_mask = 0
+        if slab_plan["k1"] > slab_plan["k0"]:
+            ctx.dev_proc_oa(ddesc, op, slab_plan["k0"], slab_plan["k1"])
+
     def step_resident():
-        ctx.dev_proc_qc(ddesc, case.qc_params, K0, KR, True)
-        ctx.dev_proc_oa(ddesc, case.oa_params, K0, KR)
+        resident_qc()
+        resident_oa()
 
     # ---- e2e: pinned host arrays through the host-pointer C ABI -----------------------------
     host0 = {nm: getattr(case, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
@@ -309,8 +348,17 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     upd_ell, upd_ban = st["cressman_updates_ellipse"], st["cressman_updates_banana"]
     buddy_obs, pair_tests = st["buddy_obs"], st["buddy_pair_tests"]
     restore_host(); step_e2e()
-    same = all(np.array_equal(work[nm].cpu().numpy(), getattr(hcase, nm)) for nm in FIELD_NAMES + FLAG_NAMES)
-    assert same, "resident and host-pointer paths disagree"
+    ref_out = {nm: getattr(hcase, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
+    if slab_plan is None:
+        same = all(np.array_equal(work[nm].cpu().numpy(), ref_out[nm]) for nm in FIELD_NAMES + FLAG_NAMES)
+        assert same, "resident and host-pointer paths disagree"
+    else:
+        # the resident path analysed this rank's (level, variable) slabs, the e2e path its level range:
+        # compare where both did the work -- the upper levels the two plans share
+        ka, kb = max(K0, slab_plan["k0"]), min(KR, slab_plan["k1"])
+        same = all(np.array_equal(work[nm].cpu().numpy()[ka:kb], ref_out[nm][ka:kb])
+                   for nm in ("t", "u", "v", "rh", "qc_u", "qc_v", "qc_t", "qc_rh"))
+        assert same, "slab-sharded resident path and level-sharded host-pointer path disagree"
 
     # ---- warm-up -------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -328,9 +376,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     for i in range(args.steps):
         restore_resident()
         ev[i][0].record(lib_stream)
-        ctx.dev_proc_qc(ddesc, case.qc_params, K0, KR, True)
+        resident_qc()
         ev[i][1].record(lib_stream)
-        ctx.dev_proc_oa(ddesc, case.oa_params, K0, KR)
+        resident_oa()
         ev[i][2].record(lib_stream)
     ctx.sync()
     barrier()
@@ -374,9 +422,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     e2e_blocking_ms = float(np.mean(blocking[1:]))
     restore_host()
     run_e2e(NS + 1)          # touches every slot: no allocation is left for the timed steps
-    same = all(np.array_equal(work[nm].cpu().numpy(), getattr(ocase[s_], nm))
+    same = all(np.array_equal(ref_out[nm], getattr(ocase[s_], nm))
                for nm in FIELD_NAMES + FLAG_NAMES for s_ in range(NS))
-    assert same, "resident and asynchronous host-pointer paths disagree"
+    assert same, "blocking and asynchronous host-pointer paths disagree"
     ctx.reset_stats()
     barrier()
     t0 = time.perf_counter()
@@ -408,7 +456,10 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                       ALGO_FLOP_BANANA * upd_ban)
         flops_per_launch = algo_flops / max(n_scan_launch, 1)
         achieved_tf = flops_per_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
-        n_oa_slabs = (5 if K0 == 0 else 0) + 4 * (KR - max(K0, 1))
+        if slab_plan is None:
+            n_oa_slabs = (5 if K0 == 0 else 0) + 4 * (KR - max(K0, 1))
+        else:
+            n_oa_slabs = bin(slab_plan["sfc_mask"] & 0x1f).count("1") + 4 * (slab_plan["k1"] - slab_plan["k0"])
         hbm_bytes_launch = n_oa_slabs * 8.0 * case.iew * case.jns
         roofline = {
             "kernel": "cressman_scan_kernel", "bound": "fp32",
@@ -443,7 +494,10 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                        "scan_arithmetic": ctx.arithmetic(),
                        "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
                              "pristine copy before every step",
-                       "parallelism": (f"1 analysis time, levels sharded over {world} ranks" if args.scaling == "strong"
+                       "parallelism": ((f"1 analysis time, (level, variable) slabs sharded over {world} ranks, surface "
+                                        f"flags combined with one NCCL all-reduce between QC and OA; e2e shards whole levels"
+                                        if slab_plan is not None else
+                                        f"1 analysis time, levels sharded over {world} ranks") if args.scaling == "strong"
                                        else f"{world} x independent analysis time"),
                        "cpu_affinity": affinity},
             "e2e": {"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -484,6 +538,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one analysis time per rank; strong: one time, levels sharded over the ranks")
+    ap.add_argument("--shard", default="slabs", choices=["slabs", "levels"],
+                    help="strong scaling: deal out the surface level's variable slabs (slabs) or whole levels only")
     ap.add_argument("--pipeline-groups", type=int, default=0,
                     help="level groups of the pipelined e2e call (0: library default)")
     ap.add_argument("--ref-levels", type=int, default=64,

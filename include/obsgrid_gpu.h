@@ -295,6 +295,13 @@ typedef struct og_time_desc {
 
 /* proc_qc level x variable loop + qc_consistency.  Flags are updated in place. */
 int og_qc_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p);
+/* qc_consistency (qc0_module.F90:371-404) of the levels [k_begin,k_end) on its own: u/v flags
+ * merged, T's error_max / buddy bits copied to RH.  og_qc_time* run it themselves when
+ * run_consistency != 0; the stand-alone form is the step between the QC and the OA phase when
+ * the variables of a level were checked on different GPUs (var_mask; obsgrid_b200/shard.py).
+ * Host arrays (blocking) and device-resident form. */
+int og_qc_consistency(og_ctx* ctx, const og_time_desc* d, int k_begin, int k_end);
+int og_dev_qc_consistency(og_ctx* ctx, const og_time_desc* d, int k_begin, int k_end);
 /* proc_qc of a surface-FDDA time (proc_qc.F90:243-420): og_qc_time plus the observation
  * density.  tobbox (jns,iew; in/out) receives +1 per surface ob of every checked variable within
  * 250 km (ob_density at kp = 1, :349-351), is divided by 5 and zeroed below 1 (:416-417); odis

@@ -242,6 +242,14 @@ class Context:
               "og_qc_time_fdda")
         return tb, od
 
+    def qc_consistency(self, case, k_begin=0, k_end=None):
+        d = case.desc()
+        check(self._lib.og_qc_consistency(self._h, C.byref(d), k_begin,
+                                          case.kbu if k_end is None else k_end), "og_qc_consistency")
+
+    def dev_qc_consistency(self, desc, k_begin, k_end):
+        check(self._lib.og_dev_qc_consistency(self._h, C.byref(desc), k_begin, k_end), "og_dev_qc_consistency")
+
     def proc_oa(self, case, k_begin=0, k_end=None):
         d = case.desc()
         k_end = case.kbu if k_end is None else k_end

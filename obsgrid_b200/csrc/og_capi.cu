@@ -1056,6 +1056,40 @@ extern "C" int og_dev_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_para
     return qc_time_core(c, view_of(d), p, k0, k1, run_consistency);
 }
 
+// qc_consistency (qc0_module.F90:371-404) on its own: the step between the QC and OA phases when
+// the variables of a level were checked by different ranks (obsgrid_b200/shard.py).
+extern "C" int og_dev_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k1)
+{
+    REQUIRE(c, "null context");
+    OG_TRY(check_desc(d, k0, k1, false));
+    if (k1 == k0 || d->nrep == 0) return OG_OK;
+    const size_t n = (size_t)(k1 - k0) * d->nrep, off = (size_t)k0 * d->nrep;
+    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(d->qc_u + off, d->qc_v + off, d->qc_t + off, d->qc_rh + off, n);
+    c->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+extern "C" int og_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k1)
+{
+    REQUIRE(c, "null context");
+    OG_TRY(check_desc(d, k0, k1, false));
+    if (k1 == k0 || d->nrep == 0) return OG_OK;
+    const size_t n = (size_t)(k1 - k0) * d->nrep, off = (size_t)k0 * d->nrep;
+    int* dev[4];
+    int* host[4] = {d->qc_u + off, d->qc_v + off, d->qc_t + off, d->qc_rh + off};
+    const char* names[4] = {"cons.u", "cons.v", "cons.t", "cons.rh"};
+    for (int i = 0; i < 4; ++i) OG_TRY(upload(c, names[i], host[i], n, &dev[i]));
+    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(dev[0], dev[1], dev[2], dev[3], n);
+    c->count_launch();
+    OG_CUDA(cudaGetLastError());
+    OG_TRY(download(c, host[0], dev[0], n));
+    OG_TRY(download(c, host[1], dev[1], n));
+    OG_TRY(download(c, host[3], dev[3], n));
+    OG_CUDA(cudaStreamSynchronize(c->stream));
+    return OG_OK;
+}
+
 extern "C" int og_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* p, int k0, int k1)
 {
     REQUIRE(c && p, "null argument");

@@ -154,3 +154,119 @@ def run_time_sharded(case, rank: int, world: int, proc_qc: Callable, proc_oa: Ca
                     dist.recv(t, src=owner)
                     a[...] = t.cpu().numpy()
     return ranges
+
+
+# ---- level x variable sharding --------------------------------------------------------------
+# The surface pseudo-level carries every report and is the one level worth more than a rank's
+# fair share (a third of cfg3, a quarter of cfg2), so its five variable slabs (UU VV TT RH PMSL;
+# DEWPOINT rides with RH, whose flag row it shares) are dealt out on their own; the upper levels
+# stay whole and contiguous.  The price is one exchange step: qc_consistency couples the flags of
+# U and V and of T and RH (qc0_module.F90:371-404), so between the QC and the OA phase the ranks
+# combine the surface flag rows (each row was updated by exactly one rank and flags only gain
+# bits: an element-wise MAX) and run the consistency pass on the merged rows.
+SFC_VARS = (("u", 1 << 0), ("v", 1 << 1), ("t", 1 << 2), ("rh", (1 << 3) | (1 << 6)), ("slp", 1 << 4))
+ANISO_COST = 1.6          # a UU / VV / RH update against a TT / PMSL one (measured, profiles/exp_levels.py)
+SFC_FLAGS = ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp")
+
+
+def surface_unit_costs(case) -> list[float]:
+    """Cost of the surface slab of each variable, same unit as level_costs."""
+    radii = [int(r) for r in case.oa_params.radius_influence if r >= 0]
+    r2 = float(sum(r * r for r in radii)) or 1.0
+    area = float(case.iew * case.jns)
+    rc = 500.0 / float(case.dx_km)
+    out = []
+    for nm, _ in SFC_VARS:
+        ob = case.ob_slp if nm == "slp" else getattr(case, "ob_" + nm)[0]
+        n = float(np.count_nonzero(np.abs(ob - OG_MISSING_R) > 1.0))
+        pairs = n * n * min(9.0 * rc * rc / area, 1.0) * (2.0 if nm == "rh" else 1.0)
+        shape = ANISO_COST if nm in ("u", "v", "rh") else 1.0
+        out.append(n * np.pi * r2 * shape + PAIR_PER_UPDATE * pairs + LEVEL_FIXED_UPDATES / 5.0)
+    return out
+
+
+def plan_slabs(case, world: int) -> list[dict]:
+    """One entry per rank: {'sfc_mask': variable bits of the surface slabs it owns (0: none),
+    'k0', 'k1': its contiguous range of upper levels (k0 >= 1)}."""
+    world = max(int(world), 1)
+    K = case.kbu
+    if world == 1:
+        return [{"sfc_mask": sum(b for _, b in SFC_VARS), "k0": 1, "k1": K}]
+    up = level_costs(case)[1:]
+    loads = [0.0] * world
+    masks = [0] * world
+    units = sorted(zip(surface_unit_costs(case), (b for _, b in SFC_VARS)), reverse=True)
+    for cost, bits in units:                        # longest processing time first
+        r = int(np.argmin(loads))
+        loads[r] += cost
+        masks[r] |= bits
+    # upper levels: contiguous runs, lightest rank first, each filled up to the mean of what is left
+    order = sorted(range(world), key=lambda r: loads[r])
+    ranges = {r: (K, K) for r in range(world)}
+    k = 1
+    for pos, r in enumerate(order):
+        rest = order[pos:]
+        remaining = float(up[k - 1:].sum())
+        target = (remaining + sum(loads[q] for q in rest)) / len(rest)
+        k0 = k
+        if pos == world - 1:
+            k = K
+        else:
+            while k < K and loads[r] + up[k - 1] <= target * 1.02:
+                loads[r] += up[k - 1]
+                k += 1
+        ranges[r] = (k0, k)
+    return [{"sfc_mask": masks[r], "k0": ranges[r][0], "k1": ranges[r][1]} for r in range(world)]
+
+
+def run_time_sharded_slabs(case, rank: int, world: int, proc_qc: Callable, proc_oa: Callable,
+                           consistency: Callable, dist=None, dst: int = 0, device=None, plan=None):
+    """QC then OA of one time period sharded by (level, variable).
+
+    proc_qc(case, k0, k1, run_consistency, var_mask), proc_oa(case, k0, k1, var_mask) and
+    consistency(case, k0, k1) update `case` in place.  Phases: QC of the rank's surface slabs
+    (no consistency) and of its upper levels (with); exchange of the surface flag rows (MAX);
+    consistency of the surface level; OA of the same slabs; gather to `dst`.
+    """
+    import torch
+
+    plan = plan_slabs(case, world) if plan is None else plan
+    me = plan[rank]
+    if me["sfc_mask"]:
+        proc_qc(case, 0, 1, False, me["sfc_mask"])
+    if me["k1"] > me["k0"]:
+        proc_qc(case, me["k0"], me["k1"], True, 0)
+    if world > 1:
+        assert dist is not None, "world > 1 needs torch.distributed"
+        rows = np.stack([case.qc_u[0], case.qc_v[0], case.qc_t[0], case.qc_rh[0], case.qc_slp])
+        t = torch.from_numpy(rows)
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rows = t.cpu().numpy()
+        case.qc_u[0], case.qc_v[0], case.qc_t[0], case.qc_rh[0] = rows[0], rows[1], rows[2], rows[3]
+        case.qc_slp[...] = rows[4]
+    consistency(case, 0, 1)
+    if me["sfc_mask"]:
+        proc_oa(case, 0, 1, me["sfc_mask"] & 0x1f)
+    if me["k1"] > me["k0"]:
+        proc_oa(case, me["k0"], me["k1"], 0)
+    if world > 1:
+        ranges = [(p["k0"], p["k1"]) for p in plan]
+        for nm in FIELDS3 + FLAGS3:
+            _gather_rows(dist, getattr(case, nm), ranges, rank, dst, device)
+        # surface fields: each comes from the rank that analysed it
+        for nm, bits in SFC_VARS:
+            owner = next(r for r, p in enumerate(plan) if p["sfc_mask"] & bits & 0x1f)
+            if owner == dst:
+                continue
+            a = case.slp if nm == "slp" else getattr(case, nm)[0]
+            t = torch.from_numpy(np.ascontiguousarray(a))
+            if device is not None:
+                t = t.to(device)
+            if rank == owner:
+                dist.send(t, dst=dst)
+            elif rank == dst:
+                dist.recv(t, src=owner)
+                a[...] = t.cpu().numpy()
+    return plan

@@ -864,6 +864,11 @@ int ogo_qc_time_fdda(const og_time_desc* d, const og_qc_params* p, float* tobbox
     return OG_OK;
 }
 
+void ogo_qc_consistency(const og_time_desc* d, int k_begin, int k_end)
+{
+    qc_consistency(d, k_begin, k_end);
+}
+
 int ogo_qc_time(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
                 int run_consistency)
 {

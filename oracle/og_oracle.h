@@ -88,6 +88,8 @@ float ogo_dewpoint(float t, float rh);
 int ogo_qc_time(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
                 int run_consistency);
 int ogo_oa_time(const og_time_desc* d, const og_oa_params* p, int k_begin, int k_end);
+/* qc_consistency (qc0_module.F90:371-404) of the levels [k_begin,k_end) on its own. */
+void ogo_qc_consistency(const og_time_desc* d, int k_begin, int k_end);
 /* proc_qc of a surface-FDDA time: ogo_qc_time over every level + ob_density at kp = 1,
  * tobbox / 5 thresholded at 1, obs_distance (proc_qc.F90:349-351, :412-420). */
 int ogo_qc_time_fdda(const og_time_desc* d, const og_qc_params* p, float* tobbox, float* odis);

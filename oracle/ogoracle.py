@@ -276,6 +276,14 @@ def qc_time_fdda(case, tobbox):
     return tb, od
 
 
+def qc_consistency(case, k_begin=0, k_end=None):
+    d = case.desc()
+    l = lib()
+    l.ogo_qc_consistency.restype = None
+    l.ogo_qc_consistency.argtypes = [C.POINTER(OgTimeDesc), C.c_int, C.c_int]
+    l.ogo_qc_consistency(C.byref(d), k_begin, case.kbu if k_end is None else k_end)
+
+
 def oa_time(case, k_begin=0, k_end=None, threads=1):
     d = case.desc()
     k_end = case.kbu if k_end is None else k_end

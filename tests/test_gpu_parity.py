@@ -614,3 +614,53 @@ def test_contracted_time_small(contracted, oracle):
 def test_arithmetic_mode_is_validated(ctx):
     from obsgrid_b200._capi import lib
     assert lib().og_set_arithmetic(ctx._h, 7) == -2 and ctx.arithmetic() == "exact"
+
+
+def test_time_slab_sharding_is_exact(ctx):
+    """Level x variable sharding (obsgrid_b200/shard.py, north star: 'partitioned by pressure level x
+    variable x analysis time'): the per-rank programs of run_time_sharded_slabs, run one after the
+    other on this GPU and merged as the collectives would (MAX of the surface flag rows, gather),
+    equal the unsharded time bit for bit."""
+    from obsgrid_b200 import shard
+    base = synth.small_case(iew=50, jns=44, kbu=7, n_sfc=300, n_snd=100, radii=(5, 3))
+    full = base.copy()
+    ctx.proc_qc(full); ctx.proc_oa(full)
+
+    def qc(c, k0, k1, cons, mask):
+        c.qc_params.var_mask = mask; ctx.proc_qc(c, k0, k1, cons); c.qc_params.var_mask = 0
+
+    def oa(c, k0, k1, mask):
+        c.oa_params.var_mask = mask; ctx.proc_oa(c, k0, k1); c.oa_params.var_mask = 0
+
+    for world in (2, 4):
+        plan = shard.plan_slabs(base, world)
+        cs = [base.copy() for _ in range(world)]
+        for c, p in zip(cs, plan):
+            if p["sfc_mask"]:
+                qc(c, 0, 1, False, p["sfc_mask"])
+            if p["k1"] > p["k0"]:
+                qc(c, p["k0"], p["k1"], True, 0)
+        rows = [np.max([c.qc_slp if nm == "qc_slp" else getattr(c, nm)[0] for c in cs], axis=0)
+                for nm in shard.SFC_FLAGS]
+        out = base.copy()
+        for c, p in zip(cs, plan):
+            c.qc_u[0], c.qc_v[0], c.qc_t[0], c.qc_rh[0] = rows[0], rows[1], rows[2], rows[3]
+            c.qc_slp[...] = rows[4]
+            ctx.qc_consistency(c, 0, 1)
+            if p["sfc_mask"]:
+                oa(c, 0, 1, p["sfc_mask"] & 0x1f)
+            if p["k1"] > p["k0"]:
+                oa(c, p["k0"], p["k1"], 0)
+            for nm in ("t", "u", "v", "rh", "qc_u", "qc_v", "qc_t", "qc_rh"):
+                getattr(out, nm)[p["k0"]:p["k1"]] = getattr(c, nm)[p["k0"]:p["k1"]]
+            for nm, bits in shard.SFC_VARS:
+                if p["sfc_mask"] & bits & 0x1f:
+                    if nm == "slp":
+                        out.slp[...] = c.slp
+                    else:
+                        getattr(out, nm)[0] = getattr(c, nm)[0]
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh"):
+            getattr(out, nm)[0] = getattr(cs[0], nm)[0]
+        out.qc_slp[...] = cs[0].qc_slp
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
+            np.testing.assert_array_equal(getattr(full, nm), getattr(out, nm), err_msg=f"{nm} world {world}")

@@ -78,3 +78,109 @@ def test_two_ranks_over_gloo_match_one_process(tmp_path, oracle):
     oracle.oa_time(ref)
     for n in FIELDS:
         assert np.array_equal(got[n], getattr(ref, n)), n
+
+
+# ---- level x variable sharding ------------------------------------------------------------------
+def _oracle_callables():
+    from oracle import ogoracle
+
+    def qc(c, k0, k1, cons, mask):
+        c.qc_params.var_mask = mask
+        ogoracle.qc_time(c, k0, k1, run_consistency=cons)
+        c.qc_params.var_mask = 0
+
+    def oa(c, k0, k1, mask):
+        c.oa_params.var_mask = mask
+        ogoracle.oa_time(c, k0, k1)
+        c.oa_params.var_mask = 0
+
+    return qc, oa, ogoracle.qc_consistency
+
+
+def test_plan_slabs_covers_every_slab_once():
+    case = synth.small_case(iew=40, jns=36, kbu=9, n_sfc=400, n_snd=60, seed=3)
+    allbits = sum(b for _, b in shard.SFC_VARS)
+    for world in (1, 2, 3, 4, 8, 16):
+        plan = shard.plan_slabs(case, world)
+        assert len(plan) == world
+        seen = 0
+        for p in plan:
+            assert seen & p["sfc_mask"] == 0
+            seen |= p["sfc_mask"]
+            assert bool(p["sfc_mask"] & (1 << 3)) == bool(p["sfc_mask"] & (1 << 6))   # DEWPOINT rides with RH
+        assert seen == allbits
+        ks = sorted((p["k0"], p["k1"]) for p in plan if p["k1"] > p["k0"])
+        assert ks[0][0] == 1 and ks[-1][1] == case.kbu and all(a[1] == b[0] for a, b in zip(ks, ks[1:]))
+        if world >= 2:      # the surface is shared out: no rank holds all five of its slabs
+            assert all(p["sfc_mask"] != allbits for p in plan)
+
+
+def test_slab_sharding_sequential_equals_one_process(oracle):
+    """The phases of run_time_sharded_slabs, executed rank after rank in one process on separate
+    copies and merged as the collectives would, reproduce the unsharded time exactly."""
+    base = synth.small_case(iew=40, jns=36, kbu=6, n_sfc=150, n_snd=40, seed=11, radii=(5, 3))
+    ref = base.copy()
+    oracle.qc_time(ref); oracle.oa_time(ref)
+    qc, oa, cons = _oracle_callables()
+    world = 3
+    plan = shard.plan_slabs(base, world)
+    cs = [base.copy() for _ in range(world)]
+    for r, p in enumerate(plan):
+        if p["sfc_mask"]:
+            qc(cs[r], 0, 1, False, p["sfc_mask"])
+        if p["k1"] > p["k0"]:
+            qc(cs[r], p["k0"], p["k1"], True, 0)
+    rows = [np.max([getattr(c, nm)[0] if nm != "qc_slp" else c.qc_slp for c in cs], axis=0) for nm in shard.SFC_FLAGS]
+    out = base.copy()
+    for r, p in enumerate(plan):
+        c = cs[r]
+        c.qc_u[0], c.qc_v[0], c.qc_t[0], c.qc_rh[0] = rows[0], rows[1], rows[2], rows[3]
+        c.qc_slp[...] = rows[4]
+        cons(c, 0, 1)
+        if p["sfc_mask"]:
+            oa(c, 0, 1, p["sfc_mask"] & 0x1f)
+        if p["k1"] > p["k0"]:
+            oa(c, p["k0"], p["k1"], 0)
+        for nm in ("t", "u", "v", "rh", "qc_u", "qc_v", "qc_t", "qc_rh"):
+            getattr(out, nm)[p["k0"]:p["k1"]] = getattr(c, nm)[p["k0"]:p["k1"]]
+        for nm, bits in shard.SFC_VARS:
+            if p["sfc_mask"] & bits & 0x1f:
+                if nm == "slp":
+                    out.slp[...] = c.slp
+                else:
+                    getattr(out, nm)[0] = getattr(c, nm)[0]
+    for i, nm in enumerate(("qc_u", "qc_v", "qc_t", "qc_rh")):
+        getattr(out, nm)[0] = getattr(cs[0], nm)[0]
+    out.qc_slp[...] = cs[0].qc_slp
+    for n in FIELDS:
+        assert np.array_equal(getattr(out, n), getattr(ref, n)), n
+
+
+def _worker_slabs(rank, world, port, tmp):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    case = synth.small_case(iew=40, jns=36, kbu=6, n_sfc=150, n_snd=40, seed=11, radii=(5, 3))
+    qc, oa, cons = _oracle_callables()
+    plan = shard.run_time_sharded_slabs(case, rank, world, qc, oa, cons, dist=dist, dst=0)
+    if rank == 0:
+        np.savez(tmp, masks=np.array([p["sfc_mask"] for p in plan]), **{n: getattr(case, n) for n in FIELDS})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_slab_sharding_over_gloo(tmp_path, oracle):
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "sharded_slabs.npz")
+    mp.spawn(_worker_slabs, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    assert np.all(got["masks"] != 0)                    # both ranks own surface slabs
+    ref = synth.small_case(iew=40, jns=36, kbu=6, n_sfc=150, n_snd=40, seed=11, radii=(5, 3))
+    oracle.qc_time(ref)
+    oracle.oa_time(ref)
+    for n in FIELDS:
+        assert np.array_equal(got[n], getattr(ref, n)), n
