@@ -259,6 +259,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             # resident path: the surface level's variable slabs are dealt out on their own
             # (shard.plan_slabs); the flags of the surface level are combined between the phases
             slab_plan = shard.plan_slabs(case, world)[rank]
+            item_levels = ([0] if slab_plan["sfc_mask"] else []) + list(range(slab_plan["k0"], slab_plan["k1"]))
+            item_masks = ([slab_plan["sfc_mask"]] if slab_plan["sfc_mask"] else []) + [0] * (slab_plan["k1"] - slab_plan["k0"])
 
     # ---- resident copy: pristine inputs + working set in HBM ---------------------------------
     pristine, work = {}, {}
@@ -280,13 +282,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         if slab_plan is None:
             ctx.dev_proc_qc(ddesc, case.qc_params, K0, KR, True)
             return
-        qp = case.qc_params
-        if slab_plan["sfc_mask"]:
-            qp.var_mask = slab_plan["sfc_mask"]
-            ctx.dev_proc_qc(ddesc, qp, 0, 1, False)
-            qp.var_mask = 0
-        if slab_plan["k1"] > slab_plan["k0"]:
-            ctx.dev_proc_qc(ddesc, qp, slab_plan["k0"], slab_plan["k1"], True)
+        # one batch: the rank's surface slabs and its upper levels share every launch
+        ctx.dev_proc_qc_items(ddesc, case.qc_params, item_levels, item_masks, True)
         # exchange: every surface flag row was updated by exactly one rank and flags only gain
         # bits -> element-wise MAX over the ranks (NCCL, on the library's stream), then the
         # consistency pass of the surface level (qc0_module.F90:371-404) on the merged rows
@@ -302,13 +299,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         if slab_plan is None:
             ctx.dev_proc_oa(ddesc, case.oa_params, K0, KR)
             return
-        op = case.oa_params
-        if slab_plan["sfc_mask"] & 0x1f:
-            op.var_mask = slab_plan["sfc_mask"] & 0x1f
-            ctx.dev_proc_oa(ddesc, op, 0, 1)
-            op.var_mask = 0
-        if slab_plan["k1"] > slab_plan["k0"]:
-            ctx.dev_proc_oa(ddesc, op, slab_plan["k0"], slab_plan["k1"])
+        ctx.dev_proc_oa_items(ddesc, case.oa_params, item_levels, [m & 0x1f for m in item_masks])
 
     def step_resident():
         resident_qc()

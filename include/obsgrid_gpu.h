@@ -295,6 +295,15 @@ typedef struct og_time_desc {
 
 /* proc_qc level x variable loop + qc_consistency.  Flags are updated in place. */
 int og_qc_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p);
+/* Device-resident stages over an explicit list of (level, variable mask) items instead of a level
+ * range: levels strictly increasing, var_masks[i] as og_*_params.var_mask (0 / NULL: every
+ * variable).  One batch -- one set of launches -- for "some slabs of the surface level plus a run of
+ * upper levels", the share of a rank under level x variable sharding.  run_consistency applies to
+ * the items that check every variable. */
+int og_dev_qc_time_items(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p,
+                         const int* levels, const int* var_masks, int nitems, int run_consistency);
+int og_dev_oa_time_items(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
+                         const int* levels, const int* var_masks, int nitems);
 /* qc_consistency (qc0_module.F90:371-404) of the levels [k_begin,k_end) on its own: u/v flags
  * merged, T's error_max / buddy bits copied to RH.  og_qc_time* run it themselves when
  * run_consistency != 0; the stand-alone form is the step between the QC and the OA phase when

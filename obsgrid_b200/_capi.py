@@ -117,6 +117,8 @@ SIGNATURES = {
     "og_qc_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams)]),
     "og_qc_time_fdda": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), _vp, _vp]),
     "og_qc_consistency": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.c_int, C.c_int]),
+    "og_dev_qc_time_items": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), _vp, _vp, C.c_int, C.c_int]),
+    "og_dev_oa_time_items": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgOaParams), _vp, _vp, C.c_int]),
     "og_dev_qc_consistency": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.c_int, C.c_int]),
     "og_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgOaParams), C.c_int, C.c_int]),
     "og_qc_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.POINTER(OgOaParams),

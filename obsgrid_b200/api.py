@@ -302,3 +302,15 @@ class Context:
         if rc not in (0, -5):
             check(rc, "og_dev_oa_time")
         return rc
+
+    def dev_proc_qc_items(self, desc, qc_params, levels, masks, run_consistency=True):
+        lv, mk = i32(levels), i32(masks)
+        check(self._lib.og_dev_qc_time_items(self._h, C.byref(desc), C.byref(qc_params), ptr(lv), ptr(mk),
+                                             lv.size, int(run_consistency)), "og_dev_qc_time_items")
+
+    def dev_proc_oa_items(self, desc, oa_params, levels, masks):
+        lv, mk = i32(levels), i32(masks)
+        rc = self._lib.og_dev_oa_time_items(self._h, C.byref(desc), C.byref(oa_params), ptr(lv), ptr(mk), lv.size)
+        if rc not in (0, -5):
+            check(rc, "og_dev_oa_time_items")
+        return rc

@@ -769,10 +769,35 @@ int run_selection(og_ctx* c, const TimeDev& T, std::vector<SelSlab>& sel, bool q
     return OG_OK;
 }
 
-// ---- OA over the levels [k0,k1) of a device-resident time -------------------------------
-int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int k1)
+// A set of levels to process in one batch, each with its own variable mask (0: the mask of the
+// stage parameters).  The contiguous range [k0,k1) is the common case; the (level, variable)
+// sharding of obsgrid_b200/shard.py hands a rank "some surface slabs + a run of upper levels".
+struct LevelItems {
+    std::vector<int> k, mask;
+    int size() const { return (int)k.size(); }
+};
+static LevelItems range_items(int k0, int k1)
 {
-    const int iew = T.iew, jns = T.jns, nlev = k1 - k0;
+    LevelItems L;
+    for (int k = k0; k < k1; ++k) { L.k.push_back(k); L.mask.push_back(0); }
+    return L;
+}
+// f(first_slot, first_level, count) for every maximal run of consecutive levels
+template <class F> static int for_each_run(const LevelItems& L, F f)
+{
+    for (int i = 0; i < L.size();) {
+        int j = i + 1;
+        while (j < L.size() && L.k[j] == L.k[j - 1] + 1) ++j;
+        OG_TRY(f(i, L.k[i], j - i));
+        i = j;
+    }
+    return OG_OK;
+}
+
+// ---- OA over a set of levels of a device-resident time -----------------------------------
+int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, const LevelItems& L)
+{
+    const int iew = T.iew, jns = T.jns, nlev = L.size();
     const size_t per = (size_t)iew * jns;
     if (nlev <= 0) return OG_OK;
     // x-fastest working copies (yx2xy of get_background_for_oa, oa_module.F90:634-676)
@@ -784,13 +809,17 @@ int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int
     OG_TRY(c->reserve_t("oa.w_slp", per, &w_slp));
     OG_TRY(c->reserve_t("oa.b_u", per * nlev, &b_u));
     OG_TRY(c->reserve_t("oa.b_v", per * nlev, &b_v));
-    const size_t lo = per * (size_t)k0;
-    OG_TRY(transpose_levels(c, T.t + lo, w_t, jns, iew, nlev));
-    // u, v twice: the pre-analysis winds of each level feed the banana scheme (proc_oa.F90:376-386)
-    OG_TRY(transpose_levels(c, T.u + lo, w_u, jns, iew, nlev, b_u));
-    OG_TRY(transpose_levels(c, T.v + lo, w_v, jns, iew, nlev, b_v));
-    OG_TRY(transpose_levels(c, T.rh + lo, w_rh, jns, iew, nlev));
-    const bool has_sfc = (k0 == 0);
+    bool has_sfc = false;
+    for (int k : L.k) has_sfc = has_sfc || (k == 0);
+    OG_TRY(for_each_run(L, [&](int slot, int k, int n) -> int {
+        const size_t lo = per * (size_t)k, so = per * (size_t)slot;
+        OG_TRY(transpose_levels(c, T.t + lo, w_t + so, jns, iew, n));
+        // u, v twice: the pre-analysis winds of each level feed the banana scheme (proc_oa.F90:376-386)
+        OG_TRY(transpose_levels(c, T.u + lo, w_u + so, jns, iew, n, b_u + so));
+        OG_TRY(transpose_levels(c, T.v + lo, w_v + so, jns, iew, n, b_v + so));
+        OG_TRY(transpose_levels(c, T.rh + lo, w_rh + so, jns, iew, n));
+        return OG_OK;
+    }));
     if (has_sfc) OG_TRY(transpose_levels(c, T.slp, w_slp, jns, iew, 1));
     if (p->clamp_fg_rh) {
         clamp_fg_rh_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_rh, iew, jns, nlev);
@@ -805,12 +834,14 @@ int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int
     b.use_first_guess = p->use_first_guess; b.scale_rh = p->scale_cressman_rh_decreases;
     b.smooth_type = p->smooth_type; b.given_diff = false; b.clean_rh = true;
     int rc_radius = OG_OK;
-    for (int k = k0; k < k1; ++k) {
-        if (p->surface_only && k > 0) break; // proc_oa.F90:365
-        const size_t row = (size_t)k * T.nrep, lev = per * (size_t)(k - k0);
+    for (int slot = 0; slot < nlev; ++slot) {
+        const int k = L.k[slot];
+        const int vmask = L.mask[slot] ? L.mask[slot] : p->var_mask;
+        if (p->surface_only && k > 0) continue; // proc_oa.F90:365
+        const size_t row = (size_t)k * T.nrep, lev = per * (size_t)slot;
         for (int ivar = 1; ivar <= 5; ++ivar) {
             if (ivar == 5 && k > 0) continue;
-            if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
+            if (vmask && !(vmask & (1 << (ivar - 1)))) continue;
             OaSlabHost s;
             SelSlab q{};
             q.kind = 0; q.qc_max = qc_max;
@@ -840,20 +871,29 @@ int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int
     b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval;
     OG_TRY(oa_run_batch(c, b));
     // put_background_from_oa (oa_module.F90:828-870): back to the (jns,iew,k) layout
-    OG_TRY(transpose_levels(c, w_t, T.t + lo, iew, jns, nlev));
-    OG_TRY(transpose_levels(c, w_u, T.u + lo, iew, jns, nlev));
-    OG_TRY(transpose_levels(c, w_v, T.v + lo, iew, jns, nlev));
-    OG_TRY(transpose_levels(c, w_rh, T.rh + lo, iew, jns, nlev));
+    OG_TRY(for_each_run(L, [&](int slot, int k, int n) -> int {
+        const size_t lo = per * (size_t)k, so = per * (size_t)slot;
+        OG_TRY(transpose_levels(c, w_t + so, T.t + lo, iew, jns, n));
+        OG_TRY(transpose_levels(c, w_u + so, T.u + lo, iew, jns, n));
+        OG_TRY(transpose_levels(c, w_v + so, T.v + lo, iew, jns, n));
+        OG_TRY(transpose_levels(c, w_rh + so, T.rh + lo, iew, jns, n));
+        return OG_OK;
+    }));
     if (has_sfc) OG_TRY(transpose_levels(c, w_slp, T.slp, iew, jns, 1));
     if (rc_radius != OG_OK) set_error("surface scan-1 radius below 4.5 cells (proc_oa.F90:694-703)");
     return rc_radius;
 }
+int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int k1)
+{
+    return oa_time_core(c, T, p, range_items(k0, k1));
+}
 
-// ---- QC over the levels [k0,k1) of a device-resident time --------------------------------
-int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int k1,
+// ---- QC over a set of levels of a device-resident time ------------------------------------
+// run_consistency: qc_consistency on the levels whose every variable is checked here (mask 0).
+int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, const LevelItems& L,
                  int run_consistency)
 {
-    const int iew = T.iew, jns = T.jns, nlev = k1 - k0;
+    const int iew = T.iew, jns = T.jns, nlev = L.size();
     const size_t per = (size_t)iew * jns;
     if (nlev <= 0) return OG_OK;
     float *w_t, *w_u, *w_v, *w_rh, *w_slp, *w_dew;
@@ -862,12 +902,16 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
     OG_TRY(c->reserve_t("qc.w_v", per * nlev, &w_v));
     OG_TRY(c->reserve_t("qc.w_rh", per * nlev, &w_rh));
     OG_TRY(c->reserve_t("qc.w_slp", per, &w_slp));
-    const size_t lo = per * (size_t)k0;
-    OG_TRY(transpose_levels(c, T.t + lo, w_t, jns, iew, nlev));
-    OG_TRY(transpose_levels(c, T.u + lo, w_u, jns, iew, nlev));
-    OG_TRY(transpose_levels(c, T.v + lo, w_v, jns, iew, nlev));
-    OG_TRY(transpose_levels(c, T.rh + lo, w_rh, jns, iew, nlev));
-    const bool has_sfc = (k0 == 0);
+    OG_TRY(for_each_run(L, [&](int slot, int k, int n) -> int {
+        const size_t lo = per * (size_t)k, so = per * (size_t)slot;
+        OG_TRY(transpose_levels(c, T.t + lo, w_t + so, jns, iew, n));
+        OG_TRY(transpose_levels(c, T.u + lo, w_u + so, jns, iew, n));
+        OG_TRY(transpose_levels(c, T.v + lo, w_v + so, jns, iew, n));
+        OG_TRY(transpose_levels(c, T.rh + lo, w_rh + so, jns, iew, n));
+        return OG_OK;
+    }));
+    bool has_sfc = false;
+    for (int k : L.k) has_sfc = has_sfc || (k == 0);
     if (has_sfc) {
         OG_TRY(transpose_levels(c, T.slp, w_slp, jns, iew, 1));
         scale_kernel<<<nblk(per), 256, 0, c->stream>>>(w_slp, w_slp, per, 100.f); // proc_qc.F90:296
@@ -895,14 +939,16 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
         b.do_error_max = p->qc_test_error_max; b.do_buddy = p->qc_test_buddy;
         std::vector<PutSlab> puts;
         std::vector<int> slab_level;
-        for (int k = k0; k < k1; ++k) {
-            const size_t row = (size_t)k * T.nrep, lev = per * (size_t)(k - k0);
+        for (int slot = 0; slot < nlev; ++slot) {
+            const int k = L.k[slot];
+            const int vmask = L.mask[slot] ? L.mask[slot] : p->var_mask;
+            const size_t row = (size_t)k * T.nrep, lev = per * (size_t)slot;
             const float pk = T.pressure[k];
             for (int ivar = 1; ivar <= 7; ++ivar) {
                 if (ivar == 7 && !p->qc_dewpoint) continue;
                 if (ivar == 6) continue;                      // qc_psfc = .FALSE.
                 if (k > 0 && ivar == 5) continue;             // proc_qc.F90:255
-                if (p->var_mask && !(p->var_mask & (1 << (ivar - 1)))) continue;
+                if (vmask && !(vmask & (1 << (ivar - 1)))) continue;
                 QcSlabHost s; SelSlab q{}; PutSlab pt{};
                 q.kind = 0; q.qc_max = 1 << 20;               // proc_qc.F90:329
                 s.var = ivar; s.pressure = pk;
@@ -961,12 +1007,22 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
         OG_TRY(obs_distance_device(c, T.tobbox, T.odis, iew, jns, T.dx_km));
     }
     if (run_consistency && T.nrep > 0) {
-        const size_t n = (size_t)nlev * T.nrep, off = (size_t)k0 * T.nrep;
-        consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(T.qc_u + off, T.qc_v + off, T.qc_t + off, T.qc_rh + off, n);
-        c->count_launch();
+        LevelItems whole;
+        for (int i = 0; i < nlev; ++i)
+            if (L.mask[i] == 0) { whole.k.push_back(L.k[i]); whole.mask.push_back(0); }
+        OG_TRY(for_each_run(whole, [&](int, int k, int nl) -> int {
+            const size_t n = (size_t)nl * T.nrep, off = (size_t)k * T.nrep;
+            consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(T.qc_u + off, T.qc_v + off, T.qc_t + off, T.qc_rh + off, n);
+            c->count_launch();
+            return OG_OK;
+        }));
     }
     OG_CUDA(cudaGetLastError());
     return OG_OK;
+}
+int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int k1, int run_consistency)
+{
+    return qc_time_core(c, T, p, range_items(k0, k1), run_consistency);
 }
 
 int check_desc(const og_time_desc* d, int k0, int k1, bool qc)
@@ -1054,6 +1110,42 @@ extern "C" int og_dev_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_para
     REQUIRE(c && p, "null argument");
     OG_TRY(check_desc(d, k0, k1, true));
     return qc_time_core(c, view_of(d), p, k0, k1, run_consistency);
+}
+
+// (level, variable mask) item lists: one batch over an arbitrary set of slabs of a device-resident
+// time -- what a rank of the level x variable sharding owns (obsgrid_b200/shard.py).
+static int items_of(const og_time_desc* d, const int* levels, const int* var_masks, int n, LevelItems& L)
+{
+    if (n < 0 || (n > 0 && !levels)) { set_error("bad level item list"); return OG_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        if (levels[i] < 0 || levels[i] >= d->kbu || (i > 0 && levels[i] <= levels[i - 1])) {
+            set_error("level items must be strictly increasing levels of the time"); return OG_ERR_INVALID;
+        }
+        const int m = var_masks ? var_masks[i] : 0;
+        if (m < 0 || m > 0x7f) { set_error("bad variable mask %d", m); return OG_ERR_INVALID; }
+        L.k.push_back(levels[i]); L.mask.push_back(m);
+    }
+    return OG_OK;
+}
+
+extern "C" int og_dev_qc_time_items(og_ctx* c, const og_time_desc* d, const og_qc_params* p,
+                                    const int* levels, const int* var_masks, int nitems, int run_consistency)
+{
+    REQUIRE(c && p, "null argument");
+    OG_TRY(check_desc(d, 0, d ? d->kbu : 0, true));
+    LevelItems L;
+    OG_TRY(items_of(d, levels, var_masks, nitems, L));
+    return qc_time_core(c, view_of(d), p, L, run_consistency);
+}
+
+extern "C" int og_dev_oa_time_items(og_ctx* c, const og_time_desc* d, const og_oa_params* p,
+                                    const int* levels, const int* var_masks, int nitems)
+{
+    REQUIRE(c && p, "null argument");
+    OG_TRY(check_desc(d, 0, d ? d->kbu : 0, false));
+    LevelItems L;
+    OG_TRY(items_of(d, levels, var_masks, nitems, L));
+    return oa_time_core(c, view_of(d), p, L);
 }
 
 // qc_consistency (qc0_module.F90:371-404) on its own: the step between the QC and OA phases when

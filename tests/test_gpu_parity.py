@@ -664,3 +664,37 @@ def test_time_slab_sharding_is_exact(ctx):
         out.qc_slp[...] = cs[0].qc_slp
         for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
             np.testing.assert_array_equal(getattr(full, nm), getattr(out, nm), err_msg=f"{nm} world {world}")
+
+
+def test_dev_item_lists_equal_the_range_calls(ctx):
+    """og_dev_qc_time_items / og_dev_oa_time_items (one batch over "surface slabs + a run of upper
+    levels") == the corresponding range calls with var_mask, bit for bit."""
+    import torch
+    base = synth.small_case(iew=50, jns=44, kbu=7, n_sfc=300, n_snd=100, radii=(5, 3))
+    sfc_mask = (1 << 0) | (1 << 3) | (1 << 6)            # UU, RH (+ DEWPOINT) of the surface level
+    ref = base.copy()
+    ref.qc_params.var_mask = sfc_mask; ctx.proc_qc(ref, 0, 1, False); ref.qc_params.var_mask = 0
+    ctx.proc_qc(ref, 3, 6, True)
+    ctx.qc_consistency(ref, 0, 1)
+    ref.oa_params.var_mask = sfc_mask & 0x1f; ctx.proc_oa(ref, 0, 1); ref.oa_params.var_mask = 0
+    ctx.proc_oa(ref, 3, 6)
+
+    dev = torch.device("cuda", 0)
+    names = ("t", "u", "v", "rh", "slp", "qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp",
+             "xob", "yob", "lon", "elev", "ob_u", "ob_v", "ob_t", "ob_rh", "ob_slp")
+    wk = {nm: torch.from_numpy(getattr(base, nm).copy()).to(dev) for nm in names}
+    d = base.desc()
+    for nm in names:
+        setattr(d, nm, wk[nm].data_ptr())
+    levels, masks = [0, 3, 4, 5], [sfc_mask, 0, 0, 0]
+    ctx.dev_proc_qc_items(d, base.qc_params, levels, masks, True)
+    ctx.dev_qc_consistency(d, 0, 1)
+    ctx.dev_proc_oa_items(d, base.oa_params, levels, [m & 0x1f for m in masks])
+    ctx.sync()
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
+        np.testing.assert_array_equal(wk[nm].cpu().numpy(), getattr(ref, nm), err_msg=nm)
+    assert np.any(ref.u[0] != base.u[0]) and np.array_equal(ref.v[0], base.v[0]) and np.array_equal(ref.t[1], base.t[1])
+    # malformed lists are reported, not executed
+    from obsgrid_b200._capi import OgError
+    with pytest.raises(OgError):
+        ctx.dev_proc_qc_items(d, base.qc_params, [3, 2], [0, 0])
