@@ -114,5 +114,46 @@ def main():
         print(f.name, f.stat().st_size)
 
 
+def epilogue():
+    """6. the rows widened in SURVEY 8f ranks 2-4: surface-FDDA QC with density / distance,
+    temporal_interp, mixing_ratio + sfcprs, wind increments onto the C grid, surface PRES.
+    Own generator: adding it leaves files 1-5 untouched (python make_golden.py --epilogue)."""
+    rng = np.random.default_rng(20261020)
+    kbu, iew, jns = 4, 30, 26
+    mk = lambda lo, hi: rng.uniform(lo, hi, (kbu, iew, jns)).astype(np.float32)
+    u, uA, uC, v, vA, vC = (mk(-30, 30) for _ in range(6))
+    gu, gv = O.wind_increment_to_c_grid(u, uA, uC, v, vA, vC)
+    pres = rng.uniform(60000, 103000, (iew, jns)).astype(np.float32)
+    slpc = rng.uniform(98000, 104000, (iew, jns)).astype(np.float32)
+    slpx = (slpc + rng.normal(0, 300, (iew, jns))).astype(np.float32)
+    a = rng.normal(280, 5, (kbu, iew, jns)).astype(np.float32); b = rng.normal(282, 5, (kbu, iew, jns)).astype(np.float32)
+    press = np.array([1001, 1000, 925, 850, 700, 500, 300], np.float32)
+    k7 = len(press)
+    t = np.empty((k7, iew, jns), np.float32); h = np.empty_like(t)
+    for k, p in enumerate(press):
+        t[k] = 288.0 * (min(p, 1000.0) / 1000.0) ** 0.19 + rng.normal(0, 1.5, (iew, jns))
+        h[k] = 44330.0 * (1 - (min(p, 1000.0) / 1013.25) ** 0.1903) + rng.normal(0, 10, (iew, jns))
+    rh = rng.uniform(-5, 110, (k7, iew, jns)).astype(np.float32)
+    terrain = rng.uniform(0, 5200, (iew, jns)).astype(np.float32)
+    slp = rng.uniform(99000, 103000, (iew, jns)).astype(np.float32)
+    rc, rh1, qv, psfc = O.mixing_ratio(rh, t, h, terrain, slp, press)
+    assert rc == 0
+    fargs = dict(iew=60, jns=50, kbu=4, n_sfc=50, n_snd=8, seed=29, radii=(6, 4), dx_m=60000.0)
+    case = synth.small_case(**fargs)
+    inputs = {"in_" + n_: getattr(case, n_).copy() for n_ in CASE_ARRAYS}
+    tb0 = rng.integers(0, 3, (case.iew, case.jns)).astype(np.float32)
+    tb, od = O.qc_time_fdda(case, tb0)
+    np.savez_compressed(OUT / "epilogue.npz", u=u, uA=uA, uC=uC, v=v, vA=vA, vC=vC, out_u=gu, out_v=gv,
+                        pres=pres, slpc=slpc, slpx=slpx, out_pres=O.pres_sfc_from_slp(pres, slpc, slpx),
+                        ta=a, tb=b, tinterp=[2, 0, 6], out_tinterp_cross=O.temporal_interp(a, b, 2, 0, 6, True)[1],
+                        out_tinterp_full=O.temporal_interp(a, b, 2, 0, 6, False)[1],
+                        press=press, t=t, h=h, rh=rh, terrain=terrain, slp=slp, out_rh=rh1, out_qv=qv, out_psfc=psfc,
+                        fdda_args=fargs, fdda_tb0=tb0, fdda_tb=tb, fdda_od=od,
+                        **{"fdda_" + k_: v_ for k_, v_ in inputs.items()},
+                        **{"fdda_" + n_: getattr(case, n_).copy() for n_ in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp")})
+    f = OUT / "epilogue.npz"
+    print(f.name, f.stat().st_size)
+
+
 if __name__ == "__main__":
-    main()
+    epilogue() if "--epilogue" in sys.argv else (main(), epilogue())

@@ -117,3 +117,32 @@ def test_time_small(impl):
             np.testing.assert_array_equal(getattr(case, n), z[n], err_msg=n)
         else:
             np.testing.assert_allclose(getattr(case, n), z[n], rtol=RTOL, atol=ATOL, err_msg=n)
+
+
+def test_epilogue_fdda_and_temporal_interp(impl):
+    """SURVEY 8f ranks 2-4 (tests/golden/epilogue.npz): bit for bit, except qv / psfc on the GPU
+    (EXP, LOG, ** in FP64-then-round vs glibc: 1e-6 relative, written here)."""
+    z = load("epilogue.npz")
+    gu, gv = impl.wind_increment_to_c_grid(z["u"], z["uA"], z["uC"], z["v"], z["vA"], z["vC"])
+    np.testing.assert_array_equal(gu, z["out_u"]); np.testing.assert_array_equal(gv, z["out_v"])
+    np.testing.assert_array_equal(impl.pres_sfc_from_slp(z["pres"], z["slpc"], z["slpx"]), z["out_pres"])
+    cf, c1, c2 = (int(q) for q in z["tinterp"])
+    for cross, key in ((True, "out_tinterp_cross"), (False, "out_tinterp_full")):
+        out = impl.temporal_interp(z["ta"], z["tb"], cf, c1, c2, cross)
+        np.testing.assert_array_equal(out[1] if impl.kind == "oracle" else out, z[key])
+    out = impl.mixing_ratio(z["rh"], z["t"], z["h"], z["terrain"], z["slp"], z["press"])
+    rh1, qv, psfc = out[-3:]
+    np.testing.assert_array_equal(rh1, z["out_rh"])
+    if impl.kind == "oracle":
+        np.testing.assert_array_equal(qv, z["out_qv"]); np.testing.assert_array_equal(psfc, z["out_psfc"])
+    else:
+        np.testing.assert_allclose(qv, z["out_qv"], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(psfc, z["out_psfc"], rtol=1e-6, atol=0)
+    case = synth.small_case(**z["fdda_args"].item())
+    for n in CASE_ARRAYS:
+        getattr(case, n)[...] = z["fdda_in_" + n]
+    tb, od = (impl.o.qc_time_fdda if impl.kind == "oracle" else impl.c.proc_qc_fdda)(case, z["fdda_tb0"])
+    np.testing.assert_array_equal(tb, z["fdda_tb"]); np.testing.assert_array_equal(od, z["fdda_od"])
+    for n in ("qc_u", "qc_v", "qc_t", "qc_slp"):
+        np.testing.assert_array_equal(getattr(case, n), z["fdda_" + n], err_msg=n)
+    assert np.count_nonzero(case.qc_rh != z["fdda_qc_rh"]) <= (0 if impl.kind == "oracle" else 2)
