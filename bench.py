@@ -306,14 +306,16 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         resident_oa()
 
     # ---- e2e: pinned host arrays through the host-pointer C ABI -----------------------------
-    host0 = {nm: getattr(case, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
-    pin = {}
-    for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
-        t = torch.from_numpy(getattr(case, nm).copy()).pin_memory()
-        pin[nm] = t
-    hcase = case.copy()
-    for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
-        setattr(hcase, nm, pin[nm].numpy())
+    do_e2e = not args.no_e2e
+    if do_e2e:
+        host0 = {nm: getattr(case, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
+        pin = {}
+        for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
+            t = torch.from_numpy(getattr(case, nm).copy()).pin_memory()
+            pin[nm] = t
+        hcase = case.copy()
+        for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
+            setattr(hcase, nm, pin[nm].numpy())
 
     def restore_host():
         for nm in FIELD_NAMES + FLAG_NAMES:
@@ -338,18 +340,19 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     updates, candidates = st["cressman_updates"], st["cressman_candidates"]
     upd_ell, upd_ban = st["cressman_updates_ellipse"], st["cressman_updates_banana"]
     buddy_obs, pair_tests = st["buddy_obs"], st["buddy_pair_tests"]
-    restore_host(); step_e2e()
-    ref_out = {nm: getattr(hcase, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
-    if slab_plan is None:
-        same = all(np.array_equal(work[nm].cpu().numpy(), ref_out[nm]) for nm in FIELD_NAMES + FLAG_NAMES)
-        assert same, "resident and host-pointer paths disagree"
-    else:
-        # the resident path analysed this rank's (level, variable) slabs, the e2e path its level range:
-        # compare where both did the work -- the upper levels the two plans share
-        ka, kb = max(K0, slab_plan["k0"]), min(KR, slab_plan["k1"])
-        same = all(np.array_equal(work[nm].cpu().numpy()[ka:kb], ref_out[nm][ka:kb])
-                   for nm in ("t", "u", "v", "rh", "qc_u", "qc_v", "qc_t", "qc_rh"))
-        assert same, "slab-sharded resident path and level-sharded host-pointer path disagree"
+    if do_e2e:
+        restore_host(); step_e2e()
+        ref_out = {nm: getattr(hcase, nm).copy() for nm in FIELD_NAMES + FLAG_NAMES}
+        if slab_plan is None:
+            same = all(np.array_equal(work[nm].cpu().numpy(), ref_out[nm]) for nm in FIELD_NAMES + FLAG_NAMES)
+            assert same, "resident and host-pointer paths disagree"
+        else:
+            # the resident path analysed this rank's (level, variable) slabs, the e2e path its level range:
+            # compare where both did the work -- the upper levels the two plans share
+            ka, kb = max(K0, slab_plan["k0"]), min(KR, slab_plan["k1"])
+            same = all(np.array_equal(work[nm].cpu().numpy()[ka:kb], ref_out[nm][ka:kb])
+                       for nm in ("t", "u", "v", "rh", "qc_u", "qc_v", "qc_t", "qc_rh"))
+            assert same, "slab-sharded resident path and level-sharded host-pointer path disagree"
 
     # ---- warm-up -------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -380,51 +383,53 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     oa_ms = sum(b.elapsed_time(c) for _, b, c in ev) / args.steps
     step_ms = qc_ms + oa_ms
 
-    # ---- timed: e2e --------------------------------------------------------------------------------
-    # The public asynchronous per-time API (og_time_upload / _compute / _download / _wait): every
-    # step uploads the time period's inputs from pinned host arrays, runs proc_qc + proc_oa and
-    # reads the analysed fields and flags back into pinned host arrays; up to NS time periods are
-    # in flight, so the copies of neighbouring steps overlap the compute of the current one.
-    NS = 3
-    ocase = []
-    for s_ in range(NS):
-        oc = case.copy()
-        for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
-            setattr(oc, nm, torch.from_numpy(getattr(case, nm).copy()).pin_memory().numpy())
-        ocase.append(oc)
-    restore_host()
-
-    def run_e2e(nsteps):
-        ctx.time_upload(hcase, 0, K0, KR)
-        for i in range(nsteps):
-            s_ = i % NS
-            if i + 1 < nsteps:
-                ctx.time_upload(hcase, (i + 1) % NS, K0, KR)
-            ctx.time_compute(hcase, s_, K0, KR)
-            ctx.time_download(ocase[s_], s_, K0, KR)
+    e2e_ms, e2e_blocking_ms, st_e = 0.0, None, {"h2d_bytes": 0, "d2h_bytes": 0}
+    if do_e2e:
+        # ---- timed: e2e --------------------------------------------------------------------------------
+        # The public asynchronous per-time API (og_time_upload / _compute / _download / _wait): every
+        # step uploads the time period's inputs from pinned host arrays, runs proc_qc + proc_oa and
+        # reads the analysed fields and flags back into pinned host arrays; up to NS time periods are
+        # in flight, so the copies of neighbouring steps overlap the compute of the current one.
+        NS = 3
+        ocase = []
         for s_ in range(NS):
-            ctx.time_wait(s_)
-
-    blocking = []
-    for _ in range(3):
+            oc = case.copy()
+            for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
+                setattr(oc, nm, torch.from_numpy(getattr(case, nm).copy()).pin_memory().numpy())
+            ocase.append(oc)
         restore_host()
-        t0 = time.perf_counter(); step_e2e(); ctx.sync()
-        blocking.append((time.perf_counter() - t0) * 1e3)
-    e2e_blocking_ms = float(np.mean(blocking[1:]))
-    restore_host()
-    run_e2e(NS + 1)          # touches every slot: no allocation is left for the timed steps
-    same = all(np.array_equal(ref_out[nm], getattr(ocase[s_], nm))
-               for nm in FIELD_NAMES + FLAG_NAMES for s_ in range(NS))
-    assert same, "blocking and asynchronous host-pointer paths disagree"
-    ctx.reset_stats()
-    barrier()
-    t0 = time.perf_counter()
-    run_e2e(args.steps)
-    ctx.sync()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps      # wall clock: host staging counts
-    barrier()
+
+        def run_e2e(nsteps):
+            ctx.time_upload(hcase, 0, K0, KR)
+            for i in range(nsteps):
+                s_ = i % NS
+                if i + 1 < nsteps:
+                    ctx.time_upload(hcase, (i + 1) % NS, K0, KR)
+                ctx.time_compute(hcase, s_, K0, KR)
+                ctx.time_download(ocase[s_], s_, K0, KR)
+            for s_ in range(NS):
+                ctx.time_wait(s_)
+
+        blocking = []
+        for _ in range(3):
+            restore_host()
+            t0 = time.perf_counter(); step_e2e(); ctx.sync()
+            blocking.append((time.perf_counter() - t0) * 1e3)
+        e2e_blocking_ms = float(np.mean(blocking[1:]))
+        restore_host()
+        run_e2e(NS + 1)          # touches every slot: no allocation is left for the timed steps
+        same = all(np.array_equal(ref_out[nm], getattr(ocase[s_], nm))
+                   for nm in FIELD_NAMES + FLAG_NAMES for s_ in range(NS))
+        assert same, "blocking and asynchronous host-pointer paths disagree"
+        ctx.reset_stats()
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(args.steps)
+        ctx.sync()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps      # wall clock: host staging counts
+        barrier()
+        st_e = ctx.stats()
     clocks = sampler.stop()
-    st_e = ctx.stats()
 
     # ---- reduce over ranks: max time, summed work ------------------------------------------------
     vec = torch.tensor([step_ms, e2e_ms, qc_ms, oa_ms, scan_ms / args.steps], device=dev, dtype=torch.float64)
@@ -491,11 +496,11 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                                         f"1 analysis time, levels sharded over {world} ranks") if args.scaling == "strong"
                                        else f"{world} x independent analysis time"),
                        "cpu_affinity": affinity},
-            "e2e": {"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "api": "og_time_upload/_compute/_download/_wait, 3 time periods in flight, pinned host arrays",
-                    "blocking_call_ms": e2e_blocking_ms,
-                    "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
-                    "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps},
+            "e2e": ({"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                     "api": "og_time_upload/_compute/_download/_wait, 3 time periods in flight, pinned host arrays",
+                     "blocking_call_ms": e2e_blocking_ms,
+                     "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
+                     "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps} if do_e2e else None),
             "gpu_launches": int(g_launch),
             "clocks": clocks,
             "roofline": roofline,
@@ -527,6 +532,9 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "contracted"],
                     help="scan-kernel arithmetic (og_set_arithmetic); exact = bit-identical to the reference's")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true",
+                    help="skip the host-pointer leg (e2e: null); for auxiliary scaling runs of the largest "
+                         "configuration, whose pinned host copies would not fit eight times into one box")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one analysis time per rank; strong: one time, levels sharded over the ranks")
     ap.add_argument("--shard", default="slabs", choices=["slabs", "levels"],
