@@ -30,6 +30,54 @@ MODULE obsgrid_gpu
 
    TYPE ( C_PTR ) , SAVE :: og_handle = C_NULL_PTR
 
+   !  The per-time batched API (include/obsgrid_gpu.h, INTEGRATION.md section 2): interoperable
+   !  mirrors of og_qc_params (namelist record 4), og_oa_params (records 7-9) and og_time_desc.
+   !  Member order and types are the C structs'; BIND(C) gives them the C compiler's padding
+   !  (tests/test_abi.py compares the member lists).
+   INTEGER , PARAMETER :: OG_MAX_SCAN = 10            ! src/proc_oa.F90:105
+
+   TYPE , BIND ( C ) :: og_qc_params
+      INTEGER ( C_INT ) :: qc_test_error_max , qc_test_buddy
+      REAL ( C_FLOAT ) :: max_error_t , max_error_uv , max_error_rh , max_error_dewpoint , max_error_p
+      REAL ( C_FLOAT ) :: max_buddy_t , max_buddy_uv , max_buddy_rh , max_buddy_dewpoint , max_buddy_p
+      REAL ( C_FLOAT ) :: buddy_weight
+      INTEGER ( C_INT ) :: time_hhmmss
+      INTEGER ( C_INT ) :: qc_dewpoint
+      INTEGER ( C_INT ) :: var_mask
+   END TYPE og_qc_params
+
+   TYPE , BIND ( C ) :: og_oa_params
+      INTEGER ( C_INT ) :: radius_influence ( OG_MAX_SCAN )
+      REAL ( C_FLOAT ) :: radius_influence_sfc_mult
+      INTEGER ( C_INT ) :: use_first_guess
+      INTEGER ( C_INT ) :: scale_cressman_rh_decreases
+      INTEGER ( C_INT ) :: smooth_type
+      INTEGER ( C_INT ) :: smooth_sfc_wind , smooth_sfc_temp , smooth_sfc_rh , smooth_sfc_slp
+      INTEGER ( C_INT ) :: smooth_upper_wind , smooth_upper_temp , smooth_upper_rh
+      INTEGER ( C_INT ) :: surface_only
+      INTEGER ( C_INT ) :: clamp_fg_rh
+      INTEGER ( C_INT ) :: var_mask
+   END TYPE og_oa_params
+
+   !  pointers: C_LOC of the caller's arrays -- t(jns,iew,kbu) etc. as src/first_guess.inc declares
+   !  them, the observation table rows as INTEGRATION.md section 2 describes
+   TYPE , BIND ( C ) :: og_time_desc
+      INTEGER ( C_INT ) :: iew , jns , kbu
+      REAL ( C_FLOAT ) :: dx_km
+      TYPE ( C_PTR ) :: pressure
+      TYPE ( C_PTR ) :: t , u , v , rh
+      TYPE ( C_PTR ) :: slp
+      INTEGER ( C_INT ) :: nrep
+      TYPE ( C_PTR ) :: xob , yob
+      TYPE ( C_PTR ) :: lon , elev
+      TYPE ( C_PTR ) :: ob_u , ob_v , ob_t , ob_rh
+      TYPE ( C_PTR ) :: ob_slp
+      TYPE ( C_PTR ) :: qc_u , qc_v , qc_t , qc_rh
+      TYPE ( C_PTR ) :: qc_slp
+   END TYPE og_time_desc
+
+   PUBLIC :: OG_MAX_SCAN , og_qc_params , og_oa_params , og_time_desc
+
    INTERFACE
 
       INTEGER ( C_INT ) FUNCTION og_init ( ctx , device ) BIND ( C , NAME = 'og_init' )
@@ -153,10 +201,53 @@ MODULE obsgrid_gpu
          INTEGER ( C_INT ) , VALUE :: iew , jns , kbu
       END FUNCTION og_mixing_ratio
 
+      !  proc_qc / proc_oa of one analysis time over the flat observation table
+      INTEGER ( C_INT ) FUNCTION og_qc_time ( ctx , d , p ) BIND ( C , NAME = 'og_qc_time' )
+         IMPORT :: C_PTR , C_INT , og_time_desc , og_qc_params
+         TYPE ( C_PTR ) , VALUE :: ctx
+         TYPE ( og_time_desc ) , INTENT ( IN ) :: d
+         TYPE ( og_qc_params ) , INTENT ( IN ) :: p
+      END FUNCTION og_qc_time
+
+      INTEGER ( C_INT ) FUNCTION og_qc_time_fdda ( ctx , d , p , tobbox , odis ) BIND ( C , NAME = 'og_qc_time_fdda' )
+         IMPORT :: C_PTR , C_INT , C_FLOAT , og_time_desc , og_qc_params
+         TYPE ( C_PTR ) , VALUE :: ctx
+         TYPE ( og_time_desc ) , INTENT ( IN ) :: d
+         TYPE ( og_qc_params ) , INTENT ( IN ) :: p
+         REAL ( C_FLOAT ) , INTENT ( INOUT ) :: tobbox ( * )
+         REAL ( C_FLOAT ) , INTENT ( OUT ) :: odis ( * )
+      END FUNCTION og_qc_time_fdda
+
+      INTEGER ( C_INT ) FUNCTION og_oa_time ( ctx , d , p , k_begin , k_end ) BIND ( C , NAME = 'og_oa_time' )
+         IMPORT :: C_PTR , C_INT , og_time_desc , og_oa_params
+         TYPE ( C_PTR ) , VALUE :: ctx
+         TYPE ( og_time_desc ) , INTENT ( IN ) :: d
+         TYPE ( og_oa_params ) , INTENT ( IN ) :: p
+         INTEGER ( C_INT ) , VALUE :: k_begin , k_end
+      END FUNCTION og_oa_time
+
+      INTEGER ( C_INT ) FUNCTION og_qc_oa_time ( ctx , d , qp , op , k_begin , k_end , pipeline_groups ) &
+      BIND ( C , NAME = 'og_qc_oa_time' )
+         IMPORT :: C_PTR , C_INT , og_time_desc , og_qc_params , og_oa_params
+         TYPE ( C_PTR ) , VALUE :: ctx
+         TYPE ( og_time_desc ) , INTENT ( IN ) :: d
+         TYPE ( og_qc_params ) , INTENT ( IN ) :: qp
+         TYPE ( og_oa_params ) , INTENT ( IN ) :: op
+         INTEGER ( C_INT ) , VALUE :: k_begin , k_end , pipeline_groups
+      END FUNCTION og_qc_oa_time
+
+      !  0 = OG_ARITH_EXACT (default), 1 = OG_ARITH_CONTRACTED
+      INTEGER ( C_INT ) FUNCTION og_set_arithmetic ( ctx , mode ) BIND ( C , NAME = 'og_set_arithmetic' )
+         IMPORT :: C_PTR , C_INT
+         TYPE ( C_PTR ) , VALUE :: ctx
+         INTEGER ( C_INT ) , VALUE :: mode
+      END FUNCTION og_set_arithmetic
+
    END INTERFACE
 
    PUBLIC :: og_cressman , og_error_max , og_buddy_check , og_ob_density , og_obs_distance , og_fail
    PUBLIC :: og_wind_increment_to_c_grid , og_pres_sfc_from_slp , og_mixing_ratio , og_temporal_interp
+   PUBLIC :: og_qc_time , og_qc_time_fdda , og_oa_time , og_qc_oa_time , og_set_arithmetic
 
 CONTAINS
 

@@ -68,3 +68,38 @@ def test_no_cpu_fallback():
 def test_null_context_is_rejected_not_dereferenced():
     lib = _capi.lib()
     assert lib.og_sync(None) == -2 and lib.og_set_counting(None, 1) == -2     # OG_ERR_INVALID
+
+
+def _c_struct_members(name):
+    m = re.search(r"typedef\s+struct\s+%s\s*\{(.*?)\}\s*%s\s*;" % (name, name), HEADER, flags=re.S)
+    body = re.sub(r"/\*.*?\*/", "", m.group(1), flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(int|float)\b", "", decl)
+        for part in decl.split(","):
+            out.append(re.sub(r"[\s\*]|\bconst\b|\bint\b|\bfloat\b|\[.*?\]", "", part))
+    return [x for x in out if x]
+
+
+def _fortran_type_members(name):
+    shim = (ROOT / "fortran" / "obsgrid_gpu_iface.F90").read_text()
+    m = re.search(r"TYPE\s*,\s*BIND\s*\(\s*C\s*\)\s*::\s*%s\b(.*?)END TYPE %s" % (name, name), shim, flags=re.S)
+    out = []
+    for line in m.group(1).splitlines():
+        line = line.split("!")[0]
+        if "::" not in line:
+            continue
+        for part in line.split("::", 1)[1].split(","):
+            part = re.sub(r"\(.*?\)", "", part).strip()
+            if part:
+                out.append(part)
+    return out
+
+
+@pytest.mark.parametrize("name", ["og_qc_params", "og_oa_params", "og_time_desc"])
+def test_fortran_derived_types_mirror_the_c_structs(name):
+    """Same members in the same order (types are all 4-byte or pointers; BIND(C) pads as C does)."""
+    assert _fortran_type_members(name) == _c_struct_members(name)
