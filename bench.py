@@ -390,25 +390,58 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         # step uploads the time period's inputs from pinned host arrays, runs proc_qc + proc_oa and
         # reads the analysed fields and flags back into pinned host arrays; up to NS time periods are
         # in flight, so the copies of neighbouring steps overlap the compute of the current one.
-        NS = 3
+        # Two contexts driven from two host threads ("lanes") when the case is small enough for two
+        # sets of device mirrors: while one lane waits on a list-size round trip the other lane's
+        # kernels keep the SMs busy.  Lane 0 is `ctx`; every lane has NS slots of its own.
+        case_bytes = sum(getattr(case, nm).nbytes for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES)
+        n_lanes = args.e2e_lanes if args.e2e_lanes > 0 else (2 if case_bytes < (4 << 30) else 1)
+        NS = 3 if n_lanes == 1 else 2
+        lanes = [ctx] + [Context(local_rank) for _ in range(n_lanes - 1)]
+        for c_ in lanes[1:]:
+            c_.set_arithmetic(args.arith)
         ocase = []
-        for s_ in range(NS):
+        for s_ in range(NS * n_lanes):
             oc = case.copy()
             for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
                 setattr(oc, nm, torch.from_numpy(getattr(case, nm).copy()).pin_memory().numpy())
             ocase.append(oc)
         restore_host()
 
-        def run_e2e(nsteps):
-            ctx.time_upload(hcase, 0, K0, KR)
+        lane_errors = []
+
+        def lane_run(l_, nsteps):
+            try:
+                lane_steps(l_, nsteps)
+            except BaseException as e_:      # noqa: BLE001  (re-raised on the main thread)
+                lane_errors.append(e_)
+
+        def lane_steps(l_, nsteps):
+            c_, outs = lanes[l_], ocase[l_ * NS:(l_ + 1) * NS]
+            if nsteps <= 0:
+                return
+            c_.time_upload(hcase, 0, K0, KR)
             for i in range(nsteps):
                 s_ = i % NS
                 if i + 1 < nsteps:
-                    ctx.time_upload(hcase, (i + 1) % NS, K0, KR)
-                ctx.time_compute(hcase, s_, K0, KR)
-                ctx.time_download(ocase[s_], s_, K0, KR)
+                    c_.time_upload(hcase, (i + 1) % NS, K0, KR)
+                c_.time_compute(hcase, s_, K0, KR)
+                c_.time_download(outs[s_], s_, K0, KR)
             for s_ in range(NS):
-                ctx.time_wait(s_)
+                c_.time_wait(s_)
+            c_.sync()
+
+        def run_e2e(nsteps):
+            share = [nsteps // n_lanes + (1 if l_ < nsteps % n_lanes else 0) for l_ in range(n_lanes)]
+            if n_lanes == 1:
+                lane_steps(0, nsteps)
+                return
+            th = [threading.Thread(target=lane_run, args=(l_, share[l_])) for l_ in range(n_lanes)]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            if lane_errors:
+                raise lane_errors[0]
 
         blocking = []
         for _ in range(3):
@@ -417,18 +450,20 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             blocking.append((time.perf_counter() - t0) * 1e3)
         e2e_blocking_ms = float(np.mean(blocking[1:]))
         restore_host()
-        run_e2e(NS + 1)          # touches every slot: no allocation is left for the timed steps
-        same = all(np.array_equal(ref_out[nm], getattr(ocase[s_], nm))
-                   for nm in FIELD_NAMES + FLAG_NAMES for s_ in range(NS))
+        run_e2e((NS + 1) * n_lanes)   # touches every slot of every lane: no allocation is left for the timed steps
+        same = all(np.array_equal(ref_out[nm], getattr(oc_, nm)) for nm in FIELD_NAMES + FLAG_NAMES for oc_ in ocase)
         assert same, "blocking and asynchronous host-pointer paths disagree"
-        ctx.reset_stats()
+        for c_ in lanes:
+            c_.reset_stats()
         barrier()
         t0 = time.perf_counter()
         run_e2e(args.steps)
         ctx.sync()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps      # wall clock: host staging counts
         barrier()
-        st_e = ctx.stats()
+        st_e = {k_: sum(c_.stats()[k_] for c_ in lanes) for k_ in ("h2d_bytes", "d2h_bytes")}
+        for c_ in lanes[1:]:
+            c_.close()
     clocks = sampler.stop()
 
     # ---- reduce over ranks: max time, summed work ------------------------------------------------
@@ -497,7 +532,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                                        else f"{world} x independent analysis time"),
                        "cpu_affinity": affinity},
             "e2e": ({"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                     "api": "og_time_upload/_compute/_download/_wait, 3 time periods in flight, pinned host arrays",
+                     "api": (f"og_time_upload/_compute/_download/_wait, pinned host arrays, {n_lanes} context(s) x "
+                             f"{NS} time periods in flight" + (", one host thread per context" if n_lanes > 1 else "")),
                      "blocking_call_ms": e2e_blocking_ms,
                      "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
                      "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps} if do_e2e else None),
@@ -539,6 +575,8 @@ def main():
                     help="weak: one analysis time per rank; strong: one time, levels sharded over the ranks")
     ap.add_argument("--shard", default="slabs", choices=["slabs", "levels"],
                     help="strong scaling: deal out the surface level's variable slabs (slabs) or whole levels only")
+    ap.add_argument("--e2e-lanes", type=int, default=0,
+                    help="contexts (each on its own host thread) of the e2e leg; 0: two when the case is small")
     ap.add_argument("--pipeline-groups", type=int, default=0,
                     help="level groups of the pipelined e2e call (0: library default)")
     ap.add_argument("--ref-levels", type=int, default=64,
