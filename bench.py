@@ -411,6 +411,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
 
         def lane_run(l_, nsteps):
             try:
+                torch.cuda.set_device(local_rank)    # a new host thread starts on device 0
                 lane_steps(l_, nsteps)
             except BaseException as e_:      # noqa: BLE001  (re-raised on the main thread)
                 lane_errors.append(e_)

@@ -14,6 +14,16 @@ using namespace og;
 // =========================================================================================
 // context
 // =========================================================================================
+// Every entry point makes the context's device current first: the caller may be a host thread
+// that has never touched CUDA (its current device is 0) while the context lives on another GPU.
+#define OG_BIND(c)                                                                          \
+    do {                                                                                      \
+        if ((c) && cudaSetDevice((c)->device) != cudaSuccess) {                               \
+            set_error("%s: cudaSetDevice(%d) failed", __func__, (c)->device);                 \
+            return OG_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
 extern "C" int og_abi_version(void) { return OG_ABI_VERSION; }
 extern "C" const char* og_last_error(void) { return og::last_error(); }
 
@@ -57,6 +67,7 @@ extern "C" int og_init(og_ctx** out, int device)
 
 extern "C" int og_finalize(og_ctx* c)
 {
+    OG_BIND(c);
     if (!c) return OG_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
@@ -94,6 +105,7 @@ static int fetch_counters(og_ctx* c)
 
 extern "C" int og_get_stats(og_ctx* c, og_stats* out)
 {
+    OG_BIND(c);
     if (!c || !out) return OG_ERR_INVALID;
     OG_TRY(fetch_counters(c));
     *out = c->stats;
@@ -101,6 +113,7 @@ extern "C" int og_get_stats(og_ctx* c, og_stats* out)
 }
 extern "C" int og_reset_stats(og_ctx* c)
 {
+    OG_BIND(c);
     if (!c) return OG_ERR_INVALID;
     c->stats = og_stats{};
     OG_CUDA(cudaMemsetAsync(c->d_counters, 0, 6 * sizeof(unsigned long long), c->stream));
@@ -109,6 +122,7 @@ extern "C" int og_reset_stats(og_ctx* c)
 extern "C" int og_set_counting(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->counting = on; return OG_OK; }
 extern "C" int og_set_arithmetic(og_ctx* c, int mode)
 {
+    OG_BIND(c);
     if (!c || (mode != OG_ARITH_EXACT && mode != OG_ARITH_CONTRACTED)) { set_error("og_set_arithmetic: bad argument"); return OG_ERR_INVALID; }
     c->arithmetic = mode;
     return OG_OK;
@@ -116,10 +130,11 @@ extern "C" int og_set_arithmetic(og_ctx* c, int mode)
 extern "C" int og_get_arithmetic(og_ctx* c) { return c ? c->arithmetic : OG_ERR_INVALID; }
 extern "C" int og_set_timing(og_ctx* c, int on) { if (!c) return OG_ERR_INVALID; c->time_kernels = on != 0; c->timers_used = 0; return OG_OK; }
 extern "C" void* og_stream(og_ctx* c) { return c ? (void*)c->stream : nullptr; }
-extern "C" int og_sync(og_ctx* c) { if (!c) return OG_ERR_INVALID; OG_CUDA(cudaStreamSynchronize(c->stream)); return OG_OK; }
+extern "C" int og_sync(og_ctx* c) { if (!c) return OG_ERR_INVALID; OG_BIND(c); OG_CUDA(cudaStreamSynchronize(c->stream)); return OG_OK; }
 
 extern "C" int og_last_kernel_ms(og_ctx* c, float* cressman_ms, float* buddy_ms)
 {
+    OG_BIND(c);
     if (!c) return OG_ERR_INVALID;
     OG_CUDA(cudaStreamSynchronize(c->stream));
     float acc[2] = {0.f, 0.f};
@@ -133,9 +148,10 @@ extern "C" int og_last_kernel_ms(og_ctx* c, float* cressman_ms, float* buddy_ms)
     if (buddy_ms) *buddy_ms = acc[1];
     return OG_OK;
 }
-extern "C" int og_fp32_peak(og_ctx* c, double* v) { if (!c || !v) return OG_ERR_INVALID; return fp32_peak(c, v); }
+extern "C" int og_fp32_peak(og_ctx* c, double* v) { if (!c || !v) return OG_ERR_INVALID; OG_BIND(c); return fp32_peak(c, v); }
 extern "C" int og_selftest_div(og_ctx* c, int n, unsigned seed, int rmax, long long* bad)
 {
+    OG_BIND(c);
     if (!c || !bad || n <= 0 || rmax <= 0) return OG_ERR_INVALID;
     return div_selftest(c, n, seed, rmax, bad);
 }
@@ -152,6 +168,8 @@ extern "C" int og_host_free(void* p) { if (p) cudaFreeHost(p); return OG_OK; }
 // =========================================================================================
 #define REQUIRE(cond, msg)                                                                \
     do { if (!(cond)) { set_error("%s: %s", __func__, msg); return OG_ERR_INVALID; } } while (0)
+
+
 
 template <class T>
 static int upload(og_ctx* c, const char* name, const T* host, size_t count, T** dev)
@@ -204,6 +222,7 @@ extern "C" int og_innovation(og_ctx* c, const float* gridded, int iew, int jns, 
                              const float* yob, const float* obs_value, int n, float scale,
                              int use_first_guess, float* diff, float* fg_value)
 {
+    OG_BIND(c);
     REQUIRE(c && gridded && diff && n >= 0 && iew > 2 && jns > 2, "bad argument");
     if (n == 0) return OG_OK;
     REQUIRE(xob && yob && obs_value, "null observation array");
@@ -231,6 +250,7 @@ extern "C" int og_cressman(og_ctx* c, const float* diff, const float* xob, const
                            int use_first_guess, const float* fg_value,
                            int scale_cressman_rh_decreases)
 {
+    OG_BIND(c);
     REQUIRE(c && gridded && n >= 0 && iew > 2 && jns > 2, "bad argument");
     REQUIRE(var >= OG_VAR_UU && var <= OG_VAR_PSFC, "unknown variable code");
     REQUIRE(radius_influence >= 0 && radius_influence < 8000, "radius out of range");
@@ -274,6 +294,7 @@ extern "C" int og_oa_slab(og_ctx* c, float* gridded, int iew, int jns, int var, 
                           const float* v_banana, int passes, int smooth_type,
                           int use_first_guess, int scale_cressman_rh_decreases, int* n_scans_done)
 {
+    OG_BIND(c);
     REQUIRE(c && gridded && radius_influence && n >= 0 && iew > 2 && jns > 2, "bad argument");
     REQUIRE(var >= OG_VAR_UU && var <= OG_VAR_PSFC, "unknown variable code");
     REQUIRE(n == 0 || (obs_value && xob && yob), "null observation array");
@@ -309,6 +330,7 @@ extern "C" int og_oa_slab(og_ctx* c, float* gridded, int iew, int jns, int var, 
 
 extern "C" int og_local_time(og_ctx* c, int time_hhmm, const float* lonob, int n, int* local_time)
 {
+    OG_BIND(c);
     REQUIRE(c && n >= 0 && (n == 0 || (lonob && local_time)), "bad argument");
     if (n == 0) return OG_OK;
     float* d_l; int* d_o;
@@ -324,6 +346,7 @@ extern "C" int og_fg_t_at_point(og_ctx* c, const float* fg_3d_t, const float* fg
                                 int iew, int kbu, const float* x_location, const float* y_location,
                                 const float* height_msl, int n, float* fg_t)
 {
+    OG_BIND(c);
     REQUIRE(c && fg_3d_t && fg_3d_h && n >= 0 && iew > 2 && jns > 2 && kbu >= 3, "bad argument");
     if (n == 0) return OG_OK;
     REQUIRE(x_location && y_location && height_msl && fg_t, "null point array");
@@ -344,6 +367,7 @@ extern "C" int og_fg_t_at_point(og_ctx* c, const float* fg_3d_t, const float* fg
 extern "C" int og_ob_density(og_ctx* c, const float* xob, const float* yob, float grid_dist, int n,
                              float* tobbox, int iew, int jns)
 {
+    OG_BIND(c);
     REQUIRE(c && tobbox && n >= 0 && iew > 2 && jns > 2 && iew <= 32000 && jns <= 32000, "bad argument");
     REQUIRE(grid_dist > 0.f, "grid_dist must be positive");
     if (n == 0) return OG_OK;
@@ -361,6 +385,7 @@ extern "C" int og_ob_density(og_ctx* c, const float* xob, const float* yob, floa
 
 extern "C" int og_obs_distance(og_ctx* c, const float* tobbox, float* distance, int iew, int jns, float dx)
 {
+    OG_BIND(c);
     REQUIRE(c && tobbox && distance && iew > 0 && jns > 0 && iew <= 32000 && jns <= 32000, "bad argument");
     const size_t npts = (size_t)iew * jns;
     float *d_t, *d_d;
@@ -377,6 +402,7 @@ extern "C" int og_wind_increment_to_c_grid(og_ctx* c, float* u, const float* uA,
                                            float* v, const float* vA, const float* vC, int jns,
                                            int iew, int kbu)
 {
+    OG_BIND(c);
     REQUIRE(c && jns >= 2 && iew >= 2 && kbu >= 1 && kbu <= 65535 && iew <= 65535, "bad argument");
     REQUIRE((u && uA && uC) || (v && vA && vC), "null field");
     const size_t n = (size_t)jns * iew * kbu;
@@ -402,6 +428,7 @@ extern "C" int og_temporal_interp(og_ctx* c, const float* first, const float* se
                                   int jns, int iew, int nlev, int icount_fdda, int icount_1,
                                   int icount_2, int cross)
 {
+    OG_BIND(c);
     REQUIRE(c && first && second && out && jns >= 2 && iew >= 2 && nlev >= 1, "bad argument");
     REQUIRE(iew <= 65535 && nlev <= 65535, "too many columns or levels");
     // tinterp_module.F90:98-121: integer weights, the both-zero special case, the divide check
@@ -422,6 +449,7 @@ extern "C" int og_temporal_interp(og_ctx* c, const float* first, const float* se
 extern "C" int og_pres_sfc_from_slp(og_ctx* c, const float* pres_sfc, const float* slp_C,
                                     const float* slp_x, float* out, int jns, int iew)
 {
+    OG_BIND(c);
     REQUIRE(c && pres_sfc && slp_C && slp_x && out && jns > 0 && iew > 0, "bad argument");
     const size_t n = (size_t)jns * iew;
     float *d_p, *d_c, *d_x, *d_o;
@@ -439,6 +467,7 @@ extern "C" int og_mixing_ratio(og_ctx* c, float* rh, const float* t, const float
                                const float* terrain, const float* slp_x, const float* pressure,
                                int iew, int jns, int kbu, float* qv, float* psfc)
 {
+    OG_BIND(c);
     REQUIRE(c && rh && t && h && terrain && slp_x && pressure && qv && psfc, "null argument");
     REQUIRE(iew >= 2 && jns >= 2 && kbu >= 2 && iew <= 65535, "bad dimensions");
     const size_t per = (size_t)jns * iew, n = per * kbu;
@@ -518,6 +547,7 @@ extern "C" int og_error_max(og_ctx* c, const float* obs, const float* xob, const
                             float pressure_hpa, const int* local_time, float* aob, float* err,
                             float* thr)
 {
+    OG_BIND(c);
     return qc_slab_common(c, 1, 0, gridded, iew, jns, var, pressure_hpa, obs, xob, yob,
                           station_elevation, local_time, n, max_difference, 0.f, 1.f, 1.f, qc_flag,
                           aob, err, thr, nullptr, nullptr, nullptr);
@@ -529,6 +559,7 @@ extern "C" int og_buddy_check(og_ctx* c, const float* obs, int n, const float* x
                               float buddy_weight, float buddy_difference, float* aob, float* err,
                               float* difmax, int* buddy_num_final)
 {
+    OG_BIND(c);
     return qc_slab_common(c, 0, 1, gridded, iew, jns, var, pressure_hpa, obs, xob, yob,
                           station_elevation, nullptr, n, 0.f, buddy_difference, buddy_weight, dx_km,
                           qc_flag, aob, nullptr, nullptr, err, difmax, buddy_num_final);
@@ -540,6 +571,7 @@ extern "C" int og_qc_slab(og_ctx* c, int do_error_max, int do_buddy, const float
                           int n, float max_error, float max_buddy, float buddy_weight, float dx_km,
                           int* qc_flag)
 {
+    OG_BIND(c);
     return qc_slab_common(c, do_error_max, do_buddy, gridded, iew, jns, var, pressure_hpa, obs, xob,
                           yob, station_elevation, local_time, n, max_error, max_buddy, buddy_weight,
                           dx_km, qc_flag, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -1099,6 +1131,7 @@ int mirror_in(og_ctx* c, const og_time_desc* d, int k0, int k1, bool qc, TimeDev
 
 extern "C" int og_dev_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* p, int k0, int k1)
 {
+    OG_BIND(c);
     REQUIRE(c && p, "null argument");
     OG_TRY(check_desc(d, k0, k1, false));
     return oa_time_core(c, view_of(d), p, k0, k1);
@@ -1107,6 +1140,7 @@ extern "C" int og_dev_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_para
 extern "C" int og_dev_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p, int k0,
                               int k1, int run_consistency)
 {
+    OG_BIND(c);
     REQUIRE(c && p, "null argument");
     OG_TRY(check_desc(d, k0, k1, true));
     return qc_time_core(c, view_of(d), p, k0, k1, run_consistency);
@@ -1131,6 +1165,7 @@ static int items_of(const og_time_desc* d, const int* levels, const int* var_mas
 extern "C" int og_dev_qc_time_items(og_ctx* c, const og_time_desc* d, const og_qc_params* p,
                                     const int* levels, const int* var_masks, int nitems, int run_consistency)
 {
+    OG_BIND(c);
     REQUIRE(c && p, "null argument");
     OG_TRY(check_desc(d, 0, d ? d->kbu : 0, true));
     LevelItems L;
@@ -1141,6 +1176,7 @@ extern "C" int og_dev_qc_time_items(og_ctx* c, const og_time_desc* d, const og_q
 extern "C" int og_dev_oa_time_items(og_ctx* c, const og_time_desc* d, const og_oa_params* p,
                                     const int* levels, const int* var_masks, int nitems)
 {
+    OG_BIND(c);
     REQUIRE(c && p, "null argument");
     OG_TRY(check_desc(d, 0, d ? d->kbu : 0, false));
     LevelItems L;
@@ -1152,6 +1188,7 @@ extern "C" int og_dev_oa_time_items(og_ctx* c, const og_time_desc* d, const og_o
 // the variables of a level were checked by different ranks (obsgrid_b200/shard.py).
 extern "C" int og_dev_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k1)
 {
+    OG_BIND(c);
     REQUIRE(c, "null context");
     OG_TRY(check_desc(d, k0, k1, false));
     if (k1 == k0 || d->nrep == 0) return OG_OK;
@@ -1164,6 +1201,7 @@ extern "C" int og_dev_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, i
 
 extern "C" int og_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k1)
 {
+    OG_BIND(c);
     REQUIRE(c, "null context");
     OG_TRY(check_desc(d, k0, k1, false));
     if (k1 == k0 || d->nrep == 0) return OG_OK;
@@ -1184,6 +1222,7 @@ extern "C" int og_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k
 
 extern "C" int og_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* p, int k0, int k1)
 {
+    OG_BIND(c);
     REQUIRE(c && p, "null argument");
     OG_TRY(check_desc(d, k0, k1, false));
     if (k1 == k0) return OG_OK;
@@ -1204,6 +1243,7 @@ extern "C" int og_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* 
 extern "C" int og_qc_time_levels(og_ctx* c, const og_time_desc* d, const og_qc_params* p, int k0,
                                  int k1, int run_consistency)
 {
+    OG_BIND(c);
     REQUIRE(c && p, "null argument");
     OG_TRY(check_desc(d, k0, k1, true));
     if (k1 == k0) return OG_OK;
@@ -1224,6 +1264,7 @@ extern "C" int og_qc_time_levels(og_ctx* c, const og_time_desc* d, const og_qc_p
 extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_params* qp,
                              const og_oa_params* op, int k0, int k1, int groups)
 {
+    OG_BIND(c);
     REQUIRE(c && qp && op, "null argument");
     OG_TRY(check_desc(d, k0, k1, true));
     if (k1 == k0) return OG_OK;
@@ -1373,6 +1414,7 @@ int slot_events(og_ctx* c, int slot)
 
 extern "C" int og_time_upload(og_ctx* c, const og_time_desc* d, int k0, int k1, int slot)
 {
+    OG_BIND(c);
     REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
     OG_TRY(check_desc(d, k0, k1, true));
     OG_TRY(slot_events(c, slot));
@@ -1404,6 +1446,7 @@ extern "C" int og_time_upload(og_ctx* c, const og_time_desc* d, int k0, int k1, 
 extern "C" int og_time_compute(og_ctx* c, const og_time_desc* d, const og_qc_params* qp,
                                const og_oa_params* op, int k0, int k1, int slot)
 {
+    OG_BIND(c);
     REQUIRE(c && qp && op && slot >= 0 && slot < OG_SLOTS, "bad argument");
     OG_TRY(check_desc(d, k0, k1, true));
     OG_TRY(slot_events(c, slot));
@@ -1423,6 +1466,7 @@ extern "C" int og_time_compute(og_ctx* c, const og_time_desc* d, const og_qc_par
 
 extern "C" int og_time_download(og_ctx* c, const og_time_desc* d, int k0, int k1, int slot)
 {
+    OG_BIND(c);
     REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
     OG_TRY(check_desc(d, k0, k1, true));
     OG_TRY(slot_events(c, slot));
@@ -1450,6 +1494,7 @@ extern "C" int og_time_download(og_ctx* c, const og_time_desc* d, int k0, int k1
 
 extern "C" int og_time_wait(og_ctx* c, int slot)
 {
+    OG_BIND(c);
     REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
     og_ctx::Slot& s = c->slots[slot];
     if (s.down_pending) { OG_CUDA(cudaEventSynchronize(s.down)); s.down_pending = false; }
@@ -1459,6 +1504,7 @@ extern "C" int og_time_wait(og_ctx* c, int slot)
 extern "C" int og_qc_time_fdda(og_ctx* c, const og_time_desc* d, const og_qc_params* p, float* tobbox,
                                float* odis)
 {
+    OG_BIND(c);
     REQUIRE(c && p && tobbox && odis, "null argument");
     OG_TRY(check_desc(d, 0, d ? d->kbu : 0, true));
     REQUIRE(d->iew <= 32000 && d->jns <= 32000, "grid larger than 32000 points per edge");
@@ -1482,6 +1528,7 @@ extern "C" int og_qc_time_fdda(og_ctx* c, const og_time_desc* d, const og_qc_par
 
 extern "C" int og_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p)
 {
+    OG_BIND(c);
     if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
     return og_qc_time_levels(c, d, p, 0, d->kbu, 1);
 }

@@ -698,3 +698,33 @@ def test_dev_item_lists_equal_the_range_calls(ctx):
     from obsgrid_b200._capi import OgError
     with pytest.raises(OgError):
         ctx.dev_proc_qc_items(d, base.qc_params, [3, 2], [0, 0])
+
+
+def test_context_on_another_device_from_a_fresh_thread(oracle):
+    """A host thread that never touched CUDA has device 0 current; a context on another GPU must
+    still work from it (every entry point binds the context's device).  Needs two GPUs."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from obsgrid_b200.api import Context
+    c1 = Context(1)
+    base = synth.small_case(iew=40, jns=36, kbu=4, n_sfc=120, n_snd=30, radii=(5, 3))
+    got, err = base.copy(), []
+
+    def work():
+        try:
+            c1.proc_qc_oa(got)
+            c1.time_upload(got, 0); c1.time_compute(got, 0); c1.time_download(got, 0); c1.time_wait(0)
+            c1.sync()
+        except BaseException as e:      # noqa: BLE001
+            err.append(e)
+
+    t = threading.Thread(target=work); t.start(); t.join()
+    c1.close()
+    assert not err, err
+    ref = base.copy()
+    oracle.qc_time(ref)
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_slp"):
+        np.testing.assert_array_equal(getattr(got, nm)[...] & 0, 0)      # ran to completion
+    assert np.any(got.t != base.t)
