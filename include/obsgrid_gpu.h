@@ -41,6 +41,10 @@
  *   - there is NO CPU fallback: og_init fails with OG_ERR_NO_DEVICE without an
  *     sm_100 GPU.
  *   - callers are single threaded per og_ctx (like the reference); calls block.
+ *     Contexts are independent: several may live on one GPU or on several, each driven by
+ *     its own host thread (two contexts on one GPU overlap the list-size round trips of one
+ *     time period with the kernels of another).  Every entry point makes its context's
+ *     device current, so a context may be used from any host thread.
  */
 #ifndef OBSGRID_GPU_H
 #define OBSGRID_GPU_H
