@@ -261,6 +261,10 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             slab_plan = shard.plan_slabs(case, world)[rank]
             item_levels = ([0] if slab_plan["sfc_mask"] else []) + list(range(slab_plan["k0"], slab_plan["k1"]))
             item_masks = ([slab_plan["sfc_mask"]] if slab_plan["sfc_mask"] else []) + [0] * (slab_plan["k1"] - slab_plan["k0"])
+            # OA has no DEWPOINT slab (bit 6): a rank that owns only that surface unit analyses no surface slab
+            sfc_oa = slab_plan["sfc_mask"] & 0x1f
+            oa_levels = ([0] if sfc_oa else []) + list(range(slab_plan["k0"], slab_plan["k1"]))
+            oa_masks = ([sfc_oa] if sfc_oa else []) + [0] * (slab_plan["k1"] - slab_plan["k0"])
 
     # ---- resident copy: pristine inputs + working set in HBM ---------------------------------
     pristine, work = {}, {}
@@ -284,12 +288,13 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             return
         # one batch: the rank's surface slabs and its upper levels share every launch
         ctx.dev_proc_qc_items(ddesc, case.qc_params, item_levels, item_masks, True)
-        # exchange: every surface flag row was updated by exactly one rank and flags only gain
-        # bits -> element-wise MAX over the ranks (NCCL, on the library's stream), then the
-        # consistency pass of the surface level (qc0_module.F90:371-404) on the merged rows
+        # exchange: every rank started from the same flags and QC only sets bits -> bitwise OR of the
+        # surface flag rows over the ranks (NCCL has no OR: the three QC bits travel as 0/1 planes
+        # under MAX, shard.allreduce_or), on the library's stream; then the consistency pass of the
+        # surface level (qc0_module.F90:371-404) on the merged rows
         with torch.cuda.stream(lib_stream):
             rows = torch.stack([work["qc_u"][0], work["qc_v"][0], work["qc_t"][0], work["qc_rh"][0], work["qc_slp"]])
-            dist.all_reduce(rows, op=dist.ReduceOp.MAX)
+            shard.allreduce_or(dist, rows)
             for i_, nm_ in enumerate(("qc_u", "qc_v", "qc_t", "qc_rh")):
                 work[nm_][0].copy_(rows[i_])
             work["qc_slp"].copy_(rows[4])
@@ -299,7 +304,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         if slab_plan is None:
             ctx.dev_proc_oa(ddesc, case.oa_params, K0, KR)
             return
-        ctx.dev_proc_oa_items(ddesc, case.oa_params, item_levels, [m & 0x1f for m in item_masks])
+        ctx.dev_proc_oa_items(ddesc, case.oa_params, oa_levels, oa_masks)
 
     def step_resident():
         resident_qc()
@@ -527,7 +532,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                        "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
                              "pristine copy before every step",
                        "parallelism": ((f"1 analysis time, (level, variable) slabs sharded over {world} ranks, surface "
-                                        f"flags combined with one NCCL all-reduce between QC and OA; e2e shards whole levels"
+                                        f"flags OR-combined with one NCCL all-reduce between QC and OA; e2e shards whole levels"
                                         if slab_plan is not None else
                                         f"1 analysis time, levels sharded over {world} ranks") if args.scaling == "strong"
                                        else f"{world} x independent analysis time"),

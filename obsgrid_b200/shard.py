@@ -158,36 +158,60 @@ def run_time_sharded(case, rank: int, world: int, proc_qc: Callable, proc_oa: Ca
 
 # ---- level x variable sharding --------------------------------------------------------------
 # The surface pseudo-level carries every report and is the one level worth more than a rank's
-# fair share (a third of cfg3, a quarter of cfg2), so its five variable slabs (UU VV TT RH PMSL;
-# DEWPOINT rides with RH, whose flag row it shares) are dealt out on their own; the upper levels
-# stay whole and contiguous.  The price is one exchange step: qc_consistency couples the flags of
-# U and V and of T and RH (qc0_module.F90:371-404), so between the QC and the OA phase the ranks
-# combine the surface flag rows (each row was updated by exactly one rank and flags only gain
-# bits: an element-wise MAX) and run the consistency pass on the merged rows.
-SFC_VARS = (("u", 1 << 0), ("v", 1 << 1), ("t", 1 << 2), ("rh", (1 << 3) | (1 << 6)), ("slp", 1 << 4))
+# fair share (a third of cfg3, a quarter of cfg2), so its slabs -- UU VV TT RH PMSL for QC and
+# OA, DEWPOINT for QC only -- are dealt out on their own; the upper levels stay whole and
+# contiguous.  The price is one exchange step: qc_consistency couples the flags of U and V and of
+# T and RH (qc0_module.F90:371-404), so between the QC and the OA phase the ranks combine the
+# surface flag rows and run the consistency pass on the merged rows.  Every rank starts from the
+# same incoming flags and QC only sets bits (qc0_module.F90:27-31, :55-72), so the merge is a
+# bitwise OR -- RH and DEWPOINT, which share a flag row, may sit on different ranks.
+SFC_VARS = (("u", 1 << 0), ("v", 1 << 1), ("t", 1 << 2), ("rh", 1 << 3), ("slp", 1 << 4), ("dew", 1 << 6))
 ANISO_COST = 1.6          # a UU / VV / RH update against a TT / PMSL one (measured, profiles/exp_levels.py)
 SFC_FLAGS = ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp")
+QC_FLAG_BITS = (14, 16, 17)   # no_buddies, fails_error_max, fails_buddy_check (missing.inc:21-43)
+
+
+def allreduce_or(dist, t):
+    """In-place bitwise OR of an int32 tensor over the ranks.  gloo has the operator; NCCL does not,
+    so there the three bits QC can set travel as 0/1 planes under MAX (every other bit is the
+    incoming flag, identical on all ranks)."""
+    import torch
+
+    if dist.get_backend() == "gloo":
+        dist.all_reduce(t, op=dist.ReduceOp.BOR)
+        return t
+    planes = torch.stack([(t >> b) & 1 for b in QC_FLAG_BITS]).to(torch.int8)
+    dist.all_reduce(planes, op=dist.ReduceOp.MAX)
+    for i, b in enumerate(QC_FLAG_BITS):
+        t |= planes[i].to(t.dtype) << b
+    return t
 
 
 def surface_unit_costs(case) -> list[float]:
-    """Cost of the surface slab of each variable, same unit as level_costs."""
+    """Cost of each surface unit of SFC_VARS, same unit as level_costs."""
     radii = [int(r) for r in case.oa_params.radius_influence if r >= 0]
     r2 = float(sum(r * r for r in radii)) or 1.0
     area = float(case.iew * case.jns)
     rc = 500.0 / float(case.dx_km)
     out = []
     for nm, _ in SFC_VARS:
-        ob = case.ob_slp if nm == "slp" else getattr(case, "ob_" + nm)[0]
-        n = float(np.count_nonzero(np.abs(ob - OG_MISSING_R) > 1.0))
-        pairs = n * n * min(9.0 * rc * rc / area, 1.0) * (2.0 if nm == "rh" else 1.0)
+        if nm == "dew":     # QC only; obs that carry both T and RH
+            ok = (np.abs(case.ob_rh[0] - OG_MISSING_R) > 1.0) & (np.abs(case.ob_t[0] - OG_MISSING_R) > 1.0)
+            n = float(np.count_nonzero(ok))
+        else:
+            ob = case.ob_slp if nm == "slp" else getattr(case, "ob_" + nm)[0]
+            n = float(np.count_nonzero(np.abs(ob - OG_MISSING_R) > 1.0))
+        pairs = n * n * min(9.0 * rc * rc / area, 1.0)
         shape = ANISO_COST if nm in ("u", "v", "rh") else 1.0
-        out.append(n * np.pi * r2 * shape + PAIR_PER_UPDATE * pairs + LEVEL_FIXED_UPDATES / 5.0)
+        oa = 0.0 if nm == "dew" else n * np.pi * r2 * shape
+        out.append(oa + PAIR_PER_UPDATE * pairs + LEVEL_FIXED_UPDATES / 6.0)
     return out
 
 
 def plan_slabs(case, world: int) -> list[dict]:
-    """One entry per rank: {'sfc_mask': variable bits of the surface slabs it owns (0: none),
-    'k0', 'k1': its contiguous range of upper levels (k0 >= 1)}."""
+    """One entry per rank: {'sfc_mask': variable bits (bit v-1 of variable v; bit 6 = DEWPOINT, QC
+    only) of the surface slabs it owns (0: none), 'k0', 'k1': its contiguous range of upper
+    levels (k0 >= 1)}."""
     world = max(int(world), 1)
     K = case.kbu
     if world == 1:
@@ -225,7 +249,7 @@ def run_time_sharded_slabs(case, rank: int, world: int, proc_qc: Callable, proc_
 
     proc_qc(case, k0, k1, run_consistency, var_mask), proc_oa(case, k0, k1, var_mask) and
     consistency(case, k0, k1) update `case` in place.  Phases: QC of the rank's surface slabs
-    (no consistency) and of its upper levels (with); exchange of the surface flag rows (MAX);
+    (no consistency) and of its upper levels (with); exchange of the surface flag rows (OR);
     consistency of the surface level; OA of the same slabs; gather to `dst`.
     """
     import torch
@@ -242,12 +266,12 @@ def run_time_sharded_slabs(case, rank: int, world: int, proc_qc: Callable, proc_
         t = torch.from_numpy(rows)
         if device is not None:
             t = t.to(device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_or(dist, t)
         rows = t.cpu().numpy()
         case.qc_u[0], case.qc_v[0], case.qc_t[0], case.qc_rh[0] = rows[0], rows[1], rows[2], rows[3]
         case.qc_slp[...] = rows[4]
     consistency(case, 0, 1)
-    if me["sfc_mask"]:
+    if me["sfc_mask"] & 0x1f:       # DEWPOINT (bit 6) has no analysis
         proc_oa(case, 0, 1, me["sfc_mask"] & 0x1f)
     if me["k1"] > me["k0"]:
         proc_oa(case, me["k0"], me["k1"], 0)
@@ -257,7 +281,9 @@ def run_time_sharded_slabs(case, rank: int, world: int, proc_qc: Callable, proc_
             _gather_rows(dist, getattr(case, nm), ranges, rank, dst, device)
         # surface fields: each comes from the rank that analysed it
         for nm, bits in SFC_VARS:
-            owner = next(r for r, p in enumerate(plan) if p["sfc_mask"] & bits & 0x1f)
+            if not bits & 0x1f:
+                continue
+            owner = next(r for r, p in enumerate(plan) if p["sfc_mask"] & bits)
             if owner == dst:
                 continue
             a = case.slp if nm == "slp" else getattr(case, nm)[0]

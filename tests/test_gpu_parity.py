@@ -619,7 +619,7 @@ def test_arithmetic_mode_is_validated(ctx):
 def test_time_slab_sharding_is_exact(ctx):
     """Level x variable sharding (obsgrid_b200/shard.py, north star: 'partitioned by pressure level x
     variable x analysis time'): the per-rank programs of run_time_sharded_slabs, run one after the
-    other on this GPU and merged as the collectives would (MAX of the surface flag rows, gather),
+    other on this GPU and merged as the collectives would (OR of the surface flag rows, gather),
     equal the unsharded time bit for bit."""
     from obsgrid_b200 import shard
     base = synth.small_case(iew=50, jns=44, kbu=7, n_sfc=300, n_snd=100, radii=(5, 3))
@@ -632,7 +632,7 @@ def test_time_slab_sharding_is_exact(ctx):
     def oa(c, k0, k1, mask):
         c.oa_params.var_mask = mask; ctx.proc_oa(c, k0, k1); c.oa_params.var_mask = 0
 
-    for world in (2, 4):
+    for world in (2, 4, 7):        # 7: RH and DEWPOINT of the surface on different ranks
         plan = shard.plan_slabs(base, world)
         cs = [base.copy() for _ in range(world)]
         for c, p in zip(cs, plan):
@@ -640,14 +640,14 @@ def test_time_slab_sharding_is_exact(ctx):
                 qc(c, 0, 1, False, p["sfc_mask"])
             if p["k1"] > p["k0"]:
                 qc(c, p["k0"], p["k1"], True, 0)
-        rows = [np.max([c.qc_slp if nm == "qc_slp" else getattr(c, nm)[0] for c in cs], axis=0)
+        rows = [np.bitwise_or.reduce([c.qc_slp if nm == "qc_slp" else getattr(c, nm)[0] for c in cs], axis=0)
                 for nm in shard.SFC_FLAGS]
         out = base.copy()
         for c, p in zip(cs, plan):
             c.qc_u[0], c.qc_v[0], c.qc_t[0], c.qc_rh[0] = rows[0], rows[1], rows[2], rows[3]
             c.qc_slp[...] = rows[4]
             ctx.qc_consistency(c, 0, 1)
-            if p["sfc_mask"]:
+            if p["sfc_mask"] & 0x1f:
                 oa(c, 0, 1, p["sfc_mask"] & 0x1f)
             if p["k1"] > p["k0"]:
                 oa(c, p["k0"], p["k1"], 0)

@@ -107,7 +107,6 @@ def test_plan_slabs_covers_every_slab_once():
         for p in plan:
             assert seen & p["sfc_mask"] == 0
             seen |= p["sfc_mask"]
-            assert bool(p["sfc_mask"] & (1 << 3)) == bool(p["sfc_mask"] & (1 << 6))   # DEWPOINT rides with RH
         assert seen == allbits
         ks = sorted((p["k0"], p["k1"]) for p in plan if p["k1"] > p["k0"])
         assert ks[0][0] == 1 and ks[-1][1] == case.kbu and all(a[1] == b[0] for a, b in zip(ks, ks[1:]))
@@ -122,22 +121,24 @@ def test_slab_sharding_sequential_equals_one_process(oracle):
     ref = base.copy()
     oracle.qc_time(ref); oracle.oa_time(ref)
     qc, oa, cons = _oracle_callables()
-    world = 3
+    world = 7          # one more rank than surface units: RH and DEWPOINT land on different ranks
     plan = shard.plan_slabs(base, world)
+    assert not any((p["sfc_mask"] & (1 << 3)) and (p["sfc_mask"] & (1 << 6)) for p in plan)
     cs = [base.copy() for _ in range(world)]
     for r, p in enumerate(plan):
         if p["sfc_mask"]:
             qc(cs[r], 0, 1, False, p["sfc_mask"])
         if p["k1"] > p["k0"]:
             qc(cs[r], p["k0"], p["k1"], True, 0)
-    rows = [np.max([getattr(c, nm)[0] if nm != "qc_slp" else c.qc_slp for c in cs], axis=0) for nm in shard.SFC_FLAGS]
+    rows = [np.bitwise_or.reduce([getattr(c, nm)[0] if nm != "qc_slp" else c.qc_slp for c in cs], axis=0)
+            for nm in shard.SFC_FLAGS]
     out = base.copy()
     for r, p in enumerate(plan):
         c = cs[r]
         c.qc_u[0], c.qc_v[0], c.qc_t[0], c.qc_rh[0] = rows[0], rows[1], rows[2], rows[3]
         c.qc_slp[...] = rows[4]
         cons(c, 0, 1)
-        if p["sfc_mask"]:
+        if p["sfc_mask"] & 0x1f:
             oa(c, 0, 1, p["sfc_mask"] & 0x1f)
         if p["k1"] > p["k0"]:
             oa(c, p["k0"], p["k1"], 0)
@@ -184,3 +185,34 @@ def test_two_ranks_slab_sharding_over_gloo(tmp_path, oracle):
     oracle.oa_time(ref)
     for n in FIELDS:
         assert np.array_equal(got[n], getattr(ref, n)), n
+
+
+def test_allreduce_or_bit_planes_equal_bitwise_or():
+    """NCCL has no OR reduction: the three bits QC can set travel as 0/1 planes under MAX.  A stub
+    collective stands in for the second rank."""
+    import torch
+
+    rng = np.random.default_rng(8)
+    q0 = rng.integers(0, 1 << 13, 5000).astype(np.int32) | (rng.integers(0, 2, 5000).astype(np.int32) << 18)
+    bits = np.array([1 << b for b in shard.QC_FLAG_BITS], np.int32)
+    a = q0 | np.bitwise_or.reduce(bits[:, None] * rng.integers(0, 2, (3, 5000)).astype(np.int32), axis=0)
+    b = q0 | np.bitwise_or.reduce(bits[:, None] * rng.integers(0, 2, (3, 5000)).astype(np.int32), axis=0)
+
+    class ReduceOp:
+        MAX = "max"
+
+    class Stub:
+        def __init__(self, other):
+            self.other, self.ReduceOp = other, ReduceOp
+
+        def get_backend(self):
+            return "nccl"
+
+        def all_reduce(self, planes, op):
+            assert op == "max" and planes.dtype == torch.int8
+            o = torch.stack([(self.other >> k) & 1 for k in shard.QC_FLAG_BITS]).to(torch.int8)
+            planes.copy_(torch.maximum(planes, o))
+
+    t = torch.from_numpy(a.copy())
+    shard.allreduce_or(Stub(torch.from_numpy(b)), t)
+    np.testing.assert_array_equal(t.numpy(), a | b)
