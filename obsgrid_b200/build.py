@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "lib" / "libobsgrid_gpu.so"
-SOURCES = ["og_capi.cu", "og_oa.cu", "og_qc.cu", "og_bin.cu", "og_density.cu", "og_final.cu", "og_misc.cu"]
+SOURCES = ["og_capi.cu", "og_time.cu", "og_oa.cu", "og_qc.cu", "og_bin.cu", "og_density.cu", "og_final.cu", "og_misc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",

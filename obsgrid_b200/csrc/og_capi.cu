@@ -1,8 +1,9 @@
-// og_capi.cu -- the extern "C" surface of libobsgrid_gpu.so (include/obsgrid_gpu.h):
-// context, the per-slab drop-ins for the reference's three call sites, and the per-time
-// batched drivers that mirror the level x variable loops of proc_qc / proc_oa.
+// og_capi.cu -- the extern "C" surface of libobsgrid_gpu.so (include/obsgrid_gpu.h), part 1:
+// context and the per-slab drop-ins for the reference's call sites.  The per-time batched
+// drivers that mirror the level x variable loops of proc_qc / proc_oa are in og_time.cu.
 #include "og_ctx.h"
 #include "og_device.cuh"
+#include "og_capi_util.h"
 
 #include <math.h>
 #include <string.h>
@@ -14,15 +15,6 @@ using namespace og;
 // =========================================================================================
 // context
 // =========================================================================================
-// Every entry point makes the context's device current first: the caller may be a host thread
-// that has never touched CUDA (its current device is 0) while the context lives on another GPU.
-#define OG_BIND(c)                                                                          \
-    do {                                                                                      \
-        if ((c) && cudaSetDevice((c)->device) != cudaSuccess) {                               \
-            set_error("%s: cudaSetDevice(%d) failed", __func__, (c)->device);                 \
-            return OG_ERR_CUDA;                                                               \
-        }                                                                                     \
-    } while (0)
 
 extern "C" int og_abi_version(void) { return OG_ABI_VERSION; }
 extern "C" const char* og_last_error(void) { return og::last_error(); }
@@ -162,58 +154,6 @@ extern "C" int og_host_alloc(void** p, size_t bytes)
     return OG_OK;
 }
 extern "C" int og_host_free(void* p) { if (p) cudaFreeHost(p); return OG_OK; }
-
-// =========================================================================================
-// helpers
-// =========================================================================================
-#define REQUIRE(cond, msg)                                                                \
-    do { if (!(cond)) { set_error("%s: %s", __func__, msg); return OG_ERR_INVALID; } } while (0)
-
-
-
-template <class T>
-static int upload(og_ctx* c, const char* name, const T* host, size_t count, T** dev)
-{
-    OG_TRY(c->reserve_t(name, std::max<size_t>(count, 1), dev));
-    if (count) {
-        OG_CUDA(cudaMemcpyAsync(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-        c->stats.h2d_bytes += (int64_t)(count * sizeof(T));
-    }
-    return OG_OK;
-}
-template <class T>
-static int download(og_ctx* c, T* host, const T* dev, size_t count)
-{
-    if (count && host) {
-        OG_CUDA(cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
-        c->stats.d2h_bytes += (int64_t)(count * sizeof(T));
-    }
-    return OG_OK;
-}
-
-static inline int h_nint(float x) { return (int)lroundf(x); }
-
-// Radii actually used by the multi_scan loop of one slab (proc_oa.F90:641-707).
-// Returns OG_ERR_RADIUS when the reference would STOP (surface scan 1 below 4.5 cells).
-static int scan_radii(const int* radius_influence, float sfc_mult, float pressure, int* out,
-                      int* nscan)
-{
-    int rc = OG_OK, n = 0;
-    for (int num_scan = 1; num_scan <= OG_MAX_SCAN; ++num_scan) {
-        if (radius_influence[num_scan - 1] < 0) break;
-        const bool is_sfc = fabsf(pressure - 1001.0f) < 0.0001f;
-        volatile float sf = is_sfc ? sfc_mult : 1.00f;
-        volatile float r_scaled = (float)radius_influence[num_scan - 1] * sf;
-        volatile float r_scan1 = (float)radius_influence[0] * sf;
-        if (sfc_mult < 0.99999f && is_sfc) {
-            if (r_scan1 > 100.0f) { volatile float q = 100.0f / r_scan1; r_scaled = r_scaled * q; }
-            if (r_scaled < 4.5f) { if (num_scan == 1) rc = OG_ERR_RADIUS; break; }
-        }
-        out[n++] = h_nint(r_scaled);
-    }
-    *nscan = n;
-    return rc;
-}
 
 // =========================================================================================
 // per-slab drop-ins (host arrays, blocking)
@@ -577,958 +517,3 @@ extern "C" int og_qc_slab(og_ctx* c, int do_error_max, int do_buddy, const float
                           dx_km, qc_flag, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
 }
 
-// =========================================================================================
-// per-time drivers
-// =========================================================================================
-namespace {
-
-// One slab's selection rule ('get' / 'use' of proc_ob_access.F90:146-355 over the flat table)
-struct SelSlab {
-    const float* ob;     // value row of the level ([nrep])
-    const int* qc;       // flag row
-    const float* ob_t;   // DEWPOINT only: temperature row
-    const int* qc_t;
-    int kind;            // 0 plain variable, 1 DEWPOINT (ob = rh row)
-    int qc_max;
-    int ob_off;          // output offset (filled after the count pass)
-};
-
-struct SelDev {
-    const SelSlab* slabs;
-    int nrep, nchunk, iew, jns;
-    const float* xob; const float* yob;
-    const float* elev; const int* lt_rep;   // nullable (OA)
-    int* chunk_cnt;      // [nslab][nchunk] -> exclusive offsets after the scan
-    int* slab_n;         // [nslab]
-    float* ox; float* oy; float* oval; float* oelev; int* olt; int* oqc; int* oidx;
-};
-
-constexpr int SEL_THREADS = 256;
-
-__device__ __forceinline__ bool not_missing(float r) { return fabsf(fsub(r, OG_MISSING_R)) > 1.f; }
-
-// ob_access_module.F90:476-486 / proc_qc.F90:315-319.  LOG is evaluated in double and rounded
-// once (glibc's logf is not reproducible bit-for-bit on the device).
-__device__ __forceinline__ float dewpoint_dev(float t, float rh)
-{
-    const float Rv_over_L = fdiv(1.f, 5418.12f);
-    const float very_small_rh = 0.0001f;
-    float arg = (rh < very_small_rh) ? fdiv(very_small_rh, 100.f) : fdiv(rh, 100.f);
-    float lg = (float)log((double)arg);
-    return fdiv(1.f, fsub(fdiv(1.f, t), fmul(Rv_over_L, lg)));
-}
-
-__device__ __forceinline__ bool sel_pred(const SelDev& A, const SelSlab& S, int r)
-{
-    if (r >= A.nrep) return false;
-    bool ok = not_missing(S.ob[r]) && (S.qc[r] < S.qc_max);
-    if (S.kind == 1) ok = ok && not_missing(S.ob_t[r]) && (S.qc_t[r] < S.qc_max);
-    const float x = A.xob[r], y = A.yob[r];   // proc_ob_access.F90:231-234
-    ok = ok && (x >= 2.f) && (x <= (float)(A.iew - 1)) && (y >= 2.f) && (y <= (float)(A.jns - 1));
-    return ok;
-}
-
-__global__ void __launch_bounds__(SEL_THREADS) sel_count_kernel(SelDev A)
-{
-    const SelSlab& S = A.slabs[blockIdx.y];
-    const int r = blockIdx.x * SEL_THREADS + threadIdx.x;
-    const int c = __syncthreads_count(sel_pred(A, S, r) ? 1 : 0);
-    if (threadIdx.x == 0) A.chunk_cnt[(size_t)blockIdx.y * A.nchunk + blockIdx.x] = c;
-}
-
-// per slab: exclusive scan of its chunk counts; total -> slab_n
-__global__ void __launch_bounds__(1024) sel_scan_kernel(SelDev A)
-{
-    int* cnt = A.chunk_cnt + (size_t)blockIdx.x * A.nchunk;
-    const int n = A.nchunk;
-    __shared__ int s_sum[1024];
-    const int per = (n + 1023) / 1024;
-    const int b = threadIdx.x * per, e = min(b + per, n);
-    int s = 0;
-    for (int i = b; i < e; ++i) s += cnt[i];
-    s_sum[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        int v = (threadIdx.x >= o) ? s_sum[threadIdx.x - o] : 0;
-        __syncthreads();
-        s_sum[threadIdx.x] += v;
-        __syncthreads();
-    }
-    int run = s_sum[threadIdx.x] - s;
-    for (int i = b; i < e; ++i) { int v = cnt[i]; cnt[i] = run; run += v; }
-    if (threadIdx.x == 1023) A.slab_n[blockIdx.x] = s_sum[1023];
-}
-
-__global__ void __launch_bounds__(SEL_THREADS) sel_scatter_kernel(SelDev A)
-{
-    const SelSlab& S = A.slabs[blockIdx.y];
-    const int r = blockIdx.x * SEL_THREADS + threadIdx.x;
-    const bool p = sel_pred(A, S, r);
-    __shared__ int s_w[SEL_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned m = __ballot_sync(0xffffffffu, p);
-    if (lane == 0) s_w[warp] = __popc(m);
-    __syncthreads();
-    if (!p) return;
-    int woff = 0;
-    for (int w = 0; w < warp; ++w) woff += s_w[w];
-    const int pos = S.ob_off + A.chunk_cnt[(size_t)blockIdx.y * A.nchunk + blockIdx.x] + woff +
-                    __popc(m & ((1u << lane) - 1u));
-    A.ox[pos] = A.xob[r];
-    A.oy[pos] = A.yob[r];
-    A.oval[pos] = (S.kind == 1) ? dewpoint_dev(S.ob_t[r], S.ob[r]) : S.ob[r];
-    if (A.oqc) A.oqc[pos] = S.qc[r];
-    if (A.oidx) A.oidx[pos] = r;
-    if (A.oelev) A.oelev[pos] = A.elev[r];
-    if (A.olt) A.olt[pos] = A.lt_rep[r];
-}
-
-// 'put' (proc_ob_access.F90:381-403): flags back into the table rows
-struct PutSlab { int* qc; int ob_off; int n; int blk_off; };
-__global__ void put_kernel(const PutSlab* slabs, int ns, const int* oqc, const int* oidx)
-{
-    const PutSlab S = slabs[slab_of_block(slabs, ns, (int)blockIdx.x)];
-    const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
-    if (li >= S.n) return;
-    // the RH row is written by two slabs (RH and DEWPOINT): each ORs its bits in
-    atomicOr(&S.qc[oidx[S.ob_off + li]], oqc[S.ob_off + li]);
-}
-
-// qc_consistency (qc0_module.F90:371-404) on the table rows of the levels in range;
-// contains_2n(q, 2**n) == bit test for 0 <= q < 2**19 (tests/test_oracle_kat.py).
-__global__ void consistency_kernel(int* qc_u, int* qc_v, const int* qc_t, int* qc_rh, size_t n)
-{
-    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const int u = qc_u[q], v = qc_v[q];
-    if (u > v) qc_v[q] = u;
-    if (v > u) qc_u[q] = v;
-    const int t = qc_t[q];
-    int rh = qc_rh[q];
-    const int rh0 = rh;
-    if ((t & OG_FAILS_ERROR_MAX) && !(rh0 & OG_FAILS_ERROR_MAX)) rh = qc_add_flag(rh, OG_FAILS_ERROR_MAX);
-    if ((t & OG_FAILS_BUDDY_CHECK) && !(rh0 & OG_FAILS_BUDDY_CHECK)) rh = qc_add_flag(rh, OG_FAILS_BUDDY_CHECK);
-    qc_rh[q] = rh;
-}
-
-__global__ void scale_kernel(const float* __restrict__ a, float* __restrict__ o, size_t n, float f)
-{
-    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n) o[q] = fmul(a[q], f);
-}
-__global__ void dewfield_kernel(const float* __restrict__ t, const float* __restrict__ rh,
-                                float* __restrict__ o, size_t n)
-{
-    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n) o[q] = dewpoint_dev(t[q], rh[q]);
-}
-// mixing_ratio's in-place clamp of the first-guess RH (final_analysis_module.F90:1055) on the
-// x-fastest copy: rh(1:jns-1, 1:iew-1, :) = MIN(MAX(rh, 1.), 100.)
-__global__ void clamp_fg_rh_kernel(float* rh, int iew, int jns, int nlev)
-{
-    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t per = (size_t)iew * jns;
-    if (q >= per * nlev) return;
-    int i = (int)((q % per) % iew), j = (int)((q % per) / iew);
-    if (i < iew - 1 && j < jns - 1) rh[q] = fminf(fmaxf(rh[q], 1.f), 100.f);
-}
-
-inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
-
-// Device-resident view of one time (every pointer a device pointer, reference layouts).
-struct TimeDev {
-    int iew, jns, kbu, nrep;
-    float dx_km;
-    const float* pressure;   // host
-    float *t, *u, *v, *rh, *slp;
-    const float *xob, *yob, *lon, *elev;
-    const float *ob_u, *ob_v, *ob_t, *ob_rh, *ob_slp;
-    int *qc_u, *qc_v, *qc_t, *qc_rh, *qc_slp;
-    float* tobbox = nullptr;   // optional (surface FDDA): (jns,iew) observation density, in/out
-    float* odis = nullptr;     //                          (jns,iew) distance to the nearest observed box
-};
-
-// proc_qc.F90:416-417: tobbox = tobbox / 5. ; WHERE ( tobbox .LT. 1 ) tobbox = 0
-__global__ void tobbox_average_kernel(float* __restrict__ tb, size_t n)
-{
-    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const float v = fdiv(tb[q], 5.f);
-    tb[q] = (v < 1.f) ? 0.f : v;
-}
-
-// Run the three selection kernels for `sel` and return per-slab counts / offsets on the host.
-int run_selection(og_ctx* c, const TimeDev& T, std::vector<SelSlab>& sel, bool qc_outputs,
-                  const int* lt_rep, SelDev& A, std::vector<int>& n_out, int& total)
-{
-    const int ns = (int)sel.size();
-    const int nchunk = (T.nrep + SEL_THREADS - 1) / SEL_THREADS;
-    A = SelDev{};
-    A.nrep = T.nrep; A.nchunk = nchunk; A.iew = T.iew; A.jns = T.jns;
-    A.xob = T.xob; A.yob = T.yob; A.elev = qc_outputs ? T.elev : nullptr; A.lt_rep = lt_rep;
-    SelSlab* d_sel;
-    OG_TRY(c->reserve_t("sel.slabs", (size_t)ns, &d_sel));
-    OG_TRY(c->reserve_t("sel.chunk", (size_t)ns * std::max(nchunk, 1), &A.chunk_cnt));
-    OG_TRY(c->reserve_t("sel.n", (size_t)ns, &A.slab_n));
-    A.slabs = d_sel;
-    n_out.assign(ns, 0);
-    total = 0;
-    if (T.nrep == 0) return OG_OK;
-    OG_TRY(c->put_small(d_sel, sel.data(), sizeof(SelSlab) * ns));
-    dim3 g(nchunk, ns);
-    sel_count_kernel<<<g, SEL_THREADS, 0, c->stream>>>(A);
-    sel_scan_kernel<<<ns, 1024, 0, c->stream>>>(A);
-    c->count_launch(2);
-    void* h_n = nullptr;
-    OG_TRY(c->get_small(A.slab_n, sizeof(int) * ns, &h_n));
-    OG_CUDA(cudaStreamSynchronize(c->stream));
-    memcpy(n_out.data(), h_n, sizeof(int) * ns);
-    for (int s = 0; s < ns; ++s) { sel[s].ob_off = total; total += n_out[s]; }
-    OG_TRY(c->put_small(d_sel, sel.data(), sizeof(SelSlab) * ns));
-    const size_t tot = (size_t)std::max(total, 1);
-    OG_TRY(c->reserve_t("sel.x", tot, &A.ox));
-    OG_TRY(c->reserve_t("sel.y", tot, &A.oy));
-    OG_TRY(c->reserve_t("sel.val", tot, &A.oval));
-    if (qc_outputs) {
-        OG_TRY(c->reserve_t("sel.elev", tot, &A.oelev));
-        OG_TRY(c->reserve_t("sel.lt", tot, &A.olt));
-        OG_TRY(c->reserve_t("sel.qc", tot, &A.oqc));
-        OG_TRY(c->reserve_t("sel.idx", tot, &A.oidx));
-    }
-    sel_scatter_kernel<<<g, SEL_THREADS, 0, c->stream>>>(A);
-    c->count_launch();
-    OG_CUDA(cudaGetLastError());
-    return OG_OK;
-}
-
-// A set of levels to process in one batch, each with its own variable mask (0: the mask of the
-// stage parameters).  The contiguous range [k0,k1) is the common case; the (level, variable)
-// sharding of obsgrid_b200/shard.py hands a rank "some surface slabs + a run of upper levels".
-struct LevelItems {
-    std::vector<int> k, mask;
-    int size() const { return (int)k.size(); }
-};
-static LevelItems range_items(int k0, int k1)
-{
-    LevelItems L;
-    for (int k = k0; k < k1; ++k) { L.k.push_back(k); L.mask.push_back(0); }
-    return L;
-}
-// f(first_slot, first_level, count) for every maximal run of consecutive levels
-template <class F> static int for_each_run(const LevelItems& L, F f)
-{
-    for (int i = 0; i < L.size();) {
-        int j = i + 1;
-        while (j < L.size() && L.k[j] == L.k[j - 1] + 1) ++j;
-        OG_TRY(f(i, L.k[i], j - i));
-        i = j;
-    }
-    return OG_OK;
-}
-
-// ---- OA over a set of levels of a device-resident time -----------------------------------
-int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, const LevelItems& L)
-{
-    const int iew = T.iew, jns = T.jns, nlev = L.size();
-    const size_t per = (size_t)iew * jns;
-    if (nlev <= 0) return OG_OK;
-    // x-fastest working copies (yx2xy of get_background_for_oa, oa_module.F90:634-676)
-    float *w_t, *w_u, *w_v, *w_rh, *w_slp, *b_u, *b_v;
-    OG_TRY(c->reserve_t("oa.w_t", per * nlev, &w_t));
-    OG_TRY(c->reserve_t("oa.w_u", per * nlev, &w_u));
-    OG_TRY(c->reserve_t("oa.w_v", per * nlev, &w_v));
-    OG_TRY(c->reserve_t("oa.w_rh", per * nlev, &w_rh));
-    OG_TRY(c->reserve_t("oa.w_slp", per, &w_slp));
-    OG_TRY(c->reserve_t("oa.b_u", per * nlev, &b_u));
-    OG_TRY(c->reserve_t("oa.b_v", per * nlev, &b_v));
-    bool has_sfc = false;
-    for (int k : L.k) has_sfc = has_sfc || (k == 0);
-    OG_TRY(for_each_run(L, [&](int slot, int k, int n) -> int {
-        const size_t lo = per * (size_t)k, so = per * (size_t)slot;
-        OG_TRY(transpose_levels(c, T.t + lo, w_t + so, jns, iew, n));
-        // u, v twice: the pre-analysis winds of each level feed the banana scheme (proc_oa.F90:376-386)
-        OG_TRY(transpose_levels(c, T.u + lo, w_u + so, jns, iew, n, b_u + so));
-        OG_TRY(transpose_levels(c, T.v + lo, w_v + so, jns, iew, n, b_v + so));
-        OG_TRY(transpose_levels(c, T.rh + lo, w_rh + so, jns, iew, n));
-        return OG_OK;
-    }));
-    if (has_sfc) OG_TRY(transpose_levels(c, T.slp, w_slp, jns, iew, 1));
-    if (p->clamp_fg_rh) {
-        clamp_fg_rh_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_rh, iew, jns, nlev);
-        c->count_launch();
-    }
-
-    // slabs in the reference's loop order: level, then UU VV TT RH PMSL
-    const int qc_max = std::min(OG_FAILS_ERROR_MAX, OG_FAILS_BUDDY_CHECK); // proc_oa.F90:462
-    std::vector<SelSlab> sel;
-    OaBatch b;
-    b.iew = iew; b.jns = jns; b.crsdot = 1; b.dxd = T.dx_km;
-    b.use_first_guess = p->use_first_guess; b.scale_rh = p->scale_cressman_rh_decreases;
-    b.smooth_type = p->smooth_type; b.given_diff = false; b.clean_rh = true;
-    int rc_radius = OG_OK;
-    for (int slot = 0; slot < nlev; ++slot) {
-        const int k = L.k[slot];
-        const int vmask = L.mask[slot] ? L.mask[slot] : p->var_mask;
-        if (p->surface_only && k > 0) continue; // proc_oa.F90:365
-        const size_t row = (size_t)k * T.nrep, lev = per * (size_t)slot;
-        for (int ivar = 1; ivar <= 5; ++ivar) {
-            if (ivar == 5 && k > 0) continue;
-            if (vmask && !(vmask & (1 << (ivar - 1)))) continue;
-            OaSlabHost s;
-            SelSlab q{};
-            q.kind = 0; q.qc_max = qc_max;
-            switch (ivar) {
-            case 1: s.g = w_u + lev; q.ob = T.ob_u + row; q.qc = T.qc_u + row; break;
-            case 2: s.g = w_v + lev; q.ob = T.ob_v + row; q.qc = T.qc_v + row; break;
-            case 3: s.g = w_t + lev; q.ob = T.ob_t + row; q.qc = T.qc_t + row; break;
-            case 4: s.g = w_rh + lev; q.ob = T.ob_rh + row; q.qc = T.qc_rh + row; break;
-            default: s.g = w_slp; q.ob = T.ob_slp; q.qc = T.qc_slp; break;
-            }
-            s.ub = b_u + lev; s.vb = b_v + lev;
-            s.var = ivar; s.pressure = T.pressure[k]; s.scale = (ivar == 5) ? 100.f : 1.f;
-            const int psfc[5] = {p->smooth_sfc_wind, p->smooth_sfc_wind, p->smooth_sfc_temp, p->smooth_sfc_rh, p->smooth_sfc_slp};
-            const int pup[5] = {p->smooth_upper_wind, p->smooth_upper_wind, p->smooth_upper_temp, p->smooth_upper_rh, 0};
-            s.passes = (k == 0) ? psfc[ivar - 1] : pup[ivar - 1];
-            int r = scan_radii(p->radius_influence, p->radius_influence_sfc_mult, s.pressure, s.radius, &s.nscan);
-            if (r != OG_OK) rc_radius = r;
-            b.slabs.push_back(s);
-            sel.push_back(q);
-        }
-    }
-    SelDev SA;
-    std::vector<int> ncount;
-    int total = 0;
-    OG_TRY(run_selection(c, T, sel, false, nullptr, SA, ncount, total));
-    for (size_t s = 0; s < b.slabs.size(); ++s) { b.slabs[s].n = ncount[s]; b.slabs[s].ob_off = sel[s].ob_off; }
-    b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval;
-    OG_TRY(oa_run_batch(c, b));
-    // put_background_from_oa (oa_module.F90:828-870): back to the (jns,iew,k) layout
-    OG_TRY(for_each_run(L, [&](int slot, int k, int n) -> int {
-        const size_t lo = per * (size_t)k, so = per * (size_t)slot;
-        OG_TRY(transpose_levels(c, w_t + so, T.t + lo, iew, jns, n));
-        OG_TRY(transpose_levels(c, w_u + so, T.u + lo, iew, jns, n));
-        OG_TRY(transpose_levels(c, w_v + so, T.v + lo, iew, jns, n));
-        OG_TRY(transpose_levels(c, w_rh + so, T.rh + lo, iew, jns, n));
-        return OG_OK;
-    }));
-    if (has_sfc) OG_TRY(transpose_levels(c, w_slp, T.slp, iew, jns, 1));
-    if (rc_radius != OG_OK) set_error("surface scan-1 radius below 4.5 cells (proc_oa.F90:694-703)");
-    return rc_radius;
-}
-int oa_time_core(og_ctx* c, const TimeDev& T, const og_oa_params* p, int k0, int k1)
-{
-    return oa_time_core(c, T, p, range_items(k0, k1));
-}
-
-// ---- QC over a set of levels of a device-resident time ------------------------------------
-// run_consistency: qc_consistency on the levels whose every variable is checked here (mask 0).
-int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, const LevelItems& L,
-                 int run_consistency)
-{
-    const int iew = T.iew, jns = T.jns, nlev = L.size();
-    const size_t per = (size_t)iew * jns;
-    if (nlev <= 0) return OG_OK;
-    float *w_t, *w_u, *w_v, *w_rh, *w_slp, *w_dew;
-    OG_TRY(c->reserve_t("qc.w_t", per * nlev, &w_t));
-    OG_TRY(c->reserve_t("qc.w_u", per * nlev, &w_u));
-    OG_TRY(c->reserve_t("qc.w_v", per * nlev, &w_v));
-    OG_TRY(c->reserve_t("qc.w_rh", per * nlev, &w_rh));
-    OG_TRY(c->reserve_t("qc.w_slp", per, &w_slp));
-    OG_TRY(for_each_run(L, [&](int slot, int k, int n) -> int {
-        const size_t lo = per * (size_t)k, so = per * (size_t)slot;
-        OG_TRY(transpose_levels(c, T.t + lo, w_t + so, jns, iew, n));
-        OG_TRY(transpose_levels(c, T.u + lo, w_u + so, jns, iew, n));
-        OG_TRY(transpose_levels(c, T.v + lo, w_v + so, jns, iew, n));
-        OG_TRY(transpose_levels(c, T.rh + lo, w_rh + so, jns, iew, n));
-        return OG_OK;
-    }));
-    bool has_sfc = false;
-    for (int k : L.k) has_sfc = has_sfc || (k == 0);
-    if (has_sfc) {
-        OG_TRY(transpose_levels(c, T.slp, w_slp, jns, iew, 1));
-        scale_kernel<<<nblk(per), 256, 0, c->stream>>>(w_slp, w_slp, per, 100.f); // proc_qc.F90:296
-        c->count_launch();
-    }
-    int* lt_rep;
-    OG_TRY(c->reserve_t("qc.lt_rep", (size_t)std::max(T.nrep, 1), &lt_rep));
-    OG_TRY(local_time_device(c, p->time_hhmmss / 100, T.lon, T.nrep, lt_rep)); // proc_qc.F90:344
-
-    // One batch for every slab of the level range.  The reference runs DEWPOINT (ivar 7) after RH
-    // (ivar 4) of the same level and hands it RH's output flags (ob_access_module.F90:466-487,
-    // :771-774); here both slabs start from the incoming flags and 'put' ORs their results into the
-    // row.  That is the same value: selection only asks qc < 2**20, which no flag set here can
-    // change, no test reads the flags, and modify_qc_flag / add_to_qc_flag set one bit of a
-    // non-negative integer (qc0_module.F90:27-31, :55-72), so (q | rh_bits) | dew_bits either way.
-    {
-        if (p->qc_dewpoint) {
-            OG_TRY(c->reserve_t("qc.w_dew", per * nlev, &w_dew));
-            dewfield_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_t, w_rh, w_dew, per * nlev);
-            c->count_launch();
-        }
-        std::vector<SelSlab> sel;
-        QcBatch b;
-        b.iew = iew; b.jns = jns; b.dx_km = T.dx_km; b.buddy_weight = p->buddy_weight;
-        b.do_error_max = p->qc_test_error_max; b.do_buddy = p->qc_test_buddy;
-        std::vector<PutSlab> puts;
-        std::vector<int> slab_level;
-        for (int slot = 0; slot < nlev; ++slot) {
-            const int k = L.k[slot];
-            const int vmask = L.mask[slot] ? L.mask[slot] : p->var_mask;
-            const size_t row = (size_t)k * T.nrep, lev = per * (size_t)slot;
-            const float pk = T.pressure[k];
-            for (int ivar = 1; ivar <= 7; ++ivar) {
-                if (ivar == 7 && !p->qc_dewpoint) continue;
-                if (ivar == 6) continue;                      // qc_psfc = .FALSE.
-                if (k > 0 && ivar == 5) continue;             // proc_qc.F90:255
-                if (vmask && !(vmask & (1 << (ivar - 1)))) continue;
-                QcSlabHost s; SelSlab q{}; PutSlab pt{};
-                q.kind = 0; q.qc_max = 1 << 20;               // proc_qc.F90:329
-                s.var = ivar; s.pressure = pk;
-                switch (ivar) {
-                case 1: s.g = w_u + lev; q.ob = T.ob_u + row; q.qc = T.qc_u + row; pt.qc = T.qc_u + row;
-                        s.max_error = p->max_error_uv; s.max_buddy = p->max_buddy_uv; break;
-                case 2: s.g = w_v + lev; q.ob = T.ob_v + row; q.qc = T.qc_v + row; pt.qc = T.qc_v + row;
-                        s.max_error = p->max_error_uv; s.max_buddy = p->max_buddy_uv; break;
-                case 3: s.g = w_t + lev; q.ob = T.ob_t + row; q.qc = T.qc_t + row; pt.qc = T.qc_t + row;
-                        s.max_error = p->max_error_t; s.max_buddy = p->max_buddy_t; break;
-                case 4: s.g = w_rh + lev; q.ob = T.ob_rh + row; q.qc = T.qc_rh + row; pt.qc = T.qc_rh + row;
-                        if (pk == 300.f) s.max_error = p->max_error_rh * 2.f;        // proc_qc.F90:282-288
-                        else if (pk < 300.f) s.max_error = p->max_error_rh * 3.f;
-                        else s.max_error = p->max_error_rh;
-                        s.max_buddy = p->max_buddy_rh; break;
-                case 5: s.g = w_slp; q.ob = T.ob_slp; q.qc = T.qc_slp; pt.qc = T.qc_slp;
-                        s.max_error = p->max_error_p; s.max_buddy = p->max_buddy_p; break;
-                default: s.g = w_dew + lev; q.kind = 1; q.ob = T.ob_rh + row; q.qc = T.qc_rh + row;
-                        q.ob_t = T.ob_t + row; q.qc_t = T.qc_t + row; pt.qc = T.qc_rh + row;
-                        s.max_error = p->max_error_dewpoint; s.max_buddy = p->max_buddy_dewpoint; break;
-                }
-                b.slabs.push_back(s); sel.push_back(q); puts.push_back(pt); slab_level.push_back(k);
-            }
-        }
-        if (!b.slabs.empty()) {
-            SelDev SA;
-            std::vector<int> ncount;
-            int total = 0, max_n = 0, nblk_ob = 0;
-            OG_TRY(run_selection(c, T, sel, true, lt_rep, SA, ncount, total));
-            for (size_t s = 0; s < b.slabs.size(); ++s) {
-                b.slabs[s].n = ncount[s]; b.slabs[s].ob_off = sel[s].ob_off;
-                puts[s].n = ncount[s]; puts[s].ob_off = sel[s].ob_off;
-                puts[s].blk_off = nblk_ob; nblk_ob += (ncount[s] + 255) / 256;
-                max_n = std::max(max_n, ncount[s]);
-            }
-            b.total_obs = total; b.xob = SA.ox; b.yob = SA.oy; b.val = SA.oval; b.elev = SA.oelev;
-            b.local_time = SA.olt; b.qc = SA.oqc;
-            if (T.tobbox)   // proc_qc.F90:349-351: every surface variable's obs add to the density
-                for (size_t s = 0; s < b.slabs.size(); ++s)
-                    if (slab_level[s] == 0)
-                        OG_TRY(ob_density_device(c, SA.ox + sel[s].ob_off, SA.oy + sel[s].ob_off, T.dx_km,
-                                                 ncount[s], T.tobbox, iew, jns));
-            OG_TRY(qc_run_batch(c, b));
-            if (max_n > 0) {
-                PutSlab* d_put;
-                OG_TRY(c->reserve_t("qc.put", puts.size(), &d_put));
-                OG_TRY(c->put_small(d_put, puts.data(), sizeof(PutSlab) * puts.size()));
-                put_kernel<<<nblk_ob, 256, 0, c->stream>>>(d_put, (int)puts.size(), SA.oqc, SA.oidx);
-                c->count_launch();
-            }
-        }
-    }
-    if (T.tobbox && T.odis && has_sfc) {   // proc_qc.F90:412-420
-        tobbox_average_kernel<<<nblk(per), 256, 0, c->stream>>>(T.tobbox, per);
-        c->count_launch();
-        OG_TRY(obs_distance_device(c, T.tobbox, T.odis, iew, jns, T.dx_km));
-    }
-    if (run_consistency && T.nrep > 0) {
-        LevelItems whole;
-        for (int i = 0; i < nlev; ++i)
-            if (L.mask[i] == 0) { whole.k.push_back(L.k[i]); whole.mask.push_back(0); }
-        OG_TRY(for_each_run(whole, [&](int, int k, int nl) -> int {
-            const size_t n = (size_t)nl * T.nrep, off = (size_t)k * T.nrep;
-            consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(T.qc_u + off, T.qc_v + off, T.qc_t + off, T.qc_rh + off, n);
-            c->count_launch();
-            return OG_OK;
-        }));
-    }
-    OG_CUDA(cudaGetLastError());
-    return OG_OK;
-}
-int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int k1, int run_consistency)
-{
-    return qc_time_core(c, T, p, range_items(k0, k1), run_consistency);
-}
-
-int check_desc(const og_time_desc* d, int k0, int k1, bool qc)
-{
-    if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
-    if (d->iew < 4 || d->jns < 4 || d->kbu < 1 || d->nrep < 0) { set_error("bad dimensions in og_time_desc"); return OG_ERR_INVALID; }
-    if (k0 < 0 || k1 > d->kbu || k0 > k1) { set_error("bad level range [%d,%d) of %d", k0, k1, d->kbu); return OG_ERR_INVALID; }
-    if (!d->pressure || !d->t || !d->u || !d->v || !d->rh || !d->slp) { set_error("null field pointer in og_time_desc"); return OG_ERR_INVALID; }
-    if (d->nrep > 0 && (!d->xob || !d->yob || !d->ob_u || !d->ob_v || !d->ob_t || !d->ob_rh || !d->ob_slp ||
-                        !d->qc_u || !d->qc_v || !d->qc_t || !d->qc_rh || !d->qc_slp)) { set_error("null observation pointer in og_time_desc"); return OG_ERR_INVALID; }
-    if (qc && d->nrep > 0 && (!d->lon || !d->elev)) { set_error("QC needs lon and elev"); return OG_ERR_INVALID; }
-    return OG_OK;
-}
-
-TimeDev view_of(const og_time_desc* d)
-{
-    TimeDev T{};
-    T.iew = d->iew; T.jns = d->jns; T.kbu = d->kbu; T.nrep = d->nrep; T.dx_km = d->dx_km;
-    T.pressure = d->pressure;
-    T.t = d->t; T.u = d->u; T.v = d->v; T.rh = d->rh; T.slp = d->slp;
-    T.xob = d->xob; T.yob = d->yob; T.lon = d->lon; T.elev = d->elev;
-    T.ob_u = d->ob_u; T.ob_v = d->ob_v; T.ob_t = d->ob_t; T.ob_rh = d->ob_rh; T.ob_slp = d->ob_slp;
-    T.qc_u = d->qc_u; T.qc_v = d->qc_v; T.qc_t = d->qc_t; T.qc_rh = d->qc_rh; T.qc_slp = d->qc_slp;
-    return T;
-}
-
-// Host -> device mirror of the level range [k0,k1) of a time.  Device arrays keep the full
-// [kbu] extent so that row offsets match; only the rows in range are copied.
-int mirror_in(og_ctx* c, const og_time_desc* d, int k0, int k1, bool qc, TimeDev& T)
-{
-    T = view_of(d);
-    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
-    auto up_lev = [&](const char* name, const float* h, float** dev) -> int {
-        OG_TRY(c->reserve_t(name, per * d->kbu, dev));
-        OG_CUDA(cudaMemcpyAsync(*dev + per * k0, h + per * k0, per * nlev * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-        c->stats.h2d_bytes += (int64_t)(per * nlev * sizeof(float));
-        return OG_OK;
-    };
-    OG_TRY(up_lev("m.t", d->t, &T.t));
-    OG_TRY(up_lev("m.u", d->u, &T.u));
-    OG_TRY(up_lev("m.v", d->v, &T.v));
-    OG_TRY(up_lev("m.rh", d->rh, &T.rh));
-    OG_TRY(upload(c, "m.slp", d->slp, k0 == 0 ? per : 0, &T.slp));
-    float* f; int* q;
-    OG_TRY(upload(c, "m.x", d->xob, nrep, &f)); T.xob = f;
-    OG_TRY(upload(c, "m.y", d->yob, nrep, &f)); T.yob = f;
-    if (qc) {
-        OG_TRY(upload(c, "m.lon", d->lon, nrep, &f)); T.lon = f;
-        OG_TRY(upload(c, "m.elev", d->elev, nrep, &f)); T.elev = f;
-    }
-    auto up_row = [&](const char* name, const void* h, void** dev) -> int {
-        OG_TRY(c->reserve(name, std::max<size_t>(nrep * d->kbu, 1) * 4, dev));
-        if (nrep * nlev) {
-            OG_CUDA(cudaMemcpyAsync((char*)*dev + nrep * k0 * 4, (const char*)h + nrep * k0 * 4, nrep * nlev * 4, cudaMemcpyHostToDevice, c->stream));
-            c->stats.h2d_bytes += (int64_t)(nrep * nlev * 4);
-        }
-        return OG_OK;
-    };
-    void* v;
-    OG_TRY(up_row("m.ob_u", d->ob_u, &v)); T.ob_u = (const float*)v;
-    OG_TRY(up_row("m.ob_v", d->ob_v, &v)); T.ob_v = (const float*)v;
-    OG_TRY(up_row("m.ob_t", d->ob_t, &v)); T.ob_t = (const float*)v;
-    OG_TRY(up_row("m.ob_rh", d->ob_rh, &v)); T.ob_rh = (const float*)v;
-    OG_TRY(up_row("m.qc_u", d->qc_u, &v)); T.qc_u = (int*)v;
-    OG_TRY(up_row("m.qc_v", d->qc_v, &v)); T.qc_v = (int*)v;
-    OG_TRY(up_row("m.qc_t", d->qc_t, &v)); T.qc_t = (int*)v;
-    OG_TRY(up_row("m.qc_rh", d->qc_rh, &v)); T.qc_rh = (int*)v;
-    OG_TRY(upload(c, "m.ob_slp", d->ob_slp, k0 == 0 ? nrep : 0, &f)); T.ob_slp = f;
-    OG_TRY(upload(c, "m.qc_slp", d->qc_slp, k0 == 0 ? nrep : 0, &q)); T.qc_slp = q;
-    return OG_OK;
-}
-
-} // namespace
-
-extern "C" int og_dev_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* p, int k0, int k1)
-{
-    OG_BIND(c);
-    REQUIRE(c && p, "null argument");
-    OG_TRY(check_desc(d, k0, k1, false));
-    return oa_time_core(c, view_of(d), p, k0, k1);
-}
-
-extern "C" int og_dev_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p, int k0,
-                              int k1, int run_consistency)
-{
-    OG_BIND(c);
-    REQUIRE(c && p, "null argument");
-    OG_TRY(check_desc(d, k0, k1, true));
-    return qc_time_core(c, view_of(d), p, k0, k1, run_consistency);
-}
-
-// (level, variable mask) item lists: one batch over an arbitrary set of slabs of a device-resident
-// time -- what a rank of the level x variable sharding owns (obsgrid_b200/shard.py).
-static int items_of(const og_time_desc* d, const int* levels, const int* var_masks, int n, LevelItems& L)
-{
-    if (n < 0 || (n > 0 && !levels)) { set_error("bad level item list"); return OG_ERR_INVALID; }
-    for (int i = 0; i < n; ++i) {
-        if (levels[i] < 0 || levels[i] >= d->kbu || (i > 0 && levels[i] <= levels[i - 1])) {
-            set_error("level items must be strictly increasing levels of the time"); return OG_ERR_INVALID;
-        }
-        const int m = var_masks ? var_masks[i] : 0;
-        if (m < 0 || m > 0x7f) { set_error("bad variable mask %d", m); return OG_ERR_INVALID; }
-        L.k.push_back(levels[i]); L.mask.push_back(m);
-    }
-    return OG_OK;
-}
-
-extern "C" int og_dev_qc_time_items(og_ctx* c, const og_time_desc* d, const og_qc_params* p,
-                                    const int* levels, const int* var_masks, int nitems, int run_consistency)
-{
-    OG_BIND(c);
-    REQUIRE(c && p, "null argument");
-    OG_TRY(check_desc(d, 0, d ? d->kbu : 0, true));
-    LevelItems L;
-    OG_TRY(items_of(d, levels, var_masks, nitems, L));
-    return qc_time_core(c, view_of(d), p, L, run_consistency);
-}
-
-extern "C" int og_dev_oa_time_items(og_ctx* c, const og_time_desc* d, const og_oa_params* p,
-                                    const int* levels, const int* var_masks, int nitems)
-{
-    OG_BIND(c);
-    REQUIRE(c && p, "null argument");
-    OG_TRY(check_desc(d, 0, d ? d->kbu : 0, false));
-    LevelItems L;
-    OG_TRY(items_of(d, levels, var_masks, nitems, L));
-    return oa_time_core(c, view_of(d), p, L);
-}
-
-// qc_consistency (qc0_module.F90:371-404) on its own: the step between the QC and OA phases when
-// the variables of a level were checked by different ranks (obsgrid_b200/shard.py).
-extern "C" int og_dev_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k1)
-{
-    OG_BIND(c);
-    REQUIRE(c, "null context");
-    OG_TRY(check_desc(d, k0, k1, false));
-    if (k1 == k0 || d->nrep == 0) return OG_OK;
-    const size_t n = (size_t)(k1 - k0) * d->nrep, off = (size_t)k0 * d->nrep;
-    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(d->qc_u + off, d->qc_v + off, d->qc_t + off, d->qc_rh + off, n);
-    c->count_launch();
-    OG_CUDA(cudaGetLastError());
-    return OG_OK;
-}
-
-extern "C" int og_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k1)
-{
-    OG_BIND(c);
-    REQUIRE(c, "null context");
-    OG_TRY(check_desc(d, k0, k1, false));
-    if (k1 == k0 || d->nrep == 0) return OG_OK;
-    const size_t n = (size_t)(k1 - k0) * d->nrep, off = (size_t)k0 * d->nrep;
-    int* dev[4];
-    int* host[4] = {d->qc_u + off, d->qc_v + off, d->qc_t + off, d->qc_rh + off};
-    const char* names[4] = {"cons.u", "cons.v", "cons.t", "cons.rh"};
-    for (int i = 0; i < 4; ++i) OG_TRY(upload(c, names[i], host[i], n, &dev[i]));
-    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(dev[0], dev[1], dev[2], dev[3], n);
-    c->count_launch();
-    OG_CUDA(cudaGetLastError());
-    OG_TRY(download(c, host[0], dev[0], n));
-    OG_TRY(download(c, host[1], dev[1], n));
-    OG_TRY(download(c, host[3], dev[3], n));
-    OG_CUDA(cudaStreamSynchronize(c->stream));
-    return OG_OK;
-}
-
-extern "C" int og_oa_time(og_ctx* c, const og_time_desc* d, const og_oa_params* p, int k0, int k1)
-{
-    OG_BIND(c);
-    REQUIRE(c && p, "null argument");
-    OG_TRY(check_desc(d, k0, k1, false));
-    if (k1 == k0) return OG_OK;
-    TimeDev T;
-    OG_TRY(mirror_in(c, d, k0, k1, false, T));
-    int rc = oa_time_core(c, T, p, k0, k1);
-    if (rc != OG_OK && rc != OG_ERR_RADIUS) return rc;
-    const size_t per = (size_t)d->iew * d->jns, nlev = (size_t)(k1 - k0), lo = per * k0;
-    OG_TRY(download(c, d->t + lo, T.t + lo, per * nlev));
-    OG_TRY(download(c, d->u + lo, T.u + lo, per * nlev));
-    OG_TRY(download(c, d->v + lo, T.v + lo, per * nlev));
-    OG_TRY(download(c, d->rh + lo, T.rh + lo, per * nlev));
-    if (k0 == 0) OG_TRY(download(c, d->slp, T.slp, per));
-    OG_CUDA(cudaStreamSynchronize(c->stream));
-    return rc;
-}
-
-extern "C" int og_qc_time_levels(og_ctx* c, const og_time_desc* d, const og_qc_params* p, int k0,
-                                 int k1, int run_consistency)
-{
-    OG_BIND(c);
-    REQUIRE(c && p, "null argument");
-    OG_TRY(check_desc(d, k0, k1, true));
-    if (k1 == k0) return OG_OK;
-    TimeDev T;
-    OG_TRY(mirror_in(c, d, k0, k1, true, T));
-    OG_TRY(qc_time_core(c, T, p, k0, k1, run_consistency));
-    const size_t nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0), lo = nrep * k0;
-    OG_TRY(download(c, d->qc_u + lo, T.qc_u + lo, nrep * nlev));
-    OG_TRY(download(c, d->qc_v + lo, T.qc_v + lo, nrep * nlev));
-    OG_TRY(download(c, d->qc_t + lo, T.qc_t + lo, nrep * nlev));
-    OG_TRY(download(c, d->qc_rh + lo, T.qc_rh + lo, nrep * nlev));
-    if (k0 == 0) OG_TRY(download(c, d->qc_slp, T.qc_slp, nrep));
-    OG_CUDA(cudaStreamSynchronize(c->stream));
-    return OG_OK;
-}
-
-// proc_qc + proc_oa of one time period, levels pipelined through the copy engines.
-extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_params* qp,
-                             const og_oa_params* op, int k0, int k1, int groups)
-{
-    OG_BIND(c);
-    REQUIRE(c && qp && op, "null argument");
-    OG_TRY(check_desc(d, k0, k1, true));
-    if (k1 == k0) return OG_OK;
-    const int nlev = k1 - k0;
-    if (groups <= 0) groups = (nlev >= 16) ? 2 : 1;   // each group costs ~1 ms of fixed work
-    groups = std::min(groups, nlev);
-    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep;
-    while (c->pipe_events.size() < (size_t)(2 * groups)) {
-        cudaEvent_t e;
-        OG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->pipe_events.push_back(e);
-    }
-    // device mirrors keep the full [kbu] extent so that row offsets match the host arrays
-    TimeDev T = view_of(d);
-    struct Arr { const char* name; const void* host; void** dev; size_t row; bool sfc_only; bool out; };
-    float *m_t, *m_u, *m_v, *m_rh, *m_slp, *m_x, *m_y, *m_lon, *m_elev, *o_u, *o_v, *o_t, *o_rh, *o_slp;
-    int *q_u, *q_v, *q_t, *q_rh, *q_slp;
-    Arr arrs[] = {
-        {"m.t", d->t, (void**)&m_t, per, false, true},      {"m.u", d->u, (void**)&m_u, per, false, true},
-        {"m.v", d->v, (void**)&m_v, per, false, true},      {"m.rh", d->rh, (void**)&m_rh, per, false, true},
-        {"m.ob_u", d->ob_u, (void**)&o_u, nrep, false, false}, {"m.ob_v", d->ob_v, (void**)&o_v, nrep, false, false},
-        {"m.ob_t", d->ob_t, (void**)&o_t, nrep, false, false}, {"m.ob_rh", d->ob_rh, (void**)&o_rh, nrep, false, false},
-        {"m.qc_u", d->qc_u, (void**)&q_u, nrep, false, true},  {"m.qc_v", d->qc_v, (void**)&q_v, nrep, false, true},
-        {"m.qc_t", d->qc_t, (void**)&q_t, nrep, false, true},  {"m.qc_rh", d->qc_rh, (void**)&q_rh, nrep, false, true},
-        {"m.slp", d->slp, (void**)&m_slp, per, true, true},    {"m.ob_slp", d->ob_slp, (void**)&o_slp, nrep, true, false},
-        {"m.qc_slp", d->qc_slp, (void**)&q_slp, nrep, true, true},
-    };
-    for (Arr& a : arrs)
-        OG_TRY(c->reserve(a.name, std::max<size_t>(a.row * (a.sfc_only ? 1 : d->kbu), 1) * 4, a.dev));
-    OG_TRY(c->reserve_t("m.x", std::max<size_t>(nrep, 1), &m_x));
-    OG_TRY(c->reserve_t("m.y", std::max<size_t>(nrep, 1), &m_y));
-    OG_TRY(c->reserve_t("m.lon", std::max<size_t>(nrep, 1), &m_lon));
-    OG_TRY(c->reserve_t("m.elev", std::max<size_t>(nrep, 1), &m_elev));
-    T.t = m_t; T.u = m_u; T.v = m_v; T.rh = m_rh; T.slp = m_slp;
-    T.xob = m_x; T.yob = m_y; T.lon = m_lon; T.elev = m_elev;
-    T.ob_u = o_u; T.ob_v = o_v; T.ob_t = o_t; T.ob_rh = o_rh; T.ob_slp = o_slp;
-    T.qc_u = q_u; T.qc_v = q_v; T.qc_t = q_t; T.qc_rh = q_rh; T.qc_slp = q_slp;
-
-    // the copy streams must not run ahead of work already queued on the compute stream
-    // (earlier calls may still be reading the mirrors)
-    cudaEvent_t ev0 = c->pipe_events[0];
-    OG_CUDA(cudaEventRecord(ev0, c->stream));
-    OG_CUDA(cudaStreamWaitEvent(c->stream_in, ev0, 0));
-    OG_CUDA(cudaStreamWaitEvent(c->stream_out, ev0, 0));
-    auto h2d = [&](void* dst, const void* src, size_t bytes) -> int {
-        if (!bytes) return OG_OK;
-        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream_in));
-        c->stats.h2d_bytes += (int64_t)bytes;
-        return OG_OK;
-    };
-    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
-        if (!bytes) return OG_OK;
-        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream_out));
-        c->stats.d2h_bytes += (int64_t)bytes;
-        return OG_OK;
-    };
-    OG_TRY(h2d(m_x, d->xob, nrep * 4)); OG_TRY(h2d(m_y, d->yob, nrep * 4));
-    OG_TRY(h2d(m_lon, d->lon, nrep * 4)); OG_TRY(h2d(m_elev, d->elev, nrep * 4));
-    // every group's upload is queued up front: the copy engine streams them in while the
-    // host is busy launching (and, inside the stages, briefly waiting on) the compute
-    std::vector<int> gb(groups + 1);
-    for (int g = 0; g <= groups; ++g) gb[g] = k0 + (int)((long long)nlev * g / groups);
-    for (int g = 0; g < groups; ++g) {
-        const int a0 = gb[g], a1 = gb[g + 1];
-        for (Arr& a : arrs) {
-            if (a.sfc_only) { if (a0 == 0) OG_TRY(h2d(*a.dev, a.host, a.row * 4)); continue; }
-            OG_TRY(h2d((char*)*a.dev + a.row * a0 * 4, (const char*)a.host + a.row * a0 * 4, a.row * (a1 - a0) * 4));
-        }
-        OG_CUDA(cudaEventRecord(c->pipe_events[2 * g], c->stream_in));
-    }
-    int rc_radius = OG_OK;
-    for (int g = 0; g < groups; ++g) {
-        const int a0 = gb[g], a1 = gb[g + 1];
-        OG_CUDA(cudaStreamWaitEvent(c->stream, c->pipe_events[2 * g], 0));
-        OG_TRY(qc_time_core(c, T, qp, a0, a1, 1));
-        int rc = oa_time_core(c, T, op, a0, a1);
-        if (rc == OG_ERR_RADIUS) rc_radius = rc; else if (rc != OG_OK) return rc;
-        OG_CUDA(cudaEventRecord(c->pipe_events[2 * g + 1], c->stream));
-        OG_CUDA(cudaStreamWaitEvent(c->stream_out, c->pipe_events[2 * g + 1], 0));
-        for (Arr& a : arrs) {
-            if (!a.out) continue;
-            if (a.sfc_only) { if (a0 == 0) OG_TRY(d2h(const_cast<void*>(a.host), *a.dev, a.row * 4)); continue; }
-            OG_TRY(d2h((char*)const_cast<void*>(a.host) + a.row * a0 * 4, (const char*)*a.dev + a.row * a0 * 4, a.row * (a1 - a0) * 4));
-        }
-    }
-    OG_CUDA(cudaStreamSynchronize(c->stream_out));
-    OG_CUDA(cudaStreamSynchronize(c->stream));
-    return rc_radius;
-}
-
-// ---- asynchronous per-time API ------------------------------------------------------------
-namespace {
-
-struct MirrorArr { const char* name; size_t row; bool sfc_only; bool out; };
-const MirrorArr kMirror[] = {
-    {"t", 0, false, true},     {"u", 0, false, true},     {"v", 0, false, true},     {"rh", 0, false, true},
-    {"ob_u", 1, false, false}, {"ob_v", 1, false, false}, {"ob_t", 1, false, false}, {"ob_rh", 1, false, false},
-    {"qc_u", 1, false, true},  {"qc_v", 1, false, true},  {"qc_t", 1, false, true},  {"qc_rh", 1, false, true},
-    {"slp", 0, true, true},    {"ob_slp", 1, true, false}, {"qc_slp", 1, true, true},
-};
-constexpr int kNMirror = sizeof(kMirror) / sizeof(kMirror[0]);
-
-void* host_of(const og_time_desc* d, int i)
-{
-    void* h[] = {d->t, d->u, d->v, d->rh, (void*)d->ob_u, (void*)d->ob_v, (void*)d->ob_t, (void*)d->ob_rh,
-                 d->qc_u, d->qc_v, d->qc_t, d->qc_rh, d->slp, (void*)d->ob_slp, d->qc_slp};
-    return h[i];
-}
-
-// Device mirror of one slot (full [kbu] extent so that row offsets match the host arrays).
-int slot_mirror(og_ctx* c, const og_time_desc* d, int slot, TimeDev& T, void* dev[kNMirror])
-{
-    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep;
-    char name[32];
-    for (int i = 0; i < kNMirror; ++i) {
-        const size_t row = kMirror[i].row ? nrep : per;
-        snprintf(name, sizeof name, "s%d.%s", slot, kMirror[i].name);
-        OG_TRY(c->reserve(name, std::max<size_t>(row * (kMirror[i].sfc_only ? 1 : d->kbu), 1) * 4, &dev[i]));
-    }
-    float* f4[4];
-    const char* tn[4] = {"x", "y", "lon", "elev"};
-    for (int i = 0; i < 4; ++i) {
-        snprintf(name, sizeof name, "s%d.%s", slot, tn[i]);
-        OG_TRY(c->reserve_t(name, std::max<size_t>(nrep, 1), &f4[i]));
-    }
-    T = view_of(d);
-    T.t = (float*)dev[0]; T.u = (float*)dev[1]; T.v = (float*)dev[2]; T.rh = (float*)dev[3];
-    T.ob_u = (float*)dev[4]; T.ob_v = (float*)dev[5]; T.ob_t = (float*)dev[6]; T.ob_rh = (float*)dev[7];
-    T.qc_u = (int*)dev[8]; T.qc_v = (int*)dev[9]; T.qc_t = (int*)dev[10]; T.qc_rh = (int*)dev[11];
-    T.slp = (float*)dev[12]; T.ob_slp = (float*)dev[13]; T.qc_slp = (int*)dev[14];
-    T.xob = f4[0]; T.yob = f4[1]; T.lon = f4[2]; T.elev = f4[3];
-    return OG_OK;
-}
-
-int slot_events(og_ctx* c, int slot)
-{
-    og_ctx::Slot& s = c->slots[slot];
-    if (!s.up) {
-        OG_CUDA(cudaEventCreateWithFlags(&s.up, cudaEventDisableTiming));
-        OG_CUDA(cudaEventCreateWithFlags(&s.comp, cudaEventDisableTiming));
-        OG_CUDA(cudaEventCreateWithFlags(&s.down, cudaEventDisableTiming));
-    }
-    return OG_OK;
-}
-
-} // namespace
-
-extern "C" int og_time_upload(og_ctx* c, const og_time_desc* d, int k0, int k1, int slot)
-{
-    OG_BIND(c);
-    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
-    OG_TRY(check_desc(d, k0, k1, true));
-    OG_TRY(slot_events(c, slot));
-    TimeDev T; void* dev[kNMirror];
-    OG_TRY(slot_mirror(c, d, slot, T, dev));
-    og_ctx::Slot& s = c->slots[slot];
-    // the mirror may still be read by the slot's previous compute / download
-    OG_CUDA(cudaEventRecord(s.up, c->stream));
-    OG_CUDA(cudaStreamWaitEvent(c->stream_in, s.up, 0));
-    if (s.down_pending) OG_CUDA(cudaStreamWaitEvent(c->stream_in, s.down, 0));
-    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
-    auto h2d = [&](void* dst, const void* src, size_t bytes) -> int {
-        if (!bytes) return OG_OK;
-        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream_in));
-        c->stats.h2d_bytes += (int64_t)bytes;
-        return OG_OK;
-    };
-    OG_TRY(h2d((void*)T.xob, d->xob, nrep * 4)); OG_TRY(h2d((void*)T.yob, d->yob, nrep * 4));
-    OG_TRY(h2d((void*)T.lon, d->lon, nrep * 4)); OG_TRY(h2d((void*)T.elev, d->elev, nrep * 4));
-    for (int i = 0; i < kNMirror; ++i) {
-        const size_t row = kMirror[i].row ? nrep : per;
-        if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(h2d(dev[i], host_of(d, i), row * 4)); continue; }
-        OG_TRY(h2d((char*)dev[i] + row * k0 * 4, (const char*)host_of(d, i) + row * k0 * 4, row * nlev * 4));
-    }
-    OG_CUDA(cudaEventRecord(s.up, c->stream_in));
-    return OG_OK;
-}
-
-extern "C" int og_time_compute(og_ctx* c, const og_time_desc* d, const og_qc_params* qp,
-                               const og_oa_params* op, int k0, int k1, int slot)
-{
-    OG_BIND(c);
-    REQUIRE(c && qp && op && slot >= 0 && slot < OG_SLOTS, "bad argument");
-    OG_TRY(check_desc(d, k0, k1, true));
-    OG_TRY(slot_events(c, slot));
-    TimeDev T; void* dev[kNMirror];
-    OG_TRY(slot_mirror(c, d, slot, T, dev));
-    og_ctx::Slot& s = c->slots[slot];
-    OG_CUDA(cudaStreamWaitEvent(c->stream, s.up, 0));
-    int rc_radius = OG_OK;
-    if (k1 > k0) {
-        OG_TRY(qc_time_core(c, T, qp, k0, k1, 1));
-        int rc = oa_time_core(c, T, op, k0, k1);
-        if (rc == OG_ERR_RADIUS) rc_radius = rc; else if (rc != OG_OK) return rc;
-    }
-    OG_CUDA(cudaEventRecord(s.comp, c->stream));
-    return rc_radius;
-}
-
-extern "C" int og_time_download(og_ctx* c, const og_time_desc* d, int k0, int k1, int slot)
-{
-    OG_BIND(c);
-    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
-    OG_TRY(check_desc(d, k0, k1, true));
-    OG_TRY(slot_events(c, slot));
-    TimeDev T; void* dev[kNMirror];
-    OG_TRY(slot_mirror(c, d, slot, T, dev));
-    og_ctx::Slot& s = c->slots[slot];
-    OG_CUDA(cudaStreamWaitEvent(c->stream_out, s.comp, 0));
-    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
-    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
-        if (!bytes) return OG_OK;
-        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream_out));
-        c->stats.d2h_bytes += (int64_t)bytes;
-        return OG_OK;
-    };
-    for (int i = 0; i < kNMirror; ++i) {
-        if (!kMirror[i].out) continue;
-        const size_t row = kMirror[i].row ? nrep : per;
-        if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(d2h(host_of(d, i), dev[i], row * 4)); continue; }
-        OG_TRY(d2h((char*)host_of(d, i) + row * k0 * 4, (const char*)dev[i] + row * k0 * 4, row * nlev * 4));
-    }
-    OG_CUDA(cudaEventRecord(s.down, c->stream_out));
-    s.down_pending = true;
-    return OG_OK;
-}
-
-extern "C" int og_time_wait(og_ctx* c, int slot)
-{
-    OG_BIND(c);
-    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
-    og_ctx::Slot& s = c->slots[slot];
-    if (s.down_pending) { OG_CUDA(cudaEventSynchronize(s.down)); s.down_pending = false; }
-    return OG_OK;
-}
-
-extern "C" int og_qc_time_fdda(og_ctx* c, const og_time_desc* d, const og_qc_params* p, float* tobbox,
-                               float* odis)
-{
-    OG_BIND(c);
-    REQUIRE(c && p && tobbox && odis, "null argument");
-    OG_TRY(check_desc(d, 0, d ? d->kbu : 0, true));
-    REQUIRE(d->iew <= 32000 && d->jns <= 32000, "grid larger than 32000 points per edge");
-    TimeDev T;
-    OG_TRY(mirror_in(c, d, 0, d->kbu, true, T));
-    const size_t per = (size_t)d->iew * d->jns;
-    OG_TRY(upload(c, "m.tobbox", tobbox, per, &T.tobbox));
-    OG_TRY(c->reserve_t("m.odis", per, &T.odis));
-    OG_TRY(qc_time_core(c, T, p, 0, d->kbu, 1));
-    const size_t n = (size_t)d->nrep * d->kbu;
-    OG_TRY(download(c, d->qc_u, T.qc_u, n));
-    OG_TRY(download(c, d->qc_v, T.qc_v, n));
-    OG_TRY(download(c, d->qc_t, T.qc_t, n));
-    OG_TRY(download(c, d->qc_rh, T.qc_rh, n));
-    OG_TRY(download(c, d->qc_slp, T.qc_slp, (size_t)d->nrep));
-    OG_TRY(download(c, tobbox, T.tobbox, per));
-    OG_TRY(download(c, odis, T.odis, per));
-    OG_CUDA(cudaStreamSynchronize(c->stream));
-    return OG_OK;
-}
-
-extern "C" int og_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p)
-{
-    OG_BIND(c);
-    if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
-    return og_qc_time_levels(c, d, p, 0, d->kbu, 1);
-}
