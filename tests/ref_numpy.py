@@ -5,6 +5,7 @@ IEEE-754 binary32 operation in source order; windows are vectorised per observat
 does not change any result (points are independent; obs are applied in index order).
 
     cressman     src/oa_module.F90:25-218 (+ dist_uu_vv_rh :229-574, dist_not_uu_vv_rh :577-627)
+    error_max    src/qc1_module.F90:102-249;  ob_density / obs_distance  src/qc0_module.F90:81-232
     buddy_check  src/qc2_module.F90:111-337 (+ modify_qc_flag / add_to_qc_flag, qc0_module.F90:9-76)
 """
 import math
@@ -193,3 +194,98 @@ def buddy_check(obs, xob, yob, qc_flag, elev, gridded, name, pressure, dx, buddy
         if abs(err[k]) > difmax[k]:
             qc[k] = add_flag(int(qc[k]), FAILS_BUDDY)
     return qc.astype(np.int32), aob, err, difmax, bnf
+
+
+# ---- error_max, ob_density, obs_distance: same discipline (written from the Fortran) -----------
+FAILS_ERROR_MAX = 1 << 16
+
+
+def bilinear(gridded, x, y):
+    """qc1_module.F90:197-204 == proc_oa.F90:520-527; gridded (jns, iew) == Fortran gridded(iew,jns)."""
+    iob, job = fint(x), fint(y)
+    dxob, dyob = F(x) - F(iob), F(y) - F(job)
+    g = lambda i, j: F(gridded[j - 1, i - 1])
+    one = F(1.0)
+    return F(F(one - dxob) * F(F(F(one - dyob) * g(iob, job)) + F(dyob * g(iob, job + 1)))
+             + F(dxob * F(F(F(one - dyob) * g(iob + 1, job)) + F(dyob * g(iob + 1, job + 1)))))
+
+
+def error_max(obs, xob, yob, elev, qc_flag, gridded, name, max_difference, pressure, local_time):
+    """src/qc1_module.F90:102-249 (+ modify_qc_flag, qc0_module.F90:9-34).  Returns (qc, aob, err,
+    factored_difference)."""
+    n = len(obs)
+    plevel = F(pressure)
+    qc = np.array(qc_flag, np.int32).copy()
+    aob = np.zeros(n, np.float32); err = np.zeros(n, np.float32); thr = np.zeros(n, np.float32)
+    for k in range(n):
+        factor = F(1.0)                                               # :108
+        if name in ("UU", "VV"):
+            if plevel <= F(499.9):
+                factor = F(1.5)
+            elif plevel <= F(1000.1):
+                factor = F(1.25)
+        elif name == "TT":
+            if plevel > F(1000.1):
+                factor = F(1.5) if 1100 <= int(local_time[k]) <= 2000 else F(1.25)
+            elif plevel <= F(1000.1) and plevel > F(700.0):
+                factor = F(0.85)
+            else:
+                factor = F(0.65)
+        elif name == "PMSLPSFC":
+            factor = F(F(1.0) + F(abs(F(elev[k])) / F(2000.0)))
+        elif name == "DEWPOINT":
+            o = F(obs[k])
+            if o < F(255.0) and o >= F(235.0):
+                factor = F(1.25)
+            elif o < F(235.0) and o >= F(215.0):
+                factor = F(1.50)
+            elif o < F(215.0):
+                factor = F(1.75)
+        aob[k] = bilinear(gridded, xob[k], yob[k])
+        err[k] = F(F(obs[k]) - aob[k])                                # :220
+        if name in ("UU", "VV"):
+            thr[k] = max(F(factor * F(max_difference)), F(F(0.15) * aob[k]))   # :232
+        else:
+            thr[k] = F(factor * F(max_difference))                    # :241
+        if abs(err[k]) > thr[k]:
+            qc[k] = add_flag(int(qc[k]), FAILS_ERROR_MAX)
+    return qc, aob, err, thr
+
+
+def ob_density(xob, yob, grid_dist, tobbox):
+    """src/qc0_module.F90:81-119; tobbox (iew, jns) C order == Fortran tobbox(jns,iew)."""
+    tb = np.array(tobbox, np.float32).copy()
+    iew, jns = tb.shape
+    r = F(F(250.0) / F(grid_dist))
+    rr = nint(r)
+    for x, y in zip(xob, yob):
+        iob, job = fint(x), fint(y)
+        for j in range(max(job - rr - 1, 1), min(job + rr + 1, jns - 1) + 1):
+            for i in range(max(iob - rr - 1, 1), min(iob + rr + 1, iew - 1) + 1):
+                di, dj = F(F(i) - F(x)), F(F(j) - F(y))
+                if np.sqrt(F(F(di * di) + F(dj * dj))) < r:
+                    tb[i - 1, j - 1] += F(1.0)
+    return tb
+
+
+def obs_distance(tobbox, dx):
+    """src/qc0_module.F90:123-232, the O((iew*jns)**2) search as written."""
+    tb = np.asarray(tobbox, np.float32)
+    iew, jns = tb.shape
+    dx = F(dx)
+    a = F(F(F(F(iew - 1) * dx) * F(iew - 1)) * dx); b = F(F(F(F(jns - 1) * dx) * F(jns - 1)) * dx)
+    diag_m = np.sqrt(F(a + b))
+    diag_cells = F(diag_m / dx)
+    obs = np.argwhere(tb > F(0.5))
+    out = np.zeros((iew, jns), np.float32)
+    for i in range(iew):
+        for j in range(jns):
+            if tb[i, j] > F(0.5):
+                continue
+            dijmin = diag_cells
+            for ii, jj in obs:
+                di, dj = abs(int(ii) - i), abs(int(jj) - j)
+                dij = np.sqrt(F(F(F(dj) * F(dj)) + F(F(di) * F(di))))
+                dijmin = min(dijmin, dij)
+            out[i, j] = F(dijmin * dx)
+    return out

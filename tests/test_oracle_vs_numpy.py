@@ -75,3 +75,43 @@ def test_buddy_check(oracle, var, pressure, n, dx):
     for nm, u, v in zip(("qc", "aob", "err", "difmax", "buddy_num_final"), a, b):
         np.testing.assert_array_equal(u, v, err_msg=nm)
     assert np.count_nonzero(a[0] & (1 << 17)) > 0
+
+
+@pytest.mark.parametrize("var,pressure", [(1, 300.0), (2, 850.0), (3, 1001.0), (3, 850.0), (3, 400.0), (4, 700.0),
+                                          (5, 1001.0), (6, 1001.0), (7, 500.0)])
+def test_error_max(oracle, var, pressure):
+    """qc1_module.F90:102-249: factors per variable / level / local time / elevation / dewpoint band."""
+    rng = np.random.default_rng(var * 31 + int(pressure))
+    iew, jns, n = 60, 50, 300
+    base = {1: 10.0, 2: 10.0, 3: 270.0, 4: 60.0, 5: 101000.0, 6: 101000.0, 7: 240.0}[var]
+    spread = {5: 400.0, 6: 400.0, 7: 25.0}.get(var, 6.0)
+    g = wavy(iew, jns, spread / 3, base)
+    x = rng.uniform(2.0, iew - 1.0, n).astype(np.float32); y = rng.uniform(2.0, jns - 1.0, n).astype(np.float32)
+    ob = (base + rng.normal(0, spread, n)).astype(np.float32)
+    elev = rng.uniform(-500, 3500, n).astype(np.float32)
+    lt = (rng.integers(0, 24, n) * 100).astype(np.int32)
+    q0 = (rng.integers(0, 2, n) * (1 << 14) + rng.integers(0, 2, n) * (1 << 16)).astype(np.int32)
+    maxd = {5: 300.0, 6: 300.0, 7: 12.0}.get(var, 5.0)
+    a = oracle.error_max(ob, x, y, elev, q0, g, var, maxd, pressure, lt)
+    b = R.error_max(ob, x, y, elev, q0, g, NAMES[var], maxd, pressure, lt)
+    for nm, u, v in zip(("qc", "aob", "err", "thr"), a, b):
+        np.testing.assert_array_equal(u, v, err_msg=nm)
+    assert 0 < np.count_nonzero(a[0] != q0) < n
+
+
+def test_ob_density_and_obs_distance(oracle):
+    """qc0_module.F90:81-232: the window sweep and the brute-force nearest-box search as written."""
+    rng = np.random.default_rng(12)
+    iew, jns, n = 34, 27, 25
+    x = rng.uniform(1.0, iew - 0.5, n).astype(np.float32); y = rng.uniform(1.0, jns - 0.5, n).astype(np.float32)
+    tb0 = rng.integers(0, 2, (iew, jns)).astype(np.float32)
+    for gd in (60.0, 110.0):
+        a = oracle.ob_density(x, y, gd, tb0); b = R.ob_density(x, y, gd, tb0)
+        np.testing.assert_array_equal(a, b)
+    tb = np.zeros((iew, jns), np.float32)
+    tb[rng.integers(0, iew, 6), rng.integers(0, jns, 6)] = 1.0
+    tb[3, 4] = 0.5
+    for dx in (3.0, 12.5):
+        np.testing.assert_array_equal(oracle.obs_distance(tb, dx), R.obs_distance(tb, dx))
+    np.testing.assert_array_equal(oracle.obs_distance(np.zeros((iew, jns), np.float32), 9.0),
+                                  R.obs_distance(np.zeros((iew, jns), np.float32), 9.0))
