@@ -309,7 +309,10 @@ int og_dev_qc_time_items(og_ctx* ctx, const og_time_desc* d, const og_qc_params*
 int og_dev_oa_time_items(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
                          const int* levels, const int* var_masks, int nitems);
 /* qc_consistency (qc0_module.F90:371-404) of the levels [k_begin,k_end) on its own: u/v flags
- * merged, T's error_max / buddy bits copied to RH.  og_qc_time* run it themselves when
+ * merged, T's error_max / buddy bits copied to RH.  (The reference's third rule, :405-424 --
+ * a reported dew point above the reported temperature fails RH -- compares the report's own
+ * dew-point measurement, which the flat table does not carry; it stays with the report list on
+ * the Fortran side, as do the speed / direction / dew_point copies of the flags.)  og_qc_time* run it themselves when
  * run_consistency != 0; the stand-alone form is the step between the QC and the OA phase when
  * the variables of a level were checked on different GPUs (var_mask; obsgrid_b200/shard.py).
  * Host arrays (blocking) and device-resident form. */

@@ -289,3 +289,76 @@ def obs_distance(tobbox, dx):
                 dijmin = min(dijmin, dij)
             out[i, j] = F(dijmin * dx)
     return out
+
+
+def local_time(time_hhmm, lonob):
+    """src/qc0_module.F90:259-267 (integer local_time: the REAL expression is truncated on assignment)."""
+    out = np.zeros(len(lonob), np.int32)
+    for k, lon in enumerate(lonob):
+        lt = fint(F(F(time_hhmm // 100) + F(F(lon) / F(15.0))))
+        if lt < 0:
+            lt = 24 + lt
+        out[k] = (lt % 24) * 100
+    return out
+
+
+def contains_2n(sumtocheck, numtofind):
+    """src/obs_sort_module.F90:4515-4560: is the power of two `numtofind` a term of the sum of
+    distinct powers of two `sumtocheck`?  Greedy decomposition from 2**18 down, as written."""
+    curn = 18
+    sumnow = int(sumtocheck)
+    while sumnow > 0:
+        if sumnow < numtofind:
+            return False
+        if sumnow == numtofind:
+            return True
+        cur2n = 2 ** curn
+        while cur2n > sumnow:
+            curn -= 1
+            cur2n = 2 ** curn
+        if cur2n == numtofind:
+            return True
+        sumnow -= cur2n
+    return False
+
+
+def qc_consistency(qc_u, qc_v, qc_t, qc_rh):
+    """src/qc0_module.F90:371-404 on flat rows (the td > t rule of :405-424 needs the report's
+    dew-point measurement and is outside the table)."""
+    u, v, t, rh = (np.array(a, np.int32).copy() for a in (qc_u, qc_v, qc_t, qc_rh))
+    for k in range(len(u)):
+        qu, qv = int(u[k]), int(v[k])
+        if qu > qv:
+            v[k] = qu
+        if qv > qu:
+            u[k] = qv
+        qt, qr = int(t[k]), int(rh[k])
+        contains = contains_2n
+        new = qr
+        if contains(qt, FAILS_ERROR_MAX) and not contains(qr, FAILS_ERROR_MAX):
+            new = add_flag(new, FAILS_ERROR_MAX)
+        if contains(qt, FAILS_BUDDY) and not contains(qr, FAILS_BUDDY):
+            new = add_flag(new, FAILS_BUDDY)
+        rh[k] = new
+    return u, v, rh
+
+
+def scan_radii(radius_influence, sfc_mult, pressure):
+    """src/proc_oa.F90:641-707: radii (grid cells, NINT) the multi_scan loop uses for one slab and
+    whether the reference STOPs (surface scan 1 below 4.5 cells)."""
+    out, stop = [], False
+    for num_scan, r in enumerate(radius_influence, 1):
+        if r < 0:
+            break
+        sfc = abs(F(pressure) - F(1001.0)) < F(0.0001)
+        sf = F(sfc_mult) if sfc else F(1.00)
+        scaled = F(F(r) * sf)
+        scan1 = F(F(radius_influence[0]) * sf)
+        if F(sfc_mult) < F(0.99999) and sfc:
+            if scan1 > F(100.0):
+                scaled = F(scaled * F(F(100.0) / scan1))
+            if scaled < F(4.5):
+                stop = num_scan == 1
+                break
+        out.append(nint(scaled))
+    return out, stop

@@ -115,3 +115,46 @@ def test_ob_density_and_obs_distance(oracle):
         np.testing.assert_array_equal(oracle.obs_distance(tb, dx), R.obs_distance(tb, dx))
     np.testing.assert_array_equal(oracle.obs_distance(np.zeros((iew, jns), np.float32), 9.0),
                                   R.obs_distance(np.zeros((iew, jns), np.float32), 9.0))
+
+
+def test_local_time(oracle):
+    rng = np.random.default_rng(3)
+    lon = np.concatenate([rng.uniform(-180, 180, 400), [-180.0, 180.0, 0.0, -7.5, 7.49, -172.6, 14.999]]).astype(np.float32)
+    for hhmm in (0, 600, 1200, 1830, 2359):
+        np.testing.assert_array_equal(oracle.local_time(hhmm, lon), R.local_time(hhmm, lon))
+
+
+def test_qc_consistency(oracle):
+    """qc0_module.F90:371-404 with contains_2n as written (obs_sort_module.F90:4515-4560)."""
+    from obsgrid_b200 import synth
+    case = synth.small_case(iew=30, jns=28, kbu=3, n_sfc=200, n_snd=50, seed=2)
+    rng = np.random.default_rng(6)
+    bits = np.array([1 << 14, 1 << 16, 1 << 17, 1 << 3, 1 << 11], np.int32)
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_rh"):
+        a = getattr(case, nm)
+        a[...] = (rng.integers(0, 2, (5,) + a.shape).astype(np.int32) * bits[:, None, None]).sum(axis=0)
+    want = [R.qc_consistency(case.qc_u[k], case.qc_v[k], case.qc_t[k], case.qc_rh[k]) for k in range(case.kbu)]
+    t0 = case.qc_t.copy()
+    oracle.qc_consistency(case)
+    for k in range(case.kbu):
+        np.testing.assert_array_equal(case.qc_u[k], want[k][0]); np.testing.assert_array_equal(case.qc_v[k], want[k][1])
+        np.testing.assert_array_equal(case.qc_rh[k], want[k][2])
+    np.testing.assert_array_equal(case.qc_t, t0)
+    # contains_2n is a bit test on sums of distinct powers of two below 2**19
+    for q in rng.integers(0, 1 << 19, 2000):
+        for b in (14, 16, 17):
+            assert R.contains_2n(int(q), 1 << b) == bool(int(q) >> b & 1)
+
+
+@pytest.mark.parametrize("radii,mult,pressure", [((10, 8, 6, 4), 1.0, 1001.0), ((10, 8, 6, 4), 0.8, 1001.0),
+                                                 ((10, 8, 6, 4), 0.5, 1001.0), ((10, 8, 6, 4), 0.5, 850.0),
+                                                 ((200, 150, 90, 20), 0.75, 1001.0), ((5, 4), 0.8, 1001.0),
+                                                 ((12, 9, 6, 4, 2), 1.0, 700.0)])
+def test_scan_radius_logic(oracle, radii, mult, pressure):
+    """proc_oa.F90:641-707 through ogo_oa_slab: scans done and the STOP case."""
+    want, stop = R.scan_radii(list(radii) + [-1], mult, pressure)
+    g = wavy(40, 36)
+    x = np.array([10.5, 20.25], np.float32); y = np.array([12.5, 18.75], np.float32)
+    ob = np.array([281.0, 279.0], np.float32)
+    out, rc, ns = oracle.oa_slab(g, 3, pressure, ob, x, y, radii, 12.0, sfc_mult=mult)
+    assert ns == len(want) and (rc != 0) == stop
