@@ -362,3 +362,86 @@ def scan_radii(radius_influence, sfc_mult, pressure):
                 break
         out.append(nint(scaled))
     return out, stop
+
+
+# ---- smoothers and GET_FG_T_AT_POINT ------------------------------------------------------------
+def smooth_5(field, passes, crsdot=1):
+    """src/oa_module.F90:928-1006; field (jns, iew) C order == Fortran field(iew,jns)."""
+    f = np.array(field, np.float32).copy()
+    jns, iew = f.shape
+    at = lambda a, i, j: a[j - 1, i - 1]
+    for _ in range(passes):
+        t = np.zeros_like(f)
+        for j in range(2, jns - 1 - crsdot + 1):
+            for i in range(2, iew - 1 - crsdot + 1):
+                t[j - 1, i - 1] = F(F(F(F(F(F(at(f, i, j) * F(4.0)) + at(f, i + 1, j)) + at(f, i - 1, j)) + at(f, i, j + 1))
+                                      + at(f, i, j - 1)) * F(0.125))
+        for i in (1, iew - crsdot):
+            for j in range(2, jns - 1 - crsdot + 1):
+                t[j - 1, i - 1] = F(F(F(F(at(f, i, j) * F(2.0)) + at(f, i, j + 1)) + at(f, i, j - 1)) * F(0.25))
+        for j in (1, jns - crsdot):
+            for i in range(2, iew - 1 - crsdot + 1):
+                t[j - 1, i - 1] = F(F(F(F(at(f, i, j) * F(2.0)) + at(f, i + 1, j)) + at(f, i - 1, j)) * F(0.25))
+        for j in range(2, jns - 1 - crsdot + 1):
+            for i in range(2, iew - 1 - crsdot + 1):
+                f[j - 1, i - 1] = t[j - 1, i - 1]
+        for j in range(2, jns - 1 - crsdot + 1):
+            f[j - 1, 0] = t[j - 1, 0]; f[j - 1, iew - crsdot - 1] = t[j - 1, iew - crsdot - 1]
+        for i in range(2, iew - 1 - crsdot + 1):
+            f[0, i - 1] = t[0, i - 1]; f[jns - crsdot - 1, i - 1] = t[jns - crsdot - 1, i - 1]
+    return f
+
+
+def smoother_desmoother(slab, passes, crsdot=1):
+    """src/oa_module.F90:875-923; slab (jmx, imx) C order == Fortran slab(imx,jmx)."""
+    s = np.array(slab, np.float32).copy()
+    jmx, imx = s.shape
+    xnu = (F(0.50), F(-0.52))
+    half = F(0.5)
+    for loop in range(1, passes * 2 + 1):
+        nu = xnu[2 - loop % 2 - 1]
+        new = s.copy()
+        for i in range(2, imx - 1 - crsdot + 1):
+            for j in range(2, jmx - 1 - crsdot + 1):
+                c = s[j - 1, i - 1]
+                new[j - 1, i - 1] = F(c + F(nu * F(F(F(s[j, i - 1] + s[j - 2, i - 1]) * half) - c)))
+        s = new
+        new = s.copy()
+        for j in range(2, jmx - 1 - crsdot + 1):
+            for i in range(2, imx - 1 - crsdot + 1):
+                c = s[j - 1, i - 1]
+                new[j - 1, i - 1] = F(c + F(nu * F(F(F(s[j - 1, i] + s[j - 1, i - 2]) * half) - c)))
+        s = new
+    return s
+
+
+def fg_t_at_point(t3d, h3d, x, y, height, dtdz=-0.0065, missing=-888888.0):
+    """src/get_fg_at_point_module.F90:36-114; t3d / h3d (kbu, iew, jns) C order == Fortran
+    (jns,iew,kbu); (x, y) already projected."""
+    kbu, iew, jns = t3d.shape
+    x, y, height = F(x), F(y), F(height)
+    if x < 1 or x > iew - 1 or y < 1 or y > jns - 1:
+        return F(missing)
+    fx, cx = int(math.floor(x)), int(math.ceil(x))
+    fy, cy = int(math.floor(y)), int(math.ceil(y))
+    near = []
+    for (ix, iy) in ((fx, fy), (fx, cy), (cx, fy), (cx, cy)):
+        hcol = lambda k: F(h3d[k - 1, ix - 1, iy - 1]); tcol = lambda k: F(t3d[k - 1, ix - 1, iy - 1])
+        val = None
+        for k in range(2, kbu - 1 + 1):
+            if height >= hcol(k) and height <= hcol(k + 1):
+                w = F(F(hcol(k + 1) - height) / F(hcol(k + 1) - hcol(k)))
+                val = F(F(w * tcol(k)) + F(F(F(1.0) - w) * tcol(k + 1)))
+                break
+        if val is None:
+            if height < hcol(2):
+                val = F(tcol(2) - F(F(dtdz) * F(hcol(2) - height)))
+            elif height > hcol(kbu):
+                return F(missing)
+            else:
+                raise AssertionError("branch the reference STOPs in")
+        near.append(val)
+    xn, yn = F(x - F(math.floor(x))), F(y - F(math.floor(y)))
+    one = F(1.0)
+    return F(F(F(one - xn) * F(F(F(one - yn) * near[0]) + F(yn * near[1])))
+             + F(xn * F(F(F(one - yn) * near[2]) + F(yn * near[3]))))

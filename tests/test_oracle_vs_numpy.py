@@ -158,3 +158,33 @@ def test_scan_radius_logic(oracle, radii, mult, pressure):
     ob = np.array([281.0, 279.0], np.float32)
     out, rc, ns = oracle.oa_slab(g, 3, pressure, ob, x, y, radii, 12.0, sfc_mult=mult)
     assert ns == len(want) and (rc != 0) == stop
+
+
+@pytest.mark.parametrize("crsdot", [0, 1])
+def test_smoothers(oracle, crsdot):
+    """oa_module.F90:875-1006: interior stencil, the four edges, corners untouched, pass order."""
+    g = (wavy(23, 17, 5.0, 0.0) + np.random.default_rng(1).normal(0, 1, (17, 23))).astype(np.float32)
+    for passes in (1, 3):
+        np.testing.assert_array_equal(oracle.smooth_5(g, passes, crsdot), R.smooth_5(g, passes, crsdot))
+        np.testing.assert_array_equal(oracle.smoother_desmoother(g, passes, crsdot), R.smoother_desmoother(g, passes, crsdot))
+
+
+def test_fg_t_at_point(oracle):
+    """get_fg_at_point_module.F90:36-114: trapping levels, extrapolation below level 2, missing above
+    the top and outside the domain."""
+    from oracle.ogoracle import lib, ptr
+    rng = np.random.default_rng(9)
+    kbu, iew, jns = 7, 12, 10
+    hlev = np.array([0.0, 100.0, 800.0, 1500.0, 3000.0, 5500.0, 9000.0], np.float32)
+    h = (hlev[:, None, None] + rng.normal(0, 20, (kbu, iew, jns))).astype(np.float32)
+    t = (290.0 - 0.0065 * h + rng.normal(0, 1, (kbu, iew, jns))).astype(np.float32)
+    L = lib()
+    n_missing = n_extrap = 0
+    for it in range(400):
+        x = float(rng.uniform(0.5, iew - 0.5)); y = float(rng.uniform(0.5, jns - 0.5))
+        z = float(rng.uniform(-200, 9500) if it % 2 else rng.uniform(-200, 150))
+        a = np.float32(L.ogo_fg_t_at_point(ptr(t), ptr(h), jns, iew, kbu, x, y, z))
+        b = R.fg_t_at_point(t, h, x, y, z)
+        assert a == b, (x, y, z, a, b)
+        n_missing += a == np.float32(-888888.0); n_extrap += (z < 80.0 and a != np.float32(-888888.0))
+    assert n_missing > 5 and n_extrap > 5
