@@ -723,8 +723,10 @@ def test_context_on_another_device_from_a_fresh_thread(oracle):
     t = threading.Thread(target=work); t.start(); t.join()
     c1.close()
     assert not err, err
+    # the asynchronous pass re-analysed the output of the blocking one: flags are those of the
+    # first QC (a second QC of unchanged obs sets the same bits), fields moved twice
     ref = base.copy()
     oracle.qc_time(ref)
     for nm in ("qc_u", "qc_v", "qc_t", "qc_slp"):
-        np.testing.assert_array_equal(getattr(got, nm)[...] & 0, 0)      # ran to completion
+        assert np.all((getattr(got, nm) & getattr(ref, nm)) == getattr(ref, nm)), nm
     assert np.any(got.t != base.t)
