@@ -380,6 +380,11 @@ int   og_fp32_peak(og_ctx* ctx, double* lane_ops_per_s);
 /* Self test: compares the kernels' FCHK-less exact division with __fdiv_rn on n random
  * Cressman weight operand pairs (R in 1..rmax); *mismatches must come back 0. */
 int   og_selftest_div(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches);
+/* Self test: out[i] = the device's LOG of x[i] (host arrays).  The DEWPOINT quantities of proc_qc go
+ * through Fortran's LOG, i.e. glibc's logf in the reference build (proc_qc.F90:315-319,
+ * ob_access_module.F90:476-486); the device restates that algorithm (csrc/og_logf.h) and the tests
+ * compare it with the host libm's logf over the whole argument range. */
+int   og_selftest_logf(og_ctx* ctx, const float* x, int n, float* out);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,7 @@ SIGNATURES = {
     "og_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "og_host_free": (C.c_int, [_vp]),
     "og_selftest_div": (C.c_int, [_vp, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_longlong)]),
+    "og_selftest_logf": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "og_innovation": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.c_float,
                                 C.c_int, _vp, _vp]),
     "og_cressman": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int,

@@ -81,6 +81,12 @@ class Context:
         check(self._lib.og_selftest_div(self._h, n, seed, rmax, C.byref(bad)), "og_selftest_div")
         return bad.value
 
+    def selftest_logf(self, x):
+        """The device's LOG (glibc's logf algorithm, csrc/og_logf.h) of every element of x."""
+        x = f32(x); out = np.zeros_like(x)
+        check(self._lib.og_selftest_logf(self._h, ptr(x), x.size, ptr(out)), "og_selftest_logf")
+        return out
+
     # ---- per-slab drop-ins ---------------------------------------------------------------
     def innovation(self, gridded, xob, yob, obs_value, scale=1.0, use_first_guess=True):
         g = f32(gridded); jns, iew = g.shape

@@ -147,6 +147,12 @@ extern "C" int og_selftest_div(og_ctx* c, int n, unsigned seed, int rmax, long l
     if (!c || !bad || n <= 0 || rmax <= 0) return OG_ERR_INVALID;
     return div_selftest(c, n, seed, rmax, bad);
 }
+extern "C" int og_selftest_logf(og_ctx* c, const float* x, int n, float* out)
+{
+    OG_BIND(c);
+    if (!c || !x || !out || n <= 0) return OG_ERR_INVALID;
+    return logf_selftest(c, x, n, out);
+}
 extern "C" int og_host_alloc(void** p, size_t bytes)
 {
     if (!p) return OG_ERR_INVALID;

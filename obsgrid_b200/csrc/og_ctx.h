@@ -200,6 +200,7 @@ int mixing_ratio_device(og_ctx* ctx, float* rh, const float* t, const float* h, 
 // ---- misc (og_misc.cu) ---------------------------------------------------------------
 const char* last_error();
 int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches);
+int logf_selftest(og_ctx* ctx, const float* x, int n, float* out);
 int fp32_peak(og_ctx* ctx, double* lane_ops_per_s);
 // (jns,iew) y-fastest <-> (iew,jns) x-fastest for nlev stacked levels
 int transpose_levels(og_ctx* ctx, const float* src, float* dst, int rows_fast, int cols_slow,

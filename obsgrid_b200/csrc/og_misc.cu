@@ -2,6 +2,7 @@
 // micro-benchmark of libobsgrid_gpu.so.
 #include "og_ctx.h"
 #include "og_device.cuh"
+#include "og_logf.h"
 
 #include <stdarg.h>
 #include <string.h>
@@ -156,6 +157,25 @@ __global__ void div_selftest_kernel(int n, unsigned seed, int rmax, unsigned lon
     // compared by value: -0/b comes back +0 from the residual step, and the callers square it
     if (!(fdiv_with_rcp(a2, b2, refined_rcp(b2)) == fdiv(a2, b2)))
         atomicAdd(bad, 1ULL);
+}
+
+__global__ void logf_eval_kernel(const float* __restrict__ x, int n, float* __restrict__ out)
+{
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) out[q] = logf_glibc(x[q]);
+}
+
+int logf_selftest(og_ctx* ctx, const float* x, int n, float* out)
+{
+    float *dx, *dout;
+    OG_TRY(ctx->reserve_t("selftest.logf.x", (size_t)n, &dx));
+    OG_TRY(ctx->reserve_t("selftest.logf.o", (size_t)n, &dout));
+    OG_CUDA(cudaMemcpyAsync(dx, x, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    logf_eval_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dx, n, dout);
+    ctx->count_launch();
+    OG_CUDA(cudaMemcpyAsync(out, dout, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    OG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OG_OK;
 }
 
 int div_selftest(og_ctx* ctx, int n, unsigned seed, int rmax, long long* mismatches)

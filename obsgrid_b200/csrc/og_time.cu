@@ -6,6 +6,7 @@
 #include "og_ctx.h"
 #include "og_device.cuh"
 #include "og_capi_util.h"
+#include "og_logf.h"
 
 #include <math.h>
 #include <string.h>
@@ -43,14 +44,15 @@ constexpr int SEL_THREADS = 256;
 
 __device__ __forceinline__ bool not_missing(float r) { return fabsf(fsub(r, OG_MISSING_R)) > 1.f; }
 
-// ob_access_module.F90:476-486 / proc_qc.F90:315-319.  LOG is evaluated in double and rounded
-// once (glibc's logf is not reproducible bit-for-bit on the device).
+// ob_access_module.F90:476-486 / proc_qc.F90:315-319.  LOG is glibc's logf algorithm restated
+// (og_logf.h): the reference's gfortran build calls that routine, and the DEWPOINT flags follow it
+// bit for bit.
 __device__ __forceinline__ float dewpoint_dev(float t, float rh)
 {
     const float Rv_over_L = fdiv(1.f, 5418.12f);
     const float very_small_rh = 0.0001f;
     float arg = (rh < very_small_rh) ? fdiv(very_small_rh, 100.f) : fdiv(rh, 100.f);
-    float lg = (float)log((double)arg);
+    float lg = logf_glibc(arg);
     return fdiv(1.f, fsub(fdiv(1.f, t), fmul(Rv_over_L, lg)));
 }
 

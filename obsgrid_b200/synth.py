@@ -197,21 +197,23 @@ def default_oa_params(radii=(10, 8, 6, 4), surface_only=False, scale_rh=False,
     return p
 
 
-def first_guess(iew: int, jns: int, pressure: np.ndarray, phase: float = 0.0):
+def first_guess(iew: int, jns: int, pressure: np.ndarray, phase: float = 0.0, levels=None):
     """Analytic atmosphere: lapse-rate T with waves, a meandering zonal jet peaking 60 m/s at
     250 hPa over a weak background (so circle / ellipse / banana obs all occur aloft), RH
-    30-95 % with gradients, SLP 1000-1025 hPa waves.  Returns float32 (kbu, iew, jns)."""
+    30-95 % with gradients, SLP 1000-1025 hPa waves.  Returns float32 (kbu, iew, jns); with
+    `levels` only those levels of the configuration, in that order (same values)."""
     kbu = pressure.size
+    levels = list(range(kbu)) if levels is None else list(levels)
     i = np.arange(1, iew + 1, dtype=np.float64)[:, None]
     j = np.arange(1, jns + 1, dtype=np.float64)[None, :]
     X = i / iew; Y = j / jns
-    t = np.empty((kbu, iew, jns), np.float32); u = np.empty_like(t); v = np.empty_like(t)
+    t = np.empty((len(levels), iew, jns), np.float32); u = np.empty_like(t); v = np.empty_like(t)
     rh = np.empty_like(t)
     amp = 0.09 * jns; kw = 2 * np.pi * 3.0 / iew
     yc = jns / 2.0 + amp * np.sin(kw * i + phase)
     dyc = amp * kw * np.cos(kw * i + phase)
     width = 0.11 * jns
-    for k in range(kbu):
+    for slot, k in enumerate(levels):
         p = min(float(pressure[k]), 1000.0)
         tk = 288.0 * (p / 1000.0) ** 0.19 + 8.0 * np.sin(2 * np.pi * X + phase) * np.cos(
             2 * np.pi * Y) - 15.0 * (Y - 0.5)
@@ -225,7 +227,7 @@ def first_guess(iew: int, jns: int, pressure: np.ndarray, phase: float = 0.0):
             uk = uk * 0.6; vk = vk * 0.6
         rhk = 62.0 + 30.0 * np.sin(2 * np.pi * (X * 1.5 + 0.3 * k / kbu) + phase) * np.cos(
             2 * np.pi * Y * 1.2) - 20.0 * (1.0 - p / 1000.0)
-        t[k] = tk; u[k] = uk; v[k] = vk; rh[k] = np.clip(rhk, 5.0, 98.0)
+        t[slot] = tk; u[slot] = uk; v[slot] = vk; rh[slot] = np.clip(rhk, 5.0, 98.0)
     slp = (1012.5 + 10.0 * np.sin(2 * np.pi * X * 1.3 + phase) * np.cos(2 * np.pi * Y) +
            2.5 * np.cos(2 * np.pi * Y * 2.0)).astype(np.float32)
     return t, u, v, rh, slp
@@ -234,8 +236,13 @@ def first_guess(iew: int, jns: int, pressure: np.ndarray, phase: float = 0.0):
 def make_case(cfg: int | dict, seed: int | None = None, time_index: int = 0,
               n_sfc: int | None = None, n_snd: int | None = None, kbu: int | None = None,
               gross_frac: float = 0.02, scale_rh: bool = False, sfc_mult: float = 1.0,
-              sort_reports: bool = False) -> TimeCase:
-    """Build one analysis time of configuration `cfg` (1..5, or a dict like CONFIGS[n])."""
+              sort_reports: bool = False, levels=None) -> TimeCase:
+    """Build one analysis time of configuration `cfg` (1..5, or a dict like CONFIGS[n]).
+
+    levels: an increasing list of level indices starting with 0 -> a TimeCase that holds only those
+    levels of the configuration, with exactly the values the full case has there (the random stream
+    is advanced through the skipped levels): the parity tests of the largest configurations check
+    sampled levels without building 50 levels of 4000 x 4000 points."""
     c = dict(CONFIGS[cfg]) if not isinstance(cfg, dict) else dict(cfg)
     if n_sfc is not None: c["n_sfc"] = n_sfc
     if n_snd is not None: c["n_snd"] = n_snd
@@ -245,7 +252,12 @@ def make_case(cfg: int | dict, seed: int | None = None, time_index: int = 0,
     iew, jns, K = c["iew"], c["jns"], c["kbu"]
     pressure = pressure_levels(K)
     phase = 0.4 * time_index
-    t, u, v, rh, slp = first_guess(iew, jns, pressure, phase)
+    if levels is not None:
+        levels = [int(k) for k in levels]
+        assert levels and levels[0] == 0 and all(a < b for a, b in zip(levels, levels[1:])) and levels[-1] < K
+    lev = list(range(K)) if levels is None else levels
+    slot_of = {k: s_ for s_, k in enumerate(lev)}
+    t, u, v, rh, slp = first_guess(iew, jns, pressure, phase, lev)
 
     nrep = c["n_sfc"] + c["n_snd"]
     # station positions: 80 % uniform, 20 % in 2-D Gaussian clusters; strictly inside
@@ -275,6 +287,10 @@ def make_case(cfg: int | dict, seed: int | None = None, time_index: int = 0,
 
     def observe(g_ij, sigma, present, lo=None, hi=None, scale=1.0):
         # truth = first guess + smooth large-scale perturbation; ob = truth + noise (+ gross)
+        if g_ij is None:      # a level that is not kept: only advance the random stream
+            rng.normal(0.0, sigma, nrep); rng.random(nrep)
+            rng.choice([-1.0, 1.0], nrep); rng.uniform(5, 20, nrep)
+            return None
         truth = _bilinear64(g_ij.T.astype(np.float64), x64, y64) * scale
         truth = truth + 1.5 * sigma * np.sin(2 * np.pi * x64 / iew * 2.0 + phase) * np.cos(
             2 * np.pi * y64 / jns * 2.0)
@@ -287,16 +303,24 @@ def make_case(cfg: int | dict, seed: int | None = None, time_index: int = 0,
         out[present] = ob[present].astype(np.float32)
         return out
 
-    ob_u = np.empty((K, nrep), np.float32); ob_v = np.empty_like(ob_u)
+    KS = len(lev)
+    ob_u = np.empty((KS, nrep), np.float32); ob_v = np.empty_like(ob_u)
     ob_t = np.empty_like(ob_u); ob_rh = np.empty_like(ob_u)
     everyone = np.ones(nrep, bool)
     for k in range(K):
         present = everyone if k == 0 else is_snd
-        ob_u[k] = observe(u[k], sig["u"], present)
-        ob_v[k] = observe(v[k], sig["v"], present)
-        ob_t[k] = observe(t[k], sig["t"], present)
-        ob_rh[k] = observe(rh[k], sig["rh"], present, 1.0, 100.0)
+        s_ = slot_of.get(k)
+        if s_ is None:
+            for nm in ("u", "v", "t", "rh"):
+                observe(None, sig[nm], present)
+            continue
+        ob_u[s_] = observe(u[s_], sig["u"], present)
+        ob_v[s_] = observe(v[s_], sig["v"], present)
+        ob_t[s_] = observe(t[s_], sig["t"], present)
+        ob_rh[s_] = observe(rh[s_], sig["rh"], present, 1.0, 100.0)
     ob_slp = observe(slp, sig["slp"], everyone, scale=100.0)
+    pressure = pressure[lev]
+    K = KS
 
     z = lambda shape: np.zeros(shape, np.int32)
     case = TimeCase(iew=iew, jns=jns, kbu=K, dx_km=dx_km_like_driver(c["dx_m"]), pressure=pressure,

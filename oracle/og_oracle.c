@@ -27,6 +27,20 @@ void ogo_reset_stats(void) { memset(&g_stats, 0, sizeof g_stats); }
 void ogo_get_stats(ogo_stats* out) { *out = g_stats; }
 static void stats_add(int64_t* dst, int64_t v) { __atomic_fetch_add(dst, v, __ATOMIC_RELAXED); }
 
+/* Fast paths for the large configurations (BASELINE configs 3-5: up to 2 M reports on 4000^2 points).
+ * The as-written loops above/below stay the definition; these re-schedule the very same FP32
+ * operations and are held to them bit for bit by tests/test_oracle_fast_paths.py:
+ *   inner_threads > 1  ogo_cressman deals the grid rows to pthreads (a grid point's sums see the obs
+ *                      in the same ascending order); the binned buddy check deals the target bins.
+ *   buddy_binned != 0  the station loops of buddy_check visit spatial bins one buddy range wide
+ *                      instead of all N^2 pairs. */
+static int g_inner_threads = 1, g_buddy_binned = 0;
+void ogo_set_fast_paths(int buddy_binned, int inner_threads)
+{
+    g_buddy_binned = buddy_binned;
+    g_inner_threads = inner_threads > 1 ? inner_threads : 1;
+}
+
 static inline int f_nint(float x) { return (int)lroundf(x); } /* NINT */
 static inline int imax(int a, int b) { return a > b ? a : b; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
@@ -283,6 +297,55 @@ static void dist_uu_vv_rh(int iew_min, int iew_max, int jns_min, int jns_max, in
     }
 }
 
+/* The observation loop of cressman (oa_module.F90:116-190) restricted to the grid rows
+ * [j_lo, j_hi].  One band = all rows is the loop as written; several bands on several threads
+ * perform the same additions per grid point in the same (ascending ob) order. */
+typedef struct {
+    const float* obs; const float* xob; const float* yob; int numobs;
+    const float* gridded; int iew, jns, crsdot, var, radius_influence; float dxd;
+    const float* u_banana; const float* v_banana; float pressure;
+    int use_first_guess; const float* fg_value; int scale_cressman_rh_decreases;
+    float* numerator; float* denominator;
+    int j_lo, j_hi;
+    int64_t hits, cands, nshape[3];
+} cressman_band;
+
+static void* cressman_band_run(void* arg)
+{
+    cressman_band* B = (cressman_band*)arg;
+    const float* xob = B->xob; const float* yob = B->yob;
+    const int iew = B->iew, jns = B->jns, crsdot = B->crsdot, radius_influence = B->radius_influence;
+    const int var = B->var;
+    float rc2 = (float)crsdot / 2.f;
+    for (int n = 0; n < B->numobs; ++n) {
+        if ((xob[n] <= 1.f + rc2) || (yob[n] <= 1.f + rc2) ||
+            (xob[n] >= (float)iew - rc2) || (yob[n] >= (float)jns - rc2))
+            continue; /* :134-140 */
+        int iew_min = imax(f_nint(xob[n] - rc2) - 4 * radius_influence - 1, 1);
+        int jns_min = imax(f_nint(yob[n] - rc2) - 4 * radius_influence - 1, 1);
+        int iew_max = imin(f_nint(xob[n] - rc2) + 4 * radius_influence + 1, iew - crsdot);
+        int jns_max = imin(f_nint(yob[n] - rc2) + 4 * radius_influence + 1, jns - crsdot);
+        const int first_band = (B->j_lo == 1);       /* shapes are counted once per ob */
+        jns_min = imax(jns_min, B->j_lo); jns_max = imin(jns_max, B->j_hi);
+        if (jns_min > jns_max && !first_band) continue;
+        if (var == OG_VAR_UU || var == OG_VAR_VV || var == OG_VAR_RH) {
+            int shape = 0;
+            dist_uu_vv_rh(iew_min, iew_max, jns_min, jns_max, iew, jns, rc2, var, B->obs[n],
+                          xob[n], yob[n], B->dxd, B->pressure, B->u_banana, B->v_banana,
+                          radius_influence, B->gridded, B->fg_value ? B->fg_value[n] : 0.f,
+                          B->use_first_guess, B->numerator, B->denominator,
+                          B->scale_cressman_rh_decreases, &B->hits, &B->cands, &shape);
+            if (first_band) B->nshape[shape]++;
+        } else {
+            dist_not_uu_vv_rh(iew_min, iew_max, jns_min, jns_max, iew, rc2, B->obs[n], xob[n],
+                              yob[n], radius_influence, B->numerator, B->denominator, &B->hits,
+                              &B->cands);
+            if (first_band) B->nshape[0]++;
+        }
+    }
+    return NULL;
+}
+
 /* oa_module.F90:25-218 */
 void ogo_cressman(const float* obs, const float* xob, const float* yob, int numobs,
                   float* gridded, int iew, int jns, int crsdot, int var,
@@ -295,30 +358,27 @@ void ogo_cressman(const float* obs, const float* xob, const float* yob, int numo
     float* numerator = (float*)calloc(npts, sizeof(float));
     float* denominator = (float*)calloc(npts, sizeof(float));
     float* perturbation = (float*)calloc(npts, sizeof(float));
-    float rc2 = (float)crsdot / 2.f;
     int64_t hits = 0, cands = 0, nshape[3] = {0, 0, 0};
 
-    for (int n = 0; n < numobs; ++n) {
-        if ((xob[n] <= 1.f + rc2) || (yob[n] <= 1.f + rc2) ||
-            (xob[n] >= (float)iew - rc2) || (yob[n] >= (float)jns - rc2))
-            continue; /* :134-140 */
-        int iew_min = imax(f_nint(xob[n] - rc2) - 4 * radius_influence - 1, 1);
-        int jns_min = imax(f_nint(yob[n] - rc2) - 4 * radius_influence - 1, 1);
-        int iew_max = imin(f_nint(xob[n] - rc2) + 4 * radius_influence + 1, iew - crsdot);
-        int jns_max = imin(f_nint(yob[n] - rc2) + 4 * radius_influence + 1, jns - crsdot);
-        if (var == OG_VAR_UU || var == OG_VAR_VV || var == OG_VAR_RH) {
-            int shape = 0;
-            dist_uu_vv_rh(iew_min, iew_max, jns_min, jns_max, iew, jns, rc2, var, obs[n],
-                          xob[n], yob[n], dxd, pressure, u_banana, v_banana, radius_influence,
-                          gridded, fg_value ? fg_value[n] : 0.f, use_first_guess, numerator,
-                          denominator, scale_cressman_rh_decreases, &hits, &cands, &shape);
-            nshape[shape]++;
-        } else {
-            dist_not_uu_vv_rh(iew_min, iew_max, jns_min, jns_max, iew, rc2, obs[n], xob[n],
-                              yob[n], radius_influence, numerator, denominator, &hits, &cands);
-            nshape[0]++;
-        }
+    const int nband = (g_inner_threads > 1 && jns >= 4 * g_inner_threads) ? g_inner_threads : 1;
+    cressman_band* bands = (cressman_band*)calloc((size_t)nband, sizeof(cressman_band));
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nband);
+    for (int b = 0; b < nband; ++b) {
+        bands[b] = (cressman_band){obs, xob, yob, numobs, gridded, iew, jns, crsdot, var,
+                                   radius_influence, dxd, u_banana, v_banana, pressure,
+                                   use_first_guess, fg_value, scale_cressman_rh_decreases,
+                                   numerator, denominator,
+                                   1 + (int)((long long)jns * b / nband),
+                                   (int)((long long)jns * (b + 1) / nband), 0, 0, {0, 0, 0}};
+        if (nband > 1) pthread_create(&th[b], NULL, cressman_band_run, &bands[b]);
+        else cressman_band_run(&bands[b]);
     }
+    for (int b = 0; b < nband; ++b) {
+        if (nband > 1) pthread_join(th[b], NULL);
+        hits += bands[b].hits; cands += bands[b].cands;
+        for (int q = 0; q < 3; ++q) nshape[q] += bands[b].nshape[q];
+    }
+    free(bands); free(th);
     for (size_t p = 0; p < npts; ++p) /* :195-197 */
         if (denominator[p] > 0.f) perturbation[p] = numerator[p] / denominator[p];
 
@@ -444,6 +504,14 @@ float ogo_dewpoint(float t, float rh)
     return 1.f / (1.f / t - Rv_over_L * logf(rh / 100.f));
 }
 
+/* The LOG of the lines above as the reference build evaluates it: gfortran's LOG(REAL(4)) is a call
+ * of the host libm's logf.  Exposed so that the tests can hold the device's restatement of that
+ * routine (obsgrid_b200/csrc/og_logf.h) to it over whole argument ranges. */
+void ogo_logf_array(const float* x, int n, float* out)
+{
+    for (int i = 0; i < n; ++i) out[i] = logf(x[i]);
+}
+
 /* qc1_module.F90:9-300 */
 void ogo_error_max(const float* obs, const float* xob, const float* yob,
                    const float* station_elevation, int* qc_flag, int n,
@@ -502,6 +570,236 @@ void ogo_error_max(const float* obs, const float* xob, const float* yob,
     free(err); free(factor); free(fd); free(aob);
 }
 
+/* ---- binned station loops of buddy_check (fast path, see ogo_set_fast_paths) ---------------
+ * station_loop_2 / _3 of qc2_module.F90:223-329 with the pairs restricted to spatial bins one
+ * buddy range wide.  Same operations per pair, same order per sum:
+ *   pass 1  the as-written loop nest is "for num: for num3 ascending: sum(num) += diff(num3)";
+ *           here the nest is swapped -- "for num3 ascending: for every num in the 3x3 bins around
+ *           num3" -- so each target still receives its buddies' diffs in ascending num3.
+ *   pass 2  the removal loop (:272-286) can only fire for buddies with diff > 1.25*difmax
+ *           ("suspects"; difmax either plain or relaxed by :327); per station, in ascending
+ *           station order so that the x1.2 relaxation of earlier stations is seen, the suspects of
+ *           the 3x3 bins are visited in ascending index. */
+typedef struct {
+    int numobs; const float* xob; const float* yob; const float* diff_all; float dx, range;
+    const int* bin_start; const int* bin_list; int nbx, nby;
+    /* targets in bin order (list position e): station index and coordinates, count and sum */
+    const float* l_x; const float* l_y; int* l_cnt; float* l_sum;
+    int* next_bin;                   /* shared work counter: one target bin per grab */
+    int64_t pairs;
+    char pad[64];                    /* one cache line per thread's counters */
+} buddy_band;
+
+static int cmp_int(const void* a, const void* b) { return (*(const int*)a > *(const int*)b) - (*(const int*)a < *(const int*)b); }
+
+/* One candidate num3 against the nt targets of a bin (qc2_module.F90:233-246 for every num of the
+ * bin): branch-free so that the compiler can vectorise it; every lane performs the as-written
+ * operations (the compiler may not reassociate or contract: no fast-math, -ffp-contract=off). */
+__attribute__((optimize("O3", "tree-vectorize", "no-trapping-math", "no-math-errno"), target_clones("avx2", "default")))
+static void buddy_targets_of_bin(int nt, const int* restrict t_idx, const float* restrict t_x,
+                                 const float* restrict t_y, int* restrict t_cnt,
+                                 float* restrict t_sum, int num3, float x3, float y3, float d3,
+                                 float dx, float range)
+{
+    for (int e = 0; e < nt; ++e) {
+        float x = t_x[e] - x3;          /* xob(num) - xob(num3) */
+        float y = t_y[e] - y3;
+        float distance = sqrtf(x * x + y * y) * dx;
+        int is_buddy = (distance <= range) & (distance >= 0.1f) & (t_idx[e] != num3);
+        t_cnt[e] = t_cnt[e] + is_buddy;
+        t_sum[e] = is_buddy ? t_sum[e] + d3 : t_sum[e];
+    }
+}
+
+static void* buddy_pass1_band(void* arg)
+{
+    buddy_band* B = (buddy_band*)arg;
+    const int nbx = B->nbx, nby = B->nby, nbin = nbx * nby;
+    int cap = 4096;
+    int* cand = (int*)malloc(sizeof(int) * (size_t)cap);
+    int ccap = 0;
+    float *c_x = NULL, *c_y = NULL, *c_d = NULL;
+    int64_t pairs = 0;
+    for (;;) {
+        const int c = __atomic_fetch_add(B->next_bin, 1, __ATOMIC_RELAXED);
+        if (c >= nbin) break;
+        const int t0 = B->bin_start[c], nt = B->bin_start[c + 1] - t0;
+        if (nt == 0) continue;
+        /* the stations of the 3x3 bins around c, ascending: every target of c meets its buddies in
+         * the order of the as-written num3 loop */
+        const int bx = c % nbx, by = c / nbx;
+        int nc = 0;
+        for (int cy = imax(by - 1, 0); cy <= imin(by + 1, nby - 1); ++cy)
+            for (int cx = imax(bx - 1, 0); cx <= imin(bx + 1, nbx - 1); ++cx) {
+                const int q = cy * nbx + cx, m = B->bin_start[q + 1] - B->bin_start[q];
+                if (nc + m > cap) { while (nc + m > cap) cap *= 2; cand = (int*)realloc(cand, sizeof(int) * (size_t)cap); }
+                memcpy(cand + nc, B->bin_list + B->bin_start[q], sizeof(int) * (size_t)m);
+                nc += m;
+            }
+        qsort(cand, (size_t)nc, sizeof(int), cmp_int);
+        if (nc > ccap) {
+            ccap = nc + nc / 4;
+            c_x = (float*)realloc(c_x, sizeof(float) * (size_t)ccap);
+            c_y = (float*)realloc(c_y, sizeof(float) * (size_t)ccap);
+            c_d = (float*)realloc(c_d, sizeof(float) * (size_t)ccap);
+        }
+        for (int q = 0; q < nc; ++q) { c_x[q] = B->xob[cand[q]]; c_y[q] = B->yob[cand[q]]; c_d[q] = B->diff_all[cand[q]]; }
+        /* targets in chunks that stay in the L1 cache while the candidates stream by */
+        for (int e0 = 0; e0 < nt; e0 += 1024) {
+            const int m = imin(1024, nt - e0), o = t0 + e0;
+            for (int q = 0; q < nc; ++q)
+                buddy_targets_of_bin(m, B->bin_list + o, B->l_x + o, B->l_y + o, B->l_cnt + o,
+                                     B->l_sum + o, cand[q], c_x[q], c_y[q], c_d[q], B->dx, B->range);
+        }
+        pairs += (int64_t)nc * nt - nt;
+    }
+    free(cand); free(c_x); free(c_y); free(c_d);
+    B->pairs = pairs;
+    return NULL;
+}
+
+
+static void buddy_station_loops_binned(const float* obs, int numobs, const float* xob,
+                                       const float* yob, int* qc_flag, const float* aob,
+                                       float* difmax, int iew, int jns, float dx, float range,
+                                       float* err, int* buddy_num, int* buddy_num_final,
+                                       int64_t* pairs_examined)
+{
+    size_t nn = (size_t)(numobs > 0 ? numobs : 1);
+    /* |x| <= sqrtf(x*x + y*y) up to an ulp: a pair within range is at most `reach` cells apart in
+     * either coordinate, so its two stations sit in the same or in adjacent bins */
+    const float reach = range / dx * 1.001f + 1.f;
+    const int bs = imax(1, (int)ceilf(reach));
+    const int nbx = iew / bs + 2, nby = jns / bs + 2;
+    const int nbin = nbx * nby;
+    int* bin_of = (int*)malloc(sizeof(int) * nn);
+    int* bin_start = (int*)calloc((size_t)nbin + 1, sizeof(int));
+    int* bin_list = (int*)malloc(sizeof(int) * nn);
+    float* diff_all = (float*)malloc(sizeof(float) * nn);
+    float* sum = (float*)calloc(nn, sizeof(float));
+    float* l_x = (float*)malloc(sizeof(float) * nn);
+    float* l_y = (float*)malloc(sizeof(float) * nn);
+    float* l_sum = (float*)calloc(nn, sizeof(float));
+    int* l_cnt = (int*)calloc(nn, sizeof(int));
+    for (int i = 0; i < numobs; ++i) {
+        int bx = imin(imax((int)(xob[i] / (float)bs), 0), nbx - 1);
+        int by = imin(imax((int)(yob[i] / (float)bs), 0), nby - 1);
+        bin_of[i] = by * nbx + bx;
+        bin_start[bin_of[i] + 1]++;
+        diff_all[i] = obs[i] - aob[i];          /* :243 for every station as a buddy */
+        buddy_num[i] = 0;
+    }
+    for (int c = 0; c < nbin; ++c) bin_start[c + 1] += bin_start[c];
+    int* cursor = (int*)malloc(sizeof(int) * ((size_t)nbin + 1));
+    memcpy(cursor, bin_start, sizeof(int) * ((size_t)nbin + 1));
+    for (int i = 0; i < numobs; ++i) {                                    /* ascending inside a bin */
+        const int e = cursor[bin_of[i]]++;
+        bin_list[e] = i; l_x[e] = xob[i]; l_y[e] = yob[i];
+    }
+
+    /* pass 1 */
+    const int nthr = (g_inner_threads > 1 && numobs >= 4096) ? g_inner_threads : 1;
+    buddy_band* bands = (buddy_band*)calloc((size_t)nthr, sizeof(buddy_band));
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthr);
+    int next_bin = 0;
+    for (int t = 0; t < nthr; ++t) {
+        bands[t] = (buddy_band){numobs, xob, yob, diff_all, dx, range, bin_start, bin_list, nbx, nby,
+                                l_x, l_y, l_cnt, l_sum, &next_bin, 0, {0}};
+        if (nthr > 1) pthread_create(&th[t], NULL, buddy_pass1_band, &bands[t]);
+        else buddy_pass1_band(&bands[t]);
+    }
+    for (int t = 0; t < nthr; ++t) {
+        if (nthr > 1) pthread_join(th[t], NULL);
+        *pairs_examined += bands[t].pairs;
+    }
+    free(bands); free(th);
+    for (int e = 0; e < numobs; ++e) { buddy_num[bin_list[e]] = l_cnt[e]; sum[bin_list[e]] = l_sum[e]; }
+    free(l_x); free(l_y); free(l_sum); free(l_cnt);
+
+    /* suspects per bin, ascending */
+    int* s_start = (int*)calloc((size_t)nbin + 1, sizeof(int));
+    int* s_list = (int*)malloc(sizeof(int) * nn);
+    {
+        int w = 0;
+        for (int c = 0; c < nbin; ++c) {
+            s_start[c] = w;
+            for (int e = bin_start[c]; e < bin_start[c + 1]; ++e) {
+                const int k = bin_list[e];
+                if (diff_all[k] > fminf(difmax[k], 1.2f * difmax[k]) * 1.25f) s_list[w++] = k;
+            }
+        }
+        s_start[nbin] = w;
+    }
+
+    /* the suspects of the 3x3 bins around every bin, merged ascending (shared by the bin's stations) */
+    int* m_start = (int*)calloc((size_t)nbin + 1, sizeof(int));
+    for (int c = 0; c < nbin; ++c) {
+        const int bx = c % nbx, by = c / nbx;
+        int m = 0;
+        if (bin_start[c + 1] > bin_start[c])
+            for (int cy = imax(by - 1, 0); cy <= imin(by + 1, nby - 1); ++cy)
+                for (int cx = imax(bx - 1, 0); cx <= imin(bx + 1, nbx - 1); ++cx)
+                    m += s_start[cy * nbx + cx + 1] - s_start[cy * nbx + cx];
+        m_start[c + 1] = m_start[c] + m;
+    }
+    int* m_list = (int*)malloc(sizeof(int) * (size_t)(m_start[nbin] > 0 ? m_start[nbin] : 1));
+    for (int c = 0; c < nbin; ++c) {
+        if (m_start[c + 1] == m_start[c]) continue;
+        const int bx = c % nbx, by = c / nbx;
+        int w = m_start[c];
+        for (int cy = imax(by - 1, 0); cy <= imin(by + 1, nby - 1); ++cy)
+            for (int cx = imax(bx - 1, 0); cx <= imin(bx + 1, nbx - 1); ++cx) {
+                const int q = cy * nbx + cx, m = s_start[q + 1] - s_start[q];
+                memcpy(m_list + w, s_list + s_start[q], sizeof(int) * (size_t)m);
+                w += m;
+            }
+        qsort(m_list + m_start[c], (size_t)(m_start[c + 1] - m_start[c]), sizeof(int), cmp_int);
+    }
+
+    /* pass 2, stations in order (:249-327) */
+    float average = 0.f;
+    for (int num = 0; num < numobs; ++num) {
+        float diff_at_obs = obs[num] - aob[num];
+        float s = sum[num];
+        if (buddy_num[num] > 0) average = s / (float)buddy_num[num];
+        if (buddy_num[num] >= 2) {
+            int kob = buddy_num[num];
+            const int b = bin_of[num];
+            for (int q = m_start[b]; q < m_start[b + 1]; ++q) {
+                const int num3 = m_list[q];
+                if (num3 == num) continue;
+                float x = xob[num] - xob[num3];
+                float y = yob[num] - yob[num3];
+                float distance = sqrtf(x * x + y * y) * dx;
+                ++*pairs_examined;
+                if (!(distance <= range && distance >= 0.1f)) continue;
+                float diff_check_1 = difmax[num3] * 1.25f;
+                float diff_check_2 = difmax[num3];
+                float diff_numj = fabsf(diff_all[num3] - average);
+                if (diff_all[num3] > diff_check_1 && diff_numj > diff_check_2) {
+                    kob = kob - 1;
+                    s = s - diff_all[num3];
+                }
+            }
+            buddy_num_final[num] = kob;
+            if (kob >= 2) {
+                average = s / (float)kob;
+                err[num] = diff_at_obs - average;
+            } else {
+                err[num] = 0.f;
+                ogo_add_to_qc_flag(&qc_flag[num], OG_NO_BUDDIES);
+            }
+        } else {
+            err[num] = 0.f;
+            ogo_add_to_qc_flag(&qc_flag[num], OG_NO_BUDDIES);
+        }
+        if (buddy_num_final[num] == 2) difmax[num] = 1.2f * difmax[num]; /* :327 */
+    }
+    free(m_start); free(m_list);
+    free(s_start); free(s_list);
+    free(bin_of); free(bin_start); free(bin_list); free(cursor); free(diff_all); free(sum);
+}
+
 /* qc2_module.F90:9-388 */
 void ogo_buddy_check(const float* obs, int numobs, const float* xob, const float* yob,
                      int* qc_flag, const float* station_elevation, const float* gridded,
@@ -509,7 +807,6 @@ void ogo_buddy_check(const float* obs, int numobs, const float* xob, const float
                      float buddy_difference, float* aob_out, float* err_out,
                      float* difmax_out, int* bnf_out)
 {
-    (void)jns;
     size_t nn = (size_t)(numobs > 0 ? numobs : 1);
     float* err = (float*)malloc(sizeof(float) * nn);
     float* diff = (float*)malloc(sizeof(float) * nn);
@@ -570,6 +867,13 @@ void ogo_buddy_check(const float* obs, int numobs, const float* xob, const float
     for (int i = 0; i < numobs; ++i) difmax[i] = difmax[i] * buddy_weight; /* :193 */
     for (int i = 0; i < numobs; ++i) aob[i] = bilinear(gridded, iew, xob[i], yob[i]);
 
+    if (g_buddy_binned) {
+        int64_t examined = 0;
+        buddy_station_loops_binned(obs, numobs, xob, yob, qc_flag, aob, difmax, iew, jns, dx,
+                                   range, err, buddy_num, buddy_num_final, &examined);
+        stats_add(&g_stats.buddy_pairs_examined, examined);
+        pair_tests = (int64_t)numobs * (numobs > 0 ? numobs - 1 : 0);   /* what the N^2 loop runs */
+    } else
     for (int num = 0; num < numobs; ++num) { /* station_loop_2, :223-329 */
         buddy_num[num] = 0;
         for (int num3 = 0; num3 < numobs; ++num3) {
@@ -967,26 +1271,45 @@ int ogo_oa_time(const og_time_desc* d, const og_oa_params* p, int k_begin, int k
 
 /* ---- pthread fan-out -------------------------------------------------------------------
  * OA: one job per (level, variable) slab -- slabs are independent once the pre-analysis winds
- * of every level have been snapshotted; QC: one job per level (DEWPOINT reads the
- * RH flags of its own level). */
+ * of every level have been snapshotted; QC: one job per level and variable group
+ * (DEWPOINT reads the RH flags of its own level).  Jobs over many observations ("big": the
+ * surface slabs of configs 3-5) run one after the other, each on all threads through the
+ * inner fast paths (ogo_set_fast_paths); the many small ones share a pool, one thread each. */
 typedef struct {
     const og_time_desc* d; const og_oa_params* po; const og_qc_params* pq;
     int k_begin, k_end; int* next; int rc;
     const float* ub_all; const float* vb_all;   /* [k_end-k_begin][jns][iew] */
+    const unsigned char* big;                   /* [nlev*5]: handled outside the pool */
 } mt_job;
+
+static const int k_qc_masks[5] = {1 << 0, 1 << 1, 1 << 2, 1 << 4, (1 << 3) | (1 << 6)};
+
+static int level_ob_count(const og_time_desc* d, int k)
+{
+    int n = 0;
+    const float* t = d->ob_t + (size_t)k * d->nrep;
+    for (int r = 0; r < d->nrep; ++r) n += not_missing(t[r]);
+    return n;
+}
+
+static int oa_job(const mt_job* j, int q)
+{
+    const size_t npts = (size_t)j->d->iew * j->d->jns;
+    int k = j->k_begin + q / 5, ivar = 1 + q % 5;   /* surface (largest) slabs first */
+    if (j->po->surface_only && k > 0) return OG_OK;
+    return oa_slab_job(j->d, j->po, k, ivar, j->ub_all + npts * (size_t)(k - j->k_begin),
+                       j->vb_all + npts * (size_t)(k - j->k_begin));
+}
 
 static void* oa_worker(void* arg)
 {
     mt_job* j = (mt_job*)arg;
-    const size_t npts = (size_t)j->d->iew * j->d->jns;
     const int nlev = j->k_end - j->k_begin;
     for (;;) {
         int q = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
         if (q >= nlev * 5) break;
-        int k = j->k_begin + q / 5, ivar = 1 + q % 5;   /* surface (largest) slabs first */
-        if (j->po->surface_only && k > 0) continue;
-        int r = oa_slab_job(j->d, j->po, k, ivar, j->ub_all + npts * (size_t)(k - j->k_begin),
-                            j->vb_all + npts * (size_t)(k - j->k_begin));
+        if (j->big[q]) continue;
+        int r = oa_job(j, q);
         if (r != OG_OK) j->rc = r;
     }
     return NULL;
@@ -994,16 +1317,25 @@ static void* oa_worker(void* arg)
 static void* qc_worker(void* arg)
 {
     mt_job* j = (mt_job*)arg;
-    /* per level five independent jobs: UU, VV, TT, PMSL, and RH followed by DEWPOINT (which
-     * reads the RH flags, ob_access_module.F90:466-487) */
-    static const int masks[5] = {1 << 0, 1 << 1, 1 << 2, 1 << 4, (1 << 3) | (1 << 6)};
     const int nlev = j->k_end - j->k_begin;
     for (;;) {
         int q = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
         if (q >= nlev * 5) break;
-        qc_level(j->d, j->pq, j->k_begin + q / 5, masks[q % 5]);
+        if (j->big[q]) continue;
+        qc_level(j->d, j->pq, j->k_begin + q / 5, k_qc_masks[q % 5]);
     }
     return NULL;
+}
+
+/* big[q] for the jobs of the levels [k_begin,k_end): more than `limit` observations */
+static unsigned char* mark_big_jobs(const og_time_desc* d, int k_begin, int k_end, int limit)
+{
+    const int nlev = k_end - k_begin;
+    unsigned char* big = (unsigned char*)calloc((size_t)(nlev > 0 ? nlev : 1) * 5, 1);
+    for (int k = k_begin; k < k_end; ++k)
+        if (level_ob_count(d, k) > limit)
+            for (int v = 0; v < 5; ++v) big[(k - k_begin) * 5 + v] = 1;
+    return big;
 }
 
 int ogo_oa_time_mt(const og_time_desc* d, const og_oa_params* p, int k_begin, int k_end,
@@ -1021,14 +1353,22 @@ int ogo_oa_time_mt(const og_time_desc* d, const og_oa_params* p, int k_begin, in
         slab_get(d->v, d->iew, d->jns, k, vb + npts * (size_t)(k - k_begin));
     }
     int next = 0, rc = OG_OK;
+    unsigned char* big = mark_big_jobs(d, k_begin, k_end, 30000);
+    const int saved_inner = g_inner_threads;
+    mt_job seq = {d, p, NULL, k_begin, k_end, &next, OG_OK, ub, vb, big};
+    g_inner_threads = threads;
+    for (int q = 0; q < nlev * 5; ++q)
+        if (big[q]) { int r = oa_job(&seq, q); if (r != OG_OK) rc = r; }
+    g_inner_threads = 1;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
     mt_job* jobs = (mt_job*)malloc(sizeof(mt_job) * (size_t)threads);
     for (int t = 0; t < threads; ++t) {
-        jobs[t] = (mt_job){d, p, NULL, k_begin, k_end, &next, OG_OK, ub, vb};
+        jobs[t] = (mt_job){d, p, NULL, k_begin, k_end, &next, OG_OK, ub, vb, big};
         pthread_create(&th[t], NULL, oa_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; ++t) { pthread_join(th[t], NULL); if (jobs[t].rc) rc = jobs[t].rc; }
-    free(th); free(jobs); free(ub); free(vb);
+    g_inner_threads = saved_inner;
+    free(th); free(jobs); free(ub); free(vb); free(big);
     return rc;
 }
 
@@ -1037,14 +1377,23 @@ int ogo_qc_time_mt(const og_time_desc* d, const og_qc_params* p, int k_begin, in
 {
     if (threads <= 1) return ogo_qc_time(d, p, k_begin, k_end, run_consistency);
     int next = 0;
+    const int nlev = k_end - k_begin;
+    unsigned char* big = mark_big_jobs(d, k_begin, k_end, 30000);
+    const int saved_inner = g_inner_threads;
+    if (!g_buddy_binned) memset(big, 0, (size_t)(nlev > 0 ? nlev : 1) * 5);   /* the N^2 loops do not split */
+    g_inner_threads = threads;
+    for (int q = 0; q < nlev * 5; ++q)
+        if (big[q]) qc_level(d, p, k_begin + q / 5, k_qc_masks[q % 5]);
+    g_inner_threads = 1;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
     mt_job* jobs = (mt_job*)malloc(sizeof(mt_job) * (size_t)threads);
     for (int t = 0; t < threads; ++t) {
-        jobs[t] = (mt_job){d, NULL, p, k_begin, k_end, &next, OG_OK, NULL, NULL};
+        jobs[t] = (mt_job){d, NULL, p, k_begin, k_end, &next, OG_OK, NULL, NULL, big};
         pthread_create(&th[t], NULL, qc_worker, &jobs[t]);
     }
     for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
-    free(th); free(jobs);
+    g_inner_threads = saved_inner;
+    free(th); free(jobs); free(big);
     if (run_consistency) qc_consistency(d, k_begin, k_end);
     return OG_OK;
 }

@@ -31,9 +31,15 @@ typedef struct ogo_stats {
     int64_t cressman_candidates;   /* inner-loop iterations (window sweep)           */
     int64_t buddy_pair_tests;      /* executions of qc2_module.F90:233-236           */
     int64_t n_circle, n_ellipse, n_banana;
+    int64_t buddy_pairs_examined;  /* binned fast path: pair tests actually run             */
 } ogo_stats;
 
 void ogo_reset_stats(void);
+/* Fast paths for the large configurations (same FP32 operations, re-scheduled; bit-identical to
+ * the as-written loops, tests/test_oracle_fast_paths.py).  buddy_binned: spatial bins instead of
+ * the N^2 station loops of buddy_check; inner_threads: pthreads inside one cressman / buddy_check
+ * call (grid rows / target bins dealt out). */
+void ogo_set_fast_paths(int buddy_binned, int inner_threads);
 void ogo_get_stats(ogo_stats* out);
 
 void ogo_innovation(const float* gridded, int iew, int jns, const float* xob,
@@ -83,6 +89,8 @@ void ogo_obs_distance(const float* tobbox, float* distance, int iew, int jns, fl
 /* DEWPOINT first-guess field of proc_qc.F90:315-319 and dewpoint ob of
  * ob_access_module.F90:476-486 (same formula). */
 float ogo_dewpoint(float t, float rh);
+/* libm's logf (what gfortran's LOG calls) over an array. */
+void ogo_logf_array(const float* x, int n, float* out);
 
 /* proc_qc / proc_oa level x variable loops over the flat observation table. */
 int ogo_qc_time(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,

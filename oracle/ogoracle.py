@@ -21,7 +21,8 @@ _vp = C.c_void_p
 
 class OgoStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("cressman_updates", "cressman_candidates",
-                                         "buddy_pair_tests", "n_circle", "n_ellipse", "n_banana")]
+                                         "buddy_pair_tests", "n_circle", "n_ellipse", "n_banana",
+                                         "buddy_pairs_examined")]
 
 
 def build(force: bool = False) -> Path:
@@ -83,6 +84,11 @@ def lib():
         l.ogo_get_stats.argtypes = [C.POINTER(OgoStats)]
         _lib = l
     return _lib
+
+
+def set_fast_paths(buddy_binned: bool = False, inner_threads: int = 1):
+    """Bit-identical re-schedulings of the as-written loops for the large configurations."""
+    lib().ogo_set_fast_paths(int(buddy_binned), int(inner_threads))
 
 
 def reset_stats():
@@ -255,6 +261,15 @@ def mixing_ratio(rh, t, h, terrain, slp_x_pa, pressure):
 
 def dewpoint(t, rh):
     return lib().ogo_dewpoint(float(t), float(rh))
+
+
+def logf(x):
+    """The host libm's logf over an array (gfortran's LOG)."""
+    x = f32(x); out = np.zeros_like(x)
+    l = lib()
+    l.ogo_logf_array.argtypes = [_vp, C.c_int, _vp]
+    l.ogo_logf_array(ptr(x), x.size, ptr(out))
+    return out
 
 
 def qc_time(case, k_begin=0, k_end=None, run_consistency=True, threads=1):
