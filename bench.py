@@ -128,10 +128,31 @@ def build_case(args, rank: int):
     return case
 
 
+def workload_config(case, args, world: int) -> dict:
+    """The `config` object of the JSON line: what is analysed, identical for both arms."""
+    return {"workload": case.label, "times_per_step": 1 if args.scaling == "strong" else world,
+            "grid": [case.iew, case.jns], "levels": int(case.kbu), "reports": case.nrep,
+            "scans": [int(r) for r in case.oa_params.radius_influence if r >= 0],
+            "scale_cressman_rh_decreases": bool(case.oa_params.scale_cressman_rh_decreases)}
+
+
+def qc_like_the_gpu_arm(O, case, threads: int):
+    """proc_qc of every level before the timed proc_oa, so that the CPU arm analyses exactly the
+    observations the GPU arm does (obs that fail QC are not used, proc_oa.F90:462).  Untimed, through
+    the oracle's binned buddy check (bit-identical to the N^2 station loops)."""
+    O.set_fast_paths(True, 1)
+    try:
+        O.qc_time(case, threads=threads)
+    finally:
+        O.set_fast_paths(False, 1)
+
+
 # ------------------------------------------------------------------------------------------
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU algorithm (oracle port; the Fortran original
-    cannot be built in this image) on all host threads, bounded sample per step."""
+    cannot be built in this image: no Fortran compiler, no netCDF -- profiles/r2/toolchain_probe.txt)
+    on all host threads.  One step = proc_oa of one analysis time after the same proc_qc the GPU arm
+    runs (untimed here: the metric is Cressman updates per second); bounded by --ref-levels."""
     if rank != 0:
         return
     from oracle import ogoracle as O
@@ -139,10 +160,11 @@ def run_reference(args, rank: int, world: int):
     threads = os.cpu_count() or 1
     k_end = min(case0.kbu, args.ref_levels)
     sample = (f"proc_oa over levels [0,{k_end}) of {case0.kbu} of {case0.label} "
-              f"(all 5 surface slabs + {4 * (k_end - 1)} upper slabs), {threads} pthreads over levels")
+              f"(all 5 surface slabs + {4 * (k_end - 1)} upper slabs) after proc_qc of every level, "
+              f"{threads} pthreads (slabs dealt to threads; grid rows inside the large slabs)")
     times, upd = [], 0
     qc_done = case0.copy()
-    O.qc_time(qc_done, 1, min(case0.kbu, 3), threads=threads)      # realistic flags aloft
+    qc_like_the_gpu_arm(O, qc_done, threads)
     for it in range(args.warmup + args.steps):
         c = qc_done.copy()
         O.reset_stats()
@@ -156,28 +178,40 @@ def run_reference(args, rank: int, world: int):
     val = upd / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": case0.label, "sample": sample},
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(case0, args, world),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": sample},
+                             "sample": sample, "updates_per_step": upd},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(args, case0):
-    """Oracle timed on the host cores on a bounded sample of the same workload (rank 0, N=1)."""
+    """Oracle timed on the host cores on a bounded sample of the same workload (rank 0, N=1):
+    proc_oa on all threads and on one thread (the reference is serial), the as-written N^2 buddy
+    check on the upper levels."""
     from oracle import ogoracle as O
     threads = os.cpu_count() or 1
     k_end = min(case0.kbu, args.ref_levels)
-    c = case0.copy()
+    qc_done = case0.copy()
+    qc_like_the_gpu_arm(O, qc_done, threads)
+    c = qc_done.copy()
     O.reset_stats()
     t0 = time.perf_counter()
     O.oa_time(c, 0, k_end, threads=threads)
     t_oa = time.perf_counter() - t0
     st = O.get_stats()
-    # buddy check: upper levels only (5 k obs each); the 50 k-ob surface slabs are N^2 = 2.5e9
-    # pair tests apiece on one thread and would blow the bound
+    # one thread, like the reference itself: a few upper levels (about a tenth of the time)
+    k1a, k1b = min(1, case0.kbu - 1), min(case0.kbu, 1 + args.ref_single_levels)
+    c = qc_done.copy()
+    O.reset_stats()
+    t0 = time.perf_counter()
+    O.oa_time(c, k1a, k1b, threads=1)
+    t_one = time.perf_counter() - t0
+    s1 = O.get_stats()
+    # buddy check as written: upper levels only (5 k obs each); the 50 k-ob surface slabs are
+    # N^2 = 2.5e9 pair tests apiece on one thread and would blow the bound
     c = case0.copy()
     O.reset_stats()
     kq0, kq1 = 1, min(case0.kbu, 1 + args.ref_qc_levels)
@@ -192,10 +226,14 @@ def cpu_baseline(args, case0):
         n_obs_qc += int(np.count_nonzero((np.abs(case0.ob_rh[k] + 888888.0) > 1) &
                                          (np.abs(case0.ob_t[k] + 888888.0) > 1)))
     return {"value": st["cressman_updates"] / t_oa, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": (f"proc_oa levels [0,{k_end}) of {case0.kbu} ({t_oa:.1f} s, "
+            "sample": (f"proc_oa levels [0,{k_end}) of {case0.kbu} after proc_qc of every level ({t_oa:.1f} s, "
                        f"{st['cressman_updates']:.3e} updates, {st['cressman_candidates']:.3e} "
-                       f"window iterations); buddy: proc_qc levels [{kq0},{kq1}) "
+                       f"window iterations); buddy: proc_qc levels [{kq0},{kq1}) as written "
                        f"({t_qc:.1f} s, {sq['buddy_pair_tests']:.3e} pair tests)"),
+            "updates_per_step": st["cressman_updates"],
+            "single_thread": {"value": s1["cressman_updates"] / t_one, "unit": UNIT, "cores": 1,
+                              "sample": f"proc_oa levels [{k1a},{k1b}) on one thread ({t_one:.1f} s, "
+                                        f"{s1['cressman_updates']:.3e} updates)"},
             "buddy_obs_per_s": n_obs_qc / t_qc, "buddy_pair_tests_per_s": sq["buddy_pair_tests"] / t_qc,
             "oa_seconds": t_oa, "qc_seconds": t_qc}
 
@@ -381,7 +419,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         ev[i][2].record(lib_stream)
     ctx.sync()
     barrier()
-    launches = ctx.stats()["kernel_launches"]
+    st_timed = ctx.stats()
+    launches = st_timed["kernel_launches"]
+    pairs_examined_step = st_timed["buddy_pairs_examined"] / max(args.steps, 1)
     scan_ms, buddy_ms = ctx.kernel_ms()
     ctx.set_timing(False)
     qc_ms = sum(a.elapsed_time(b) for a, b, _ in ev) / args.steps
@@ -518,25 +558,35 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "scan_kernel_share_of_oa": scan_ms_step / oa_ms if oa_ms > 0 else None,
         }
         roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / hbm_peak
+        # the buddy check's all-pairs kernel against the same lane-instruction peak: 12 issued
+        # instructions per examined pair (2 sub, 2 mul, add, 2 compares, and, count, select, add + the
+        # shared-memory load), and how much of the QC stage is that kernel (the rest builds lists)
+        b_ms = buddy_ms / max(args.steps, 1)
+        roofline["buddy"] = {
+            "kernel": "buddy_pass1_kernel", "bound": "fp32", "instructions_per_examined_pair": 12,
+            "pairs_examined_per_step": pairs_examined_step, "avg_launch_ms": b_ms,
+            "achieved": 12.0 * pairs_examined_step / (b_ms * 1e-3) / 1e12 if b_ms > 0 else 0.0,
+            "peak": fp32_peak_ops / 1e12, "unit": "T lane-instr/s",
+            "frac": (12.0 * pairs_examined_step / (b_ms * 1e-3) / fp32_peak_ops) if b_ms > 0 and fp32_peak_ops else None,
+            "share_of_qc_stage": b_ms / qc_ms if qc_ms > 0 else None,
+            "reference_pair_tests_per_step": pair_tests,
+        }
         cpu = cpu_baseline(args, case) if (world == 1 and not args.no_cpu) else None
         line = {
             "metric": METRIC, "value": g_updates / (step_ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": case.label, "times_per_step": 1 if args.scaling == "strong" else world,
-                       "grid": [case.iew, case.jns], "levels": K, "reports": case.nrep,
-                       "scans": [int(r) for r in case.oa_params.radius_influence if r >= 0],
-                       "scale_cressman_rh_decreases": bool(case.oa_params.scale_cressman_rh_decreases),
-                       "scan_arithmetic": ctx.arithmetic(),
-                       "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
-                             "pristine copy before every step",
-                       "parallelism": ((f"1 analysis time, (level, variable) slabs sharded over {world} ranks, surface "
-                                        f"flags OR-combined with one NCCL all-reduce between QC and OA; e2e shards whole levels"
-                                        if slab_plan is not None else
-                                        f"1 analysis time, levels sharded over {world} ranks") if args.scaling == "strong"
-                                       else f"{world} x independent analysis time"),
-                       "cpu_affinity": affinity},
+            "config": workload_config(case, args, world),
+            "run": {"scan_arithmetic": ctx.arithmetic(),
+                    "l2": "inputs larger than L2 (4 fields x levels x grid) and restored from a "
+                          "pristine copy before every step",
+                    "parallelism": ((f"1 analysis time, (level, variable) slabs sharded over {world} ranks, surface "
+                                     f"flags OR-combined with one NCCL all-reduce between QC and OA; e2e shards whole levels"
+                                     if slab_plan is not None else
+                                     f"1 analysis time, levels sharded over {world} ranks") if args.scaling == "strong"
+                                    else f"{world} x independent analysis time"),
+                    "cpu_affinity": affinity},
             "e2e": ({"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                      "api": (f"og_time_upload/_compute/_download/_wait, pinned host arrays, {n_lanes} context(s) x "
                              f"{NS} time periods in flight" + (", one host thread per context" if n_lanes > 1 else "")),
@@ -588,6 +638,8 @@ def main():
     ap.add_argument("--ref-levels", type=int, default=64,
                     help="levels in the CPU sample of proc_oa (bounds the CPU time)")
     ap.add_argument("--ref-qc-levels", type=int, default=8)
+    ap.add_argument("--ref-single-levels", type=int, default=4,
+                    help="upper levels in the single-thread CPU sample of proc_oa")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

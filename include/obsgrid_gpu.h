@@ -140,7 +140,10 @@ int  og_set_timing(og_ctx* ctx, int on);
 int  og_host_alloc(void** ptr, size_t bytes);
 int  og_host_free(void* ptr);
 
-/* ---- per-slab drop-ins (host arrays, blocking) ----------------------------------- */
+/* ---- per-slab drop-ins (host arrays, blocking) -----------------------------------
+ * Observations must lie inside the slab, 1 <= xob < iew and 1 <= yob < jns (they are interpolated
+ * from the four surrounding points); anything else, NaN included, is OG_ERR_INVALID.  The
+ * reference passes obs pre-filtered to 2 <= x <= iew-1 (proc_ob_access.F90:231-234). */
 
 /* proc_oa.F90:517-554 / :750-778.  diff = obs_value/scale - aob (or obs_value/scale when
  * use_first_guess==0); fg_value (nullable) receives aob as in :530. */
@@ -205,7 +208,8 @@ int og_fg_t_at_point(og_ctx* ctx, const float* fg_3d_t, const float* fg_3d_h, in
  * proc_qc.F90:350 accumulates it over the surface variables.
  * obs_distance (qc0_module.F90:123-232): distance (same layout, same unit as dx) from every
  * grid box to the nearest box with tobbox > 0.5; an exact Euclidean distance transform
- * instead of the reference's O((iew*jns)^2) search. */
+ * instead of the reference's O((iew*jns)^2) search.  Grids up to 4096 points per edge (beyond
+ * that the squared index distances are no longer exact in REAL(4): OG_ERR_INVALID). */
 int og_ob_density(og_ctx* ctx, const float* xob, const float* yob, float grid_dist, int numobs,
                   float* tobbox, int iew, int jns);
 int og_obs_distance(og_ctx* ctx, const float* tobbox, float* distance, int iew, int jns, float dx);

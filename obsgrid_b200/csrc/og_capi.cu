@@ -164,6 +164,21 @@ extern "C" int og_host_free(void* p) { if (p) cudaFreeHost(p); return OG_OK; }
 // =========================================================================================
 // per-slab drop-ins (host arrays, blocking)
 // =========================================================================================
+// The per-slab entry points interpolate the slab at every ob they are given (bilinear reads the
+// points (INT(x), INT(y)) .. +1): an ob outside [1, iew) x [1, jns), or a NaN, would be an
+// out-of-bounds device read.  The reference only ever passes obs pre-filtered by proc_ob_access
+// (2 <= x <= iew-1, proc_ob_access.F90:231-234); a C ABI must not depend on that.
+static int check_obs_xy(const float* x, const float* y, int n, int iew, int jns, const char* fn)
+{
+    for (int i = 0; i < n; ++i)
+        if (!(x[i] >= 1.f && x[i] < (float)iew && y[i] >= 1.f && y[i] < (float)jns)) {
+            set_error("%s: observation %d at (%g, %g) lies outside the slab [1,%d) x [1,%d)", fn, i,
+                      (double)x[i], (double)y[i], iew, jns);
+            return OG_ERR_INVALID;
+        }
+    return OG_OK;
+}
+
 extern "C" int og_innovation(og_ctx* c, const float* gridded, int iew, int jns, const float* xob,
                              const float* yob, const float* obs_value, int n, float scale,
                              int use_first_guess, float* diff, float* fg_value)
@@ -172,6 +187,7 @@ extern "C" int og_innovation(og_ctx* c, const float* gridded, int iew, int jns, 
     REQUIRE(c && gridded && diff && n >= 0 && iew > 2 && jns > 2, "bad argument");
     if (n == 0) return OG_OK;
     REQUIRE(xob && yob && obs_value, "null observation array");
+    OG_TRY(check_obs_xy(xob, yob, n, iew, jns, __func__));
     float *d_g, *d_x, *d_y, *d_v, *d_d, *d_f;
     OG_TRY(upload(c, "io.g", gridded, (size_t)iew * jns, &d_g));
     OG_TRY(upload(c, "io.x", xob, (size_t)n, &d_x));
@@ -203,6 +219,7 @@ extern "C" int og_cressman(og_ctx* c, const float* diff, const float* xob, const
     REQUIRE(crsdot == 0 || crsdot == 1, "crsdot must be 0 or 1");
     REQUIRE(n == 0 || (diff && xob && yob), "null observation array");
     REQUIRE(!aniso(var) || (u_banana && v_banana), "UU/VV/RH need u_banana and v_banana");
+    OG_TRY(check_obs_xy(xob, yob, n, iew, jns, __func__));
     const size_t npts = (size_t)iew * jns;
     float *d_g, *d_ub = nullptr, *d_vb = nullptr, *d_x, *d_y, *d_d, *d_f;
     OG_TRY(upload(c, "io.g", gridded, npts, &d_g));
@@ -245,6 +262,7 @@ extern "C" int og_oa_slab(og_ctx* c, float* gridded, int iew, int jns, int var, 
     REQUIRE(var >= OG_VAR_UU && var <= OG_VAR_PSFC, "unknown variable code");
     REQUIRE(n == 0 || (obs_value && xob && yob), "null observation array");
     REQUIRE(!aniso(var) || (u_banana && v_banana), "UU/VV/RH need u_banana and v_banana");
+    OG_TRY(check_obs_xy(xob, yob, n, iew, jns, __func__));
     const size_t npts = (size_t)iew * jns;
     OaBatch b;
     OaSlabHost s;
@@ -449,6 +467,7 @@ static int qc_slab_common(og_ctx* c, int do_emax, int do_buddy, const float* gri
     REQUIRE(obs && xob && yob && qc_flag, "null observation array");
     REQUIRE(var != OG_VAR_PMSLPSFC || elev, "PMSLPSFC needs station_elevation");
     REQUIRE(!(do_emax && var == OG_VAR_TT && pressure > 1000.1f) || local_time, "surface TT needs local_time");
+    OG_TRY(check_obs_xy(xob, yob, n, iew, jns, "og_qc_slab / og_error_max / og_buddy_check"));
     const size_t nn = (size_t)n;
     float *d_g, *d_o, *d_x, *d_y, *d_e = nullptr; int *d_lt = nullptr, *d_q;
     OG_TRY(upload(c, "io.g", gridded, (size_t)iew * jns, &d_g));

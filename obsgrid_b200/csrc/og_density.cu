@@ -165,6 +165,10 @@ int ob_density_device(og_ctx* ctx, const float* d_x, const float* d_y, float gri
 
 int obs_distance_device(og_ctx* ctx, const float* d_tobbox, float* d_distance, int iew, int jns, float dx)
 {
+    // sqrtf((float)(dj*dj + di*di)) equals the reference's SQRT(REAL(dj)*REAL(dj) + REAL(di)*REAL(di))
+    // only while each square is exact in FP32 (< 2**24): the bit-identical guarantee ends at 4096
+    // points per edge -- BASELINE's largest grid is 4000 x 4000 -- and larger grids are refused
+    if (iew > 4096 || jns > 4096) { set_error("obs_distance: grids beyond 4096 points per edge are not supported"); return OG_ERR_INVALID; }
     int* g2 = nullptr;
     OG_TRY(ctx->reserve_t("dens.g2", (size_t)iew * jns, &g2));
     // domain_diagonal_m / dx with the reference's evaluation order (qc0_module.F90:151-152)

@@ -451,6 +451,9 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
 {
     const int ns = (int)b.slabs.size();
     if (ns == 0) return OG_OK;
+    // cell boxes are packed into short4, slabs are gridDim.y of the per-cell kernels
+    if (b.iew > 32000 || b.jns > 32000) { set_error("grid larger than 32000 points per edge"); return OG_ERR_INVALID; }
+    if (ns > 65535) { set_error("more than 65535 slabs in one batch"); return OG_ERR_INVALID; }
     cudaStream_t st = ctx->stream;
     std::vector<QcSlabDev> hs(ns);
     int max_n = 0, ncells_all = 0, max_cells = 0, nblk_ob = 0;

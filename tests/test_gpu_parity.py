@@ -29,6 +29,7 @@ def test_fast_div_is_exact(ctx):
     """The FCHK-less division used for the Cressman weight equals IEEE division."""
     assert ctx.selftest_div(1 << 24, seed=7, rmax=100) == 0
     assert ctx.selftest_div(1 << 22, seed=99, rmax=4000) == 0
+    assert ctx.selftest_div(1 << 22, seed=5, rmax=7999) == 0      # the largest radius og_cressman admits
 
 
 @pytest.mark.parametrize("iew,jns,n", [(40, 36, 300), (131, 77, 5000), (16, 16, 1), (33, 18, 0)])
@@ -462,6 +463,40 @@ def test_empty_and_degenerate_inputs(ctx, oracle):
     np.testing.assert_array_equal(case.t, ref.t)
     # RH is clamped even without obs (mixing_ratio clamp + clean_rh)
     assert case.rh.min() >= 0 and case.rh.max() <= 100
+
+
+def test_obs_outside_the_slab_are_refused(ctx):
+    """The per-slab entry points interpolate at every ob: coordinates outside [1, iew) x [1, jns) or
+    NaN would read out of bounds; they come back as OG_ERR_INVALID and the context stays usable."""
+    from obsgrid_b200._capi import OgError
+    g = wavy(30, 20)
+    one = np.ones(1, np.float32)
+    for x, y in ((0.5, 5.0), (30.0, 5.0), (5.0, 20.0), (np.nan, 5.0), (5.0, np.inf), (-3.0, 5.0)):
+        xs, ys = one * np.float32(x), one * np.float32(y)
+        with pytest.raises(OgError):
+            ctx.cressman(one, xs, ys, g, 3, 5, 12.0)
+        with pytest.raises(OgError):
+            ctx.innovation(g, xs, ys, one)
+        with pytest.raises(OgError):
+            ctx.qc_slab(g, 3, 500.0, one, xs, ys, one, np.zeros(1, np.int32), np.zeros(1, np.int32), 10, 8, 1, 30)
+    out = ctx.cressman(one, one * 5, one * 5, g, 3, 5, 12.0)      # the context is not poisoned
+    assert np.any(out != g)
+
+
+def test_radius_zero_scan_is_a_no_op(ctx, oracle):
+    """radius_influence = 0: no squared distance is below 0, the reference updates nothing
+    (oa_module.F90:553 / :616); every shape, including a banana whose centre is a grid point."""
+    rng = np.random.default_rng(3)
+    iew, jns, n = 60, 50, 400
+    g = wavy(iew, jns, 20.0, 50.0)
+    ub, vb = wind_fields(iew, jns)
+    x, y = rng_obs(rng, n, iew, jns)
+    d = rng.normal(0, 5, n).astype(np.float32)
+    for var, p in ((3, 500.0), (1, 300.0), (4, 1001.0)):
+        a = oracle.cressman(d, x, y, g, var, 0, 12.0, ub, vb, p)
+        b = ctx.cressman(d, x, y, g, var, 0, 12.0, ub, vb, p)
+        np.testing.assert_array_equal(a, g)
+        np.testing.assert_array_equal(b, g)
 
 
 def test_bad_arguments_are_reported(ctx):
