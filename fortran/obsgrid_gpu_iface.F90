@@ -74,6 +74,9 @@ MODULE obsgrid_gpu
       TYPE ( C_PTR ) :: ob_slp
       TYPE ( C_PTR ) :: qc_u , qc_v , qc_t , qc_rh
       TYPE ( C_PTR ) :: qc_slp
+      TYPE ( C_PTR ) :: ob_td        ! optional rows (C_NULL_PTR: absent), include/obsgrid_gpu.h
+      TYPE ( C_PTR ) :: qc_td
+      TYPE ( C_PTR ) :: bogus
    END TYPE og_time_desc
 
    PUBLIC :: OG_MAX_SCAN , og_qc_params , og_oa_params , og_time_desc

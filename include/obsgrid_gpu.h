@@ -56,7 +56,7 @@
 extern "C" {
 #endif
 
-#define OG_ABI_VERSION 2
+#define OG_ABI_VERSION 3
 
 typedef enum og_status {
     OG_OK = 0,
@@ -299,6 +299,19 @@ typedef struct og_time_desc {
     const float *ob_slp;            /* [nrep] Pa */
     int *qc_u, *qc_v, *qc_t, *qc_rh;           /* [kbu*nrep] */
     int *qc_slp;                    /* [nrep] */
+    /* Optional rows (NULL: absent), ABI version 3: what qc_consistency's third rule and the 'get' of
+     * bogus reports need from the report list (include/obsgrid_reports.h fills them).
+     *   ob_td / qc_td  [kbu*nrep] the measurements' dew point and its flag.  With both present QC
+     *                  (a) stores the DEWPOINT slab's derived dew point and output flag there, as
+     *                  store_ob does (ob_access_module.F90:645-657), and (b) applies the whole of
+     *                  qc_consistency (qc0_module.F90:371-424): T's failed checks are copied to the RH
+     *                  *and* the dew-point flag, and a dew point above the temperature fails RH and
+     *                  dew point (:408-422, compared as stored, missing values included).
+     *   bogus          [nrep] info%bogus: QC skips these reports (proc_ob_access.F90:179-181), OA
+     *                  uses them. */
+    float *ob_td;
+    int   *qc_td;
+    const int *bogus;
 } og_time_desc;
 
 /* proc_qc level x variable loop + qc_consistency.  Flags are updated in place. */
@@ -313,10 +326,10 @@ int og_dev_qc_time_items(og_ctx* ctx, const og_time_desc* d, const og_qc_params*
 int og_dev_oa_time_items(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
                          const int* levels, const int* var_masks, int nitems);
 /* qc_consistency (qc0_module.F90:371-404) of the levels [k_begin,k_end) on its own: u/v flags
- * merged, T's error_max / buddy bits copied to RH.  (The reference's third rule, :405-424 --
- * a reported dew point above the reported temperature fails RH -- compares the report's own
- * dew-point measurement, which the flat table does not carry; it stays with the report list on
- * the Fortran side, as do the speed / direction / dew_point copies of the flags.)  og_qc_time* run it themselves when
+ * merged, T's error_max / buddy bits copied to RH; with the optional dew-point rows of the table
+ * (ob_td / qc_td) also the third rule, :405-424 -- a dew point above the temperature fails RH and
+ * dew point -- and the dew-point copies of the flags (the speed / direction copies of the wind flag
+ * are made by og_table_to_reports).  og_qc_time* run it themselves when
  * run_consistency != 0; the stand-alone form is the step between the QC and the OA phase when
  * the variables of a level were checked on different GPUs (var_mask; obsgrid_b200/shard.py).
  * Host arrays (blocking) and device-resident form. */

@@ -71,7 +71,8 @@ class OgTimeDesc(C.Structure):
                 ("ob_u", C.c_void_p), ("ob_v", C.c_void_p), ("ob_t", C.c_void_p),
                 ("ob_rh", C.c_void_p), ("ob_slp", C.c_void_p),
                 ("qc_u", C.c_void_p), ("qc_v", C.c_void_p), ("qc_t", C.c_void_p),
-                ("qc_rh", C.c_void_p), ("qc_slp", C.c_void_p)]
+                ("qc_rh", C.c_void_p), ("qc_slp", C.c_void_p),
+                ("ob_td", C.c_void_p), ("qc_td", C.c_void_p), ("bogus", C.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/obsgrid_gpu.h declares.
@@ -135,6 +136,9 @@ SIGNATURES = {
                                  C.c_int, C.c_int]),
     "og_dev_oa_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgOaParams), C.c_int,
                                  C.c_int]),
+    "og_reports_to_table": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(OgTimeDesc), _vp]),
+    "og_table_to_reports": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(OgTimeDesc), _vp]),
     "og_stream": (_vp, [_vp]),
     "og_sync": (C.c_int, [_vp]),
     "og_last_kernel_ms": (C.c_int, [_vp, fp, fp]),

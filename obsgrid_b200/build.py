@@ -16,7 +16,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OUT = PKG / "lib" / "libobsgrid_gpu.so"
-SOURCES = ["og_capi.cu", "og_time.cu", "og_oa.cu", "og_qc.cu", "og_bin.cu", "og_density.cu", "og_final.cu", "og_misc.cu"]
+SOURCES = ["og_capi.cu", "og_time.cu", "og_oa.cu", "og_qc.cu", "og_bin.cu", "og_density.cu", "og_final.cu", "og_misc.cu", "og_reports.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
@@ -28,8 +28,8 @@ NVCC_FLAGS = [
 def needs_build() -> bool:
     if not OUT.exists():
         return True
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [
-        PKG.parent / "include" / "obsgrid_gpu.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [
+        PKG.parent / "include" / "obsgrid_gpu.h", PKG.parent / "include" / "obsgrid_reports.h"]
     t = OUT.stat().st_mtime
     return any(d.stat().st_mtime > t for d in deps)
 

@@ -35,6 +35,7 @@ struct SelDev {
     int nrep, nchunk, iew, jns;
     const float* xob; const float* yob;
     const float* elev; const int* lt_rep;   // nullable (OA)
+    const int* bogus;    // nullable; set for the QC 'get' only: bogus reports are skipped (proc_ob_access.F90:179-181)
     int* chunk_cnt;      // [nslab][nchunk] -> exclusive offsets after the scan
     int* slab_n;         // [nslab]
     float* ox; float* oy; float* oval; float* oelev; int* olt; int* oqc; int* oidx;
@@ -59,6 +60,7 @@ __device__ __forceinline__ float dewpoint_dev(float t, float rh)
 __device__ __forceinline__ bool sel_pred(const SelDev& A, const SelSlab& S, int r)
 {
     if (r >= A.nrep) return false;
+    if (A.bogus && A.bogus[r]) return false;
     bool ok = not_missing(S.ob[r]) && (S.qc[r] < S.qc_max);
     if (S.kind == 1) ok = ok && not_missing(S.ob_t[r]) && (S.qc_t[r] < S.qc_max);
     const float x = A.xob[r], y = A.yob[r];   // proc_ob_access.F90:231-234
@@ -122,19 +124,26 @@ __global__ void __launch_bounds__(SEL_THREADS) sel_scatter_kernel(SelDev A)
 }
 
 // 'put' (proc_ob_access.F90:381-403): flags back into the table rows
-struct PutSlab { int* qc; int ob_off; int n; int blk_off; };
-__global__ void put_kernel(const PutSlab* slabs, int ns, const int* oqc, const int* oidx)
+struct PutSlab { int* qc; int ob_off; int n; int blk_off; float* td_val; int* td_qc; };
+__global__ void put_kernel(const PutSlab* slabs, int ns, const int* oqc, const int* oidx, const float* oval)
 {
     const PutSlab S = slabs[slab_of_block(slabs, ns, (int)blockIdx.x)];
     const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
     if (li >= S.n) return;
+    const int r = oidx[S.ob_off + li];
     // the RH row is written by two slabs (RH and DEWPOINT): each ORs its bits in
-    atomicOr(&S.qc[oidx[S.ob_off + li]], oqc[S.ob_off + li]);
+    atomicOr(&S.qc[r], oqc[S.ob_off + li]);
+    // store_ob 'DEWPOINT' (ob_access_module.F90:645-657 / :771-774): the derived dew point and the
+    // slab's output flag become the measurement's dew point
+    if (S.td_val) { S.td_val[r] = oval[S.ob_off + li]; S.td_qc[r] = oqc[S.ob_off + li]; }
 }
 
 // qc_consistency (qc0_module.F90:371-404) on the table rows of the levels in range;
 // contains_2n(q, 2**n) == bit test for 0 <= q < 2**19 (tests/test_oracle_kat.py).
-__global__ void consistency_kernel(int* qc_u, int* qc_v, const int* qc_t, int* qc_rh, size_t n)
+// With the dew-point rows (ob_t / ob_td / qc_td, nullable together) also :405-424: the dew-point copies of
+// the flags and "td > t fails RH and dew point", compared as stored (qc_rh as it was on entry).
+__global__ void consistency_kernel(int* qc_u, int* qc_v, const int* qc_t, int* qc_rh, const float* ob_t,
+                                   const float* ob_td, int* qc_td, size_t n)
 {
     size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -143,10 +152,22 @@ __global__ void consistency_kernel(int* qc_u, int* qc_v, const int* qc_t, int* q
     if (v > u) qc_u[q] = v;
     const int t = qc_t[q];
     int rh = qc_rh[q];
+    int td = qc_td ? qc_td[q] : 0;
     const int rh0 = rh;
-    if ((t & OG_FAILS_ERROR_MAX) && !(rh0 & OG_FAILS_ERROR_MAX)) rh = qc_add_flag(rh, OG_FAILS_ERROR_MAX);
-    if ((t & OG_FAILS_BUDDY_CHECK) && !(rh0 & OG_FAILS_BUDDY_CHECK)) rh = qc_add_flag(rh, OG_FAILS_BUDDY_CHECK);
+    if ((t & OG_FAILS_ERROR_MAX) && !(rh0 & OG_FAILS_ERROR_MAX)) {
+        rh = qc_add_flag(rh, OG_FAILS_ERROR_MAX);
+        td = qc_add_flag(td, OG_FAILS_ERROR_MAX);
+    }
+    if ((t & OG_FAILS_BUDDY_CHECK) && !(rh0 & OG_FAILS_BUDDY_CHECK)) {
+        rh = qc_add_flag(rh, OG_FAILS_BUDDY_CHECK);
+        td = qc_add_flag(td, OG_FAILS_BUDDY_CHECK);
+    }
+    if (qc_td && (ob_td[q] > ob_t[q]) && (rh0 < OG_FAILS_BUDDY_CHECK)) {
+        rh = qc_add_flag(rh, OG_FAILS_BUDDY_CHECK);
+        td = qc_add_flag(td, OG_FAILS_BUDDY_CHECK);
+    }
     qc_rh[q] = rh;
+    if (qc_td) qc_td[q] = td;
 }
 
 __global__ void scale_kernel(const float* __restrict__ a, float* __restrict__ o, size_t n, float f)
@@ -182,6 +203,9 @@ struct TimeDev {
     const float *xob, *yob, *lon, *elev;
     const float *ob_u, *ob_v, *ob_t, *ob_rh, *ob_slp;
     int *qc_u, *qc_v, *qc_t, *qc_rh, *qc_slp;
+    float* ob_td = nullptr;    // optional rows (og_time_desc, ABI 3)
+    int* qc_td = nullptr;
+    const int* bogus = nullptr;
     float* tobbox = nullptr;   // optional (surface FDDA): (jns,iew) observation density, in/out
     float* odis = nullptr;     //                          (jns,iew) distance to the nearest observed box
 };
@@ -204,6 +228,7 @@ int run_selection(og_ctx* c, const TimeDev& T, std::vector<SelSlab>& sel, bool q
     A = SelDev{};
     A.nrep = T.nrep; A.nchunk = nchunk; A.iew = T.iew; A.jns = T.jns;
     A.xob = T.xob; A.yob = T.yob; A.elev = qc_outputs ? T.elev : nullptr; A.lt_rep = lt_rep;
+    A.bogus = qc_outputs ? T.bogus : nullptr;
     SelSlab* d_sel;
     OG_TRY(c->reserve_t("sel.slabs", (size_t)ns, &d_sel));
     OG_TRY(c->reserve_t("sel.chunk", (size_t)ns * std::max(nchunk, 1), &A.chunk_cnt));
@@ -438,6 +463,7 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, const Level
                         s.max_error = p->max_error_p; s.max_buddy = p->max_buddy_p; break;
                 default: s.g = w_dew + lev; q.kind = 1; q.ob = T.ob_rh + row; q.qc = T.qc_rh + row;
                         q.ob_t = T.ob_t + row; q.qc_t = T.qc_t + row; pt.qc = T.qc_rh + row;
+                        if (T.ob_td && T.qc_td) { pt.td_val = T.ob_td + row; pt.td_qc = T.qc_td + row; }
                         s.max_error = p->max_error_dewpoint; s.max_buddy = p->max_buddy_dewpoint; break;
                 }
                 b.slabs.push_back(s); sel.push_back(q); puts.push_back(pt); slab_level.push_back(k);
@@ -466,7 +492,7 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, const Level
                 PutSlab* d_put;
                 OG_TRY(c->reserve_t("qc.put", puts.size(), &d_put));
                 OG_TRY(c->put_small(d_put, puts.data(), sizeof(PutSlab) * puts.size()));
-                put_kernel<<<nblk_ob, 256, 0, c->stream>>>(d_put, (int)puts.size(), SA.oqc, SA.oidx);
+                put_kernel<<<nblk_ob, 256, 0, c->stream>>>(d_put, (int)puts.size(), SA.oqc, SA.oidx, SA.oval);
                 c->count_launch();
             }
         }
@@ -482,7 +508,10 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, const Level
             if (L.mask[i] == 0) { whole.k.push_back(L.k[i]); whole.mask.push_back(0); }
         OG_TRY(for_each_run(whole, [&](int, int k, int nl) -> int {
             const size_t n = (size_t)nl * T.nrep, off = (size_t)k * T.nrep;
-            consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(T.qc_u + off, T.qc_v + off, T.qc_t + off, T.qc_rh + off, n);
+            const bool dew = T.ob_td && T.qc_td;
+            consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(T.qc_u + off, T.qc_v + off, T.qc_t + off, T.qc_rh + off,
+                                                               T.ob_t + off, dew ? T.ob_td + off : nullptr,
+                                                               dew ? T.qc_td + off : nullptr, n);
             c->count_launch();
             return OG_OK;
         }));
@@ -516,6 +545,7 @@ TimeDev view_of(const og_time_desc* d)
     T.xob = d->xob; T.yob = d->yob; T.lon = d->lon; T.elev = d->elev;
     T.ob_u = d->ob_u; T.ob_v = d->ob_v; T.ob_t = d->ob_t; T.ob_rh = d->ob_rh; T.ob_slp = d->ob_slp;
     T.qc_u = d->qc_u; T.qc_v = d->qc_v; T.qc_t = d->qc_t; T.qc_rh = d->qc_rh; T.qc_slp = d->qc_slp;
+    T.ob_td = d->ob_td; T.qc_td = d->qc_td; T.bogus = d->bogus;
     return T;
 }
 
@@ -562,6 +592,13 @@ int mirror_in(og_ctx* c, const og_time_desc* d, int k0, int k1, bool qc, TimeDev
     OG_TRY(up_row("m.qc_rh", d->qc_rh, &v)); T.qc_rh = (int*)v;
     OG_TRY(upload(c, "m.ob_slp", d->ob_slp, k0 == 0 ? nrep : 0, &f)); T.ob_slp = f;
     OG_TRY(upload(c, "m.qc_slp", d->qc_slp, k0 == 0 ? nrep : 0, &q)); T.qc_slp = q;
+    // optional rows (QC only): dew point of the measurements, bogus reports
+    T.ob_td = nullptr; T.qc_td = nullptr; T.bogus = nullptr;
+    if (qc && d->ob_td && d->qc_td) {
+        OG_TRY(up_row("m.ob_td", d->ob_td, &v)); T.ob_td = (float*)v;
+        OG_TRY(up_row("m.qc_td", d->qc_td, &v)); T.qc_td = (int*)v;
+    }
+    if (qc && d->bogus) { OG_TRY(upload(c, "m.bogus", d->bogus, nrep, &q)); T.bogus = q; }
     return OG_OK;
 }
 
@@ -631,7 +668,10 @@ extern "C" int og_dev_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, i
     OG_TRY(check_desc(d, k0, k1, false));
     if (k1 == k0 || d->nrep == 0) return OG_OK;
     const size_t n = (size_t)(k1 - k0) * d->nrep, off = (size_t)k0 * d->nrep;
-    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(d->qc_u + off, d->qc_v + off, d->qc_t + off, d->qc_rh + off, n);
+    const bool dew = d->ob_td && d->qc_td;
+    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(d->qc_u + off, d->qc_v + off, d->qc_t + off, d->qc_rh + off,
+                                                       d->ob_t + off, dew ? d->ob_td + off : nullptr,
+                                                       dew ? d->qc_td + off : nullptr, n);
     c->count_launch();
     OG_CUDA(cudaGetLastError());
     return OG_OK;
@@ -648,12 +688,20 @@ extern "C" int og_qc_consistency(og_ctx* c, const og_time_desc* d, int k0, int k
     int* host[4] = {d->qc_u + off, d->qc_v + off, d->qc_t + off, d->qc_rh + off};
     const char* names[4] = {"cons.u", "cons.v", "cons.t", "cons.rh"};
     for (int i = 0; i < 4; ++i) OG_TRY(upload(c, names[i], host[i], n, &dev[i]));
-    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(dev[0], dev[1], dev[2], dev[3], n);
+    const bool dew = d->ob_td && d->qc_td;
+    float *d_t = nullptr, *d_td = nullptr; int* d_qtd = nullptr;
+    if (dew) {
+        OG_TRY(upload(c, "cons.ob_t", d->ob_t + off, n, &d_t));
+        OG_TRY(upload(c, "cons.ob_td", (const float*)d->ob_td + off, n, &d_td));
+        OG_TRY(upload(c, "cons.qc_td", (const int*)d->qc_td + off, n, &d_qtd));
+    }
+    consistency_kernel<<<nblk(n), 256, 0, c->stream>>>(dev[0], dev[1], dev[2], dev[3], d_t, d_td, d_qtd, n);
     c->count_launch();
     OG_CUDA(cudaGetLastError());
     OG_TRY(download(c, host[0], dev[0], n));
     OG_TRY(download(c, host[1], dev[1], n));
     OG_TRY(download(c, host[3], dev[3], n));
+    if (dew) OG_TRY(download(c, d->qc_td + off, d_qtd, n));
     OG_CUDA(cudaStreamSynchronize(c->stream));
     return OG_OK;
 }
@@ -693,6 +741,10 @@ extern "C" int og_qc_time_levels(og_ctx* c, const og_time_desc* d, const og_qc_p
     OG_TRY(download(c, d->qc_v + lo, T.qc_v + lo, nrep * nlev));
     OG_TRY(download(c, d->qc_t + lo, T.qc_t + lo, nrep * nlev));
     OG_TRY(download(c, d->qc_rh + lo, T.qc_rh + lo, nrep * nlev));
+    if (T.qc_td) {
+        OG_TRY(download(c, d->qc_td + lo, T.qc_td + lo, nrep * nlev));
+        OG_TRY(download(c, d->ob_td + lo, T.ob_td + lo, nrep * nlev));
+    }
     if (k0 == 0) OG_TRY(download(c, d->qc_slp, T.qc_slp, nrep));
     OG_CUDA(cudaStreamSynchronize(c->stream));
     return OG_OK;
@@ -719,8 +771,9 @@ extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_param
     TimeDev T = view_of(d);
     struct Arr { const char* name; const void* host; void** dev; size_t row; bool sfc_only; bool out; };
     float *m_t, *m_u, *m_v, *m_rh, *m_slp, *m_x, *m_y, *m_lon, *m_elev, *o_u, *o_v, *o_t, *o_rh, *o_slp;
-    int *q_u, *q_v, *q_t, *q_rh, *q_slp;
-    Arr arrs[] = {
+    float* o_td = nullptr;
+    int *q_u, *q_v, *q_t, *q_rh, *q_slp, *q_td = nullptr, *m_bogus = nullptr;
+    std::vector<Arr> arrs = {
         {"m.t", d->t, (void**)&m_t, per, false, true},      {"m.u", d->u, (void**)&m_u, per, false, true},
         {"m.v", d->v, (void**)&m_v, per, false, true},      {"m.rh", d->rh, (void**)&m_rh, per, false, true},
         {"m.ob_u", d->ob_u, (void**)&o_u, nrep, false, false}, {"m.ob_v", d->ob_v, (void**)&o_v, nrep, false, false},
@@ -730,6 +783,10 @@ extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_param
         {"m.slp", d->slp, (void**)&m_slp, per, true, true},    {"m.ob_slp", d->ob_slp, (void**)&o_slp, nrep, true, false},
         {"m.qc_slp", d->qc_slp, (void**)&q_slp, nrep, true, true},
     };
+    if (d->ob_td && d->qc_td) {        // optional rows (ABI 3)
+        arrs.push_back({"m.ob_td", d->ob_td, (void**)&o_td, nrep, false, true});
+        arrs.push_back({"m.qc_td", d->qc_td, (void**)&q_td, nrep, false, true});
+    }
     for (Arr& a : arrs)
         OG_TRY(c->reserve(a.name, std::max<size_t>(a.row * (a.sfc_only ? 1 : d->kbu), 1) * 4, a.dev));
     OG_TRY(c->reserve_t("m.x", std::max<size_t>(nrep, 1), &m_x));
@@ -740,6 +797,8 @@ extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_param
     T.xob = m_x; T.yob = m_y; T.lon = m_lon; T.elev = m_elev;
     T.ob_u = o_u; T.ob_v = o_v; T.ob_t = o_t; T.ob_rh = o_rh; T.ob_slp = o_slp;
     T.qc_u = q_u; T.qc_v = q_v; T.qc_t = q_t; T.qc_rh = q_rh; T.qc_slp = q_slp;
+    T.ob_td = o_td; T.qc_td = q_td; T.bogus = nullptr;
+    if (d->bogus) { OG_TRY(c->reserve_t("m.bogus", std::max<size_t>(nrep, 1), &m_bogus)); T.bogus = m_bogus; }
 
     // the copy streams must not run ahead of work already queued on the compute stream
     // (earlier calls may still be reading the mirrors)
@@ -761,6 +820,7 @@ extern "C" int og_qc_oa_time(og_ctx* c, const og_time_desc* d, const og_qc_param
     };
     OG_TRY(h2d(m_x, d->xob, nrep * 4)); OG_TRY(h2d(m_y, d->yob, nrep * 4));
     OG_TRY(h2d(m_lon, d->lon, nrep * 4)); OG_TRY(h2d(m_elev, d->elev, nrep * 4));
+    if (m_bogus) OG_TRY(h2d(m_bogus, d->bogus, nrep * 4));
     // every group's upload is queued up front: the copy engine streams them in while the
     // host is busy launching (and, inside the stages, briefly waiting on) the compute
     std::vector<int> gb(groups + 1);
@@ -802,13 +862,16 @@ const MirrorArr kMirror[] = {
     {"ob_u", 1, false, false}, {"ob_v", 1, false, false}, {"ob_t", 1, false, false}, {"ob_rh", 1, false, false},
     {"qc_u", 1, false, true},  {"qc_v", 1, false, true},  {"qc_t", 1, false, true},  {"qc_rh", 1, false, true},
     {"slp", 0, true, true},    {"ob_slp", 1, true, false}, {"qc_slp", 1, true, true},
+    {"ob_td", 1, false, true}, {"qc_td", 1, false, true},      // optional rows (host pointer may be NULL)
 };
 constexpr int kNMirror = sizeof(kMirror) / sizeof(kMirror[0]);
 
 void* host_of(const og_time_desc* d, int i)
 {
+    const bool dew = d->ob_td && d->qc_td;
     void* h[] = {d->t, d->u, d->v, d->rh, (void*)d->ob_u, (void*)d->ob_v, (void*)d->ob_t, (void*)d->ob_rh,
-                 d->qc_u, d->qc_v, d->qc_t, d->qc_rh, d->slp, (void*)d->ob_slp, d->qc_slp};
+                 d->qc_u, d->qc_v, d->qc_t, d->qc_rh, d->slp, (void*)d->ob_slp, d->qc_slp,
+                 dew ? (void*)d->ob_td : nullptr, dew ? (void*)d->qc_td : nullptr};
     return h[i];
 }
 
@@ -818,13 +881,17 @@ int slot_mirror(og_ctx* c, const og_time_desc* d, int slot, TimeDev& T, void* de
     const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep;
     char name[32];
     for (int i = 0; i < kNMirror; ++i) {
+        dev[i] = nullptr;
+        if (!host_of(d, i)) continue;        // an optional row the caller does not have
         const size_t row = kMirror[i].row ? nrep : per;
         snprintf(name, sizeof name, "s%d.%s", slot, kMirror[i].name);
         OG_TRY(c->reserve(name, std::max<size_t>(row * (kMirror[i].sfc_only ? 1 : d->kbu), 1) * 4, &dev[i]));
     }
-    float* f4[4];
-    const char* tn[4] = {"x", "y", "lon", "elev"};
-    for (int i = 0; i < 4; ++i) {
+    float* f4[5];
+    const char* tn[5] = {"x", "y", "lon", "elev", "bogus"};
+    for (int i = 0; i < 5; ++i) {
+        f4[i] = nullptr;
+        if (i == 4 && !d->bogus) continue;
         snprintf(name, sizeof name, "s%d.%s", slot, tn[i]);
         OG_TRY(c->reserve_t(name, std::max<size_t>(nrep, 1), &f4[i]));
     }
@@ -833,7 +900,8 @@ int slot_mirror(og_ctx* c, const og_time_desc* d, int slot, TimeDev& T, void* de
     T.ob_u = (float*)dev[4]; T.ob_v = (float*)dev[5]; T.ob_t = (float*)dev[6]; T.ob_rh = (float*)dev[7];
     T.qc_u = (int*)dev[8]; T.qc_v = (int*)dev[9]; T.qc_t = (int*)dev[10]; T.qc_rh = (int*)dev[11];
     T.slp = (float*)dev[12]; T.ob_slp = (float*)dev[13]; T.qc_slp = (int*)dev[14];
-    T.xob = f4[0]; T.yob = f4[1]; T.lon = f4[2]; T.elev = f4[3];
+    T.ob_td = (float*)dev[15]; T.qc_td = (int*)dev[16];
+    T.xob = f4[0]; T.yob = f4[1]; T.lon = f4[2]; T.elev = f4[3]; T.bogus = (const int*)f4[4];
     return OG_OK;
 }
 
@@ -872,7 +940,9 @@ extern "C" int og_time_upload(og_ctx* c, const og_time_desc* d, int k0, int k1, 
     };
     OG_TRY(h2d((void*)T.xob, d->xob, nrep * 4)); OG_TRY(h2d((void*)T.yob, d->yob, nrep * 4));
     OG_TRY(h2d((void*)T.lon, d->lon, nrep * 4)); OG_TRY(h2d((void*)T.elev, d->elev, nrep * 4));
+    if (T.bogus) OG_TRY(h2d((void*)T.bogus, d->bogus, nrep * 4));
     for (int i = 0; i < kNMirror; ++i) {
+        if (!dev[i]) continue;
         const size_t row = kMirror[i].row ? nrep : per;
         if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(h2d(dev[i], host_of(d, i), row * 4)); continue; }
         OG_TRY(h2d((char*)dev[i] + row * k0 * 4, (const char*)host_of(d, i) + row * k0 * 4, row * nlev * 4));
@@ -920,7 +990,7 @@ extern "C" int og_time_download(og_ctx* c, const og_time_desc* d, int k0, int k1
         return OG_OK;
     };
     for (int i = 0; i < kNMirror; ++i) {
-        if (!kMirror[i].out) continue;
+        if (!kMirror[i].out || !dev[i]) continue;
         const size_t row = kMirror[i].row ? nrep : per;
         if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(d2h(host_of(d, i), dev[i], row * 4)); continue; }
         OG_TRY(d2h((char*)host_of(d, i) + row * k0 * 4, (const char*)dev[i] + row * k0 * 4, row * nlev * 4));
@@ -957,6 +1027,10 @@ extern "C" int og_qc_time_fdda(og_ctx* c, const og_time_desc* d, const og_qc_par
     OG_TRY(download(c, d->qc_v, T.qc_v, n));
     OG_TRY(download(c, d->qc_t, T.qc_t, n));
     OG_TRY(download(c, d->qc_rh, T.qc_rh, n));
+    if (T.qc_td) {
+        OG_TRY(download(c, d->qc_td, T.qc_td, n));
+        OG_TRY(download(c, d->ob_td, T.ob_td, n));
+    }
     OG_TRY(download(c, d->qc_slp, T.qc_slp, (size_t)d->nrep));
     OG_TRY(download(c, tobbox, T.tobbox, per));
     OG_TRY(download(c, odis, T.odis, per));

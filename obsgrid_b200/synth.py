@@ -125,6 +125,11 @@ class TimeCase:
     qc_params: OgQcParams = field(default_factory=OgQcParams)
     oa_params: OgOaParams = field(default_factory=OgOaParams)
     label: str = ""
+    # optional rows of og_time_desc (ABI 3): dew point of the measurements and its flag (kbu, nrep),
+    # bogus reports (nrep,)
+    ob_td: np.ndarray | None = None
+    qc_td: np.ndarray | None = None
+    bogus: np.ndarray | None = None
 
     @property
     def nrep(self) -> int:
@@ -142,6 +147,11 @@ class TimeCase:
             a = getattr(self, name)
             assert a.flags["C_CONTIGUOUS"], name
             setattr(d, name, a.ctypes.data)
+        for name in ("ob_td", "qc_td", "bogus"):
+            a = getattr(self, name)
+            if a is not None:
+                assert a.flags["C_CONTIGUOUS"], name
+                setattr(d, name, a.ctypes.data)
         return d
 
     def copy(self) -> "TimeCase":

@@ -1101,6 +1101,7 @@ static void qc_level_density(const og_time_desc* d, const og_qc_params* p, int k
         int n = 0;
         for (int r = 0; r < nrep; ++r) {
             float value; int q;
+            if (d->bogus && d->bogus[r]) continue;          /* proc_ob_access.F90:179-181 */
             if (ivar == 7) {
                 float rhv = d->ob_rh[off + r], tv = d->ob_t[off + r];
                 if (!(not_missing(rhv) && d->qc_rh[off + r] < (1 << 20) && not_missing(tv) &&
@@ -1125,15 +1126,18 @@ static void qc_level_density(const og_time_desc* d, const og_qc_params* p, int k
                             p->buddy_weight, buddy_difference, NULL, NULL, NULL, NULL);
         /* 'put' (proc_ob_access.F90:381-403; DEWPOINT stores into rh%qc, ob_access:771-774) */
         for (int m = 0; m < n; ++m) qcv[idx[m]] = qc[m];
+        if (ivar == 7 && d->ob_td && d->qc_td)              /* store_ob 'DEWPOINT', ob_access_module.F90:645-657 */
+            for (int m = 0; m < n; ++m) { d->ob_td[off + idx[m]] = val[m]; d->qc_td[off + idx[m]] = qc[m]; }
     }
     free(gridded); free(gt); free(val); free(x); free(y); free(lon); free(elev);
     free(qc); free(idx); free(lt);
 }
 
-/* qc0_module.F90:313-434 on the table; the td>t rule (:408-422) needs dew_point data that
- * the table does not carry and is not applied. */
+/* qc0_module.F90:313-434 on the table rows.  The dew-point copies of the flags and the td > t
+ * rule (:405-424) need the optional dew-point rows (og_time_desc.ob_td / qc_td). */
 static void qc_consistency(const og_time_desc* d, int k_begin, int k_end)
 {
+    const int dew = d->ob_td && d->qc_td;
     for (int k = k_begin; k < k_end; ++k)
         for (int r = 0; r < d->nrep; ++r) {
             size_t q = (size_t)k * d->nrep + r;
@@ -1141,10 +1145,20 @@ static void qc_consistency(const og_time_desc* d, int k_begin, int k_end)
             if (qc_u > qc_v) d->qc_v[q] = qc_u;
             if (qc_v > qc_u) d->qc_u[q] = qc_v;
             int qc_t = d->qc_t[q], qc_rh = d->qc_rh[q];
-            if (contains_2n(qc_t, OG_FAILS_ERROR_MAX) && !contains_2n(qc_rh, OG_FAILS_ERROR_MAX))
+            int scratch = 0;
+            int* qtd = dew ? &d->qc_td[q] : &scratch;
+            if (contains_2n(qc_t, OG_FAILS_ERROR_MAX) && !contains_2n(qc_rh, OG_FAILS_ERROR_MAX)) {
                 ogo_add_to_qc_flag(&d->qc_rh[q], OG_FAILS_ERROR_MAX);
-            if (contains_2n(qc_t, OG_FAILS_BUDDY_CHECK) && !contains_2n(qc_rh, OG_FAILS_BUDDY_CHECK))
+                ogo_add_to_qc_flag(qtd, OG_FAILS_ERROR_MAX);
+            }
+            if (contains_2n(qc_t, OG_FAILS_BUDDY_CHECK) && !contains_2n(qc_rh, OG_FAILS_BUDDY_CHECK)) {
                 ogo_add_to_qc_flag(&d->qc_rh[q], OG_FAILS_BUDDY_CHECK);
+                ogo_add_to_qc_flag(qtd, OG_FAILS_BUDDY_CHECK);
+            }
+            if (dew && (d->ob_td[q] > d->ob_t[q]) && (qc_rh < OG_FAILS_BUDDY_CHECK)) {   /* :408-422 */
+                ogo_add_to_qc_flag(&d->qc_rh[q], OG_FAILS_BUDDY_CHECK);
+                ogo_add_to_qc_flag(qtd, OG_FAILS_BUDDY_CHECK);
+            }
         }
 }
 

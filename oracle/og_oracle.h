@@ -66,6 +66,7 @@ void ogo_clean_rh(float* rh, int iew, int jns, float rh_min, float rh_max);
 
 void ogo_modify_qc_flag(int* qc_flag, int n, const float* err, const float* thr, int test);
 void ogo_add_to_qc_flag(int* qc_flag, int to_add);
+int ogo_contains_2n(int sumtocheck, int numtofind);        /* obs_sort_module.F90:4515-4560 */
 void ogo_local_time(int time_hhmm, const float* lonob, int n, int* local_time);
 
 void ogo_error_max(const float* obs, const float* xob, const float* yob,
@@ -107,6 +108,22 @@ int ogo_oa_time_mt(const og_time_desc* d, const og_oa_params* p, int k_begin, in
                    int threads);
 int ogo_qc_time_mt(const og_time_desc* d, const og_qc_params* p, int k_begin, int k_end,
                    int run_consistency, int threads);
+
+/* The reference's observation access as written, over the plain-array image of the report list
+ * (og_oracle_reports.c; structs in ../include/obsgrid_reports.h): query_ob, store_ob, proc_ob_access
+ * 'get' / 'use', qc_consistency over every measurement, and proc_qc's loop that calls them. */
+struct og_report; struct og_meas;
+void ogo_query_ob(struct og_report* obs, struct og_meas* meas, int date, int time, int var, float request_level,
+                  int request_qc_max, int request_p_diff, float* value, int* qc);
+int ogo_store_ob(struct og_report* obs, struct og_meas* meas, int var, float request_level, int request_p_diff,
+                 float value, int qc);
+int ogo_get_obs(struct og_report* obs, int total_numobs, struct og_meas* meas, int is_get, int var,
+                float request_level, int date, int time, int request_p_diff, int request_qc_max, int iew_alloc,
+                int jns_alloc, float* get_value, float* get_x, float* get_y, float* get_lon, float* get_elev,
+                int* get_index, int* get_qc);
+void ogo_qc_consistency_reports(struct og_report* obs, int num_obs, struct og_meas* meas);
+int ogo_qc_time_reports(const og_time_desc* d, const og_qc_params* p, struct og_report* obs, int nrep,
+                        struct og_meas* meas, int date, int time, int request_p_diff);
 
 /* GET_FG_T_AT_POINT (get_fg_at_point_module.F90:7-116) with (x,y) already projected. */
 float ogo_fg_t_at_point(const float* t3d, const float* h3d, int jns, int iew, int kbu,

@@ -26,7 +26,8 @@ class OgoStats(C.Structure):
 
 
 def build(force: bool = False) -> Path:
-    src = [HERE / "og_oracle.c", HERE / "og_oracle.h", HERE.parent / "include" / "obsgrid_gpu.h"]
+    src = [HERE / "og_oracle.c", HERE / "og_oracle_reports.c", HERE / "og_oracle.h",
+           HERE.parent / "include" / "obsgrid_gpu.h", HERE.parent / "include" / "obsgrid_reports.h"]
     if force or not LIB.exists() or any(s.stat().st_mtime > LIB.stat().st_mtime for s in src):
         subprocess.check_call(["make", "-C", str(HERE), "-s"])
     return LIB
@@ -303,3 +304,29 @@ def oa_time(case, k_begin=0, k_end=None, threads=1):
     d = case.desc()
     k_end = case.kbu if k_end is None else k_end
     return lib().ogo_oa_time_mt(C.byref(d), C.byref(case.oa_params), k_begin, k_end, threads)
+
+
+# ---- the reference's observation access as written, over a report list (og_oracle_reports.c) ----
+def qc_time_reports(case, rl, date, time, request_p_diff=1):
+    """proc_qc over the report list `rl` (obsgrid_b200.reports.ReportList) with the first guess of
+    `case`: 'get' / error_max / buddy_check / 'put' per slab, then qc_consistency; modifies rl."""
+    d = case.desc()
+    l = lib()
+    l.ogo_qc_time_reports.restype = C.c_int
+    l.ogo_qc_time_reports.argtypes = [C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), _vp, C.c_int, _vp,
+                                      C.c_int, C.c_int, C.c_int]
+    return l.ogo_qc_time_reports(C.byref(d), C.byref(case.qc_params), rl.reports, rl.nrep, rl.meas_ptr(),
+                                 date, time, request_p_diff)
+
+
+def get_obs(rl, is_get, var, level, date, time, request_p_diff, request_qc_max, iew, jns):
+    """proc_ob_access 'get' (is_get) / 'use' of one slab; returns dict of the returned arrays."""
+    n = rl.nrep
+    val, x, y, lon, elev = (np.zeros(n, np.float32) for _ in range(5))
+    idx, qc = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    l = lib()
+    l.ogo_get_obs.restype = C.c_int
+    l.ogo_get_obs.argtypes = [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_float] + [C.c_int] * 6 + [_vp] * 7
+    m = l.ogo_get_obs(rl.reports, n, rl.meas_ptr(), int(is_get), var, level, date, time, request_p_diff,
+                      request_qc_max, iew, jns, ptr(val), ptr(x), ptr(y), ptr(lon), ptr(elev), ptr(idx), ptr(qc))
+    return dict(n=m, value=val[:m], x=x[:m], y=y[:m], lon=lon[:m], elev=elev[:m], index=idx[:m], qc=qc[:m])

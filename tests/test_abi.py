@@ -11,10 +11,11 @@ from obsgrid_b200 import _capi
 
 ROOT = Path(__file__).resolve().parent.parent
 HEADER = (ROOT / "include" / "obsgrid_gpu.h").read_text()
+HEADER_REPORTS = (ROOT / "include" / "obsgrid_reports.h").read_text()
 
 
 def declared_functions():
-    body = re.sub(r"/\*.*?\*/", "", HEADER, flags=re.S)
+    body = re.sub(r"/\*.*?\*/", "", HEADER + HEADER_REPORTS, flags=re.S)
     body = re.sub(r"typedef\s+struct[^{;]*\{.*?\}\s*\w+\s*;", "", body, flags=re.S)
     return sorted(set(re.findall(r"\b(og_[a-z0-9_]+)\s*\(", body)))
 
@@ -39,7 +40,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(str(_capi.LIB_PATH))
     missing = [n for n in declared_functions() if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.og_abi_version() == 2
+    assert lib.og_abi_version() == 3
 
 
 def test_ctypes_binding_covers_the_header():
