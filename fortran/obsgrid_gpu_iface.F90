@@ -573,3 +573,180 @@ SUBROUTINE temporal_interp_field ( first , second , out , jns_alloc , iew_alloc 
       CALL og_fail ( 'temporal_interp' )
 
 END SUBROUTINE temporal_interp_field
+
+!------------------------------------------------------------------------------------------------
+!  The batched path from the reference's own data structure (SURVEY 8f rank 1).
+!
+!  og_time_desc wants one flat observation table per analysis time; OBSGRID holds TYPE(report)
+!  records with a linked list of TYPE(measurement) (src/obs_sort_module.F90:75-245) and derives
+!  every slab's observations with proc_ob_access / query_ob / store_ob.  This module flattens the
+!  list into the plain arrays of include/obsgrid_reports.h, lets og_reports_to_table decide -- once
+!  per time -- what the per-slab calls decide again and again, and scatters flags and dew points back
+!  (og_table_to_reports), leaving the list as proc_qc + qc_consistency + proc_oa leave it.
+!
+!     CALL og_flatten_reports ( obs , number_of_obs , reports , meas , nmeas )
+!     ... og_reports_to_table ( reports , n , meas , nmeas , date , time , request_p_diff , desc , meas_index )
+!     ... og_qc_time / og_oa_time / og_qc_oa_time ( desc ) ...
+!     ... og_table_to_reports ( reports , n , meas , nmeas , date , time , desc , meas_index )
+!     CALL og_unflatten_reports ( obs , number_of_obs , reports , meas )
+!
+!  replaces, in driver.F90, the calls of proc_qc (:455-459), qc_consistency and proc_oa's observation
+!  access for one time period (INTEGRATION.md section 2 shows the patch).
+MODULE obsgrid_gpu_reports
+
+   USE , INTRINSIC :: ISO_C_BINDING
+   USE observation                       !  TYPE(report), TYPE(measurement): src/obs_sort_module.F90
+   USE map_utils                         !  latlon_to_ij
+   USE map_utils_helper                  !  projd
+   USE obsgrid_gpu , ONLY : og_time_desc
+   IMPLICIT NONE
+   PRIVATE
+   PUBLIC :: og_field , og_meas , og_report , og_flatten_reports , og_unflatten_reports , &
+             og_reports_to_table , og_table_to_reports
+
+   !  include/obsgrid_reports.h, member for member
+   TYPE , BIND ( C ) :: og_field
+      REAL ( C_FLOAT ) :: data
+      INTEGER ( C_INT ) :: qc
+   END TYPE og_field
+
+   TYPE , BIND ( C ) :: og_meas
+      TYPE ( og_field ) :: pressure , height , temperature , dew_point , speed , direction , u , v , rh , thickness
+   END TYPE og_meas
+
+   TYPE , BIND ( C ) :: og_report
+      REAL ( C_FLOAT ) :: latitude , longitude
+      REAL ( C_FLOAT ) :: x , y
+      REAL ( C_FLOAT ) :: elevation
+      CHARACTER ( KIND = C_CHAR ) :: platform ( 40 )
+      CHARACTER ( KIND = C_CHAR ) :: date_char ( 14 )
+      INTEGER ( C_INT ) :: discard , bogus
+      TYPE ( og_field ) :: slp
+      TYPE ( og_field ) :: psfc
+      INTEGER ( C_INT ) :: first_meas , n_meas
+   END TYPE og_report
+
+   INTERFACE
+      INTEGER ( C_INT ) FUNCTION og_reports_to_table ( reports , nrep , meas , nmeas , date , time , &
+      request_p_diff , table , meas_index ) BIND ( C , NAME = 'og_reports_to_table' )
+         IMPORT :: C_INT , og_report , og_meas , og_time_desc
+         TYPE ( og_report ) , INTENT ( INOUT ) :: reports ( * )
+         INTEGER ( C_INT ) , VALUE :: nrep , nmeas , date , time , request_p_diff
+         TYPE ( og_meas ) , INTENT ( INOUT ) :: meas ( * )
+         TYPE ( og_time_desc ) , INTENT ( INOUT ) :: table
+         INTEGER ( C_INT ) , INTENT ( OUT ) :: meas_index ( * )
+      END FUNCTION og_reports_to_table
+
+      INTEGER ( C_INT ) FUNCTION og_table_to_reports ( reports , nrep , meas , nmeas , date , time , &
+      table , meas_index ) BIND ( C , NAME = 'og_table_to_reports' )
+         IMPORT :: C_INT , og_report , og_meas , og_time_desc
+         TYPE ( og_report ) , INTENT ( INOUT ) :: reports ( * )
+         INTEGER ( C_INT ) , VALUE :: nrep , nmeas , date , time
+         TYPE ( og_meas ) , INTENT ( INOUT ) :: meas ( * )
+         TYPE ( og_time_desc ) , INTENT ( IN ) :: table
+         INTEGER ( C_INT ) , INTENT ( IN ) :: meas_index ( * )
+      END FUNCTION og_table_to_reports
+   END INTERFACE
+
+CONTAINS
+
+   PURE FUNCTION to_field ( f ) RESULT ( g )
+      TYPE ( field ) , INTENT ( IN ) :: f
+      TYPE ( og_field ) :: g
+      g%data = f%data
+      g%qc   = f%qc
+   END FUNCTION to_field
+
+   !  The report list as plain arrays, in list order.  meas is allocated here (one entry per
+   !  measurement of every report); x, y are latlon_to_ij of the report's location, as
+   !  proc_ob_access computes them per request (src/proc_ob_access.F90:204-208).
+   SUBROUTINE og_flatten_reports ( obs , number_of_obs , reports , meas , nmeas )
+      TYPE ( report ) , INTENT ( IN ) , DIMENSION ( : ) :: obs
+      INTEGER , INTENT ( IN ) :: number_of_obs
+      TYPE ( og_report ) , INTENT ( OUT ) , DIMENSION ( : ) :: reports
+      TYPE ( og_meas ) , ALLOCATABLE , INTENT ( OUT ) , DIMENSION ( : ) :: meas
+      INTEGER , INTENT ( OUT ) :: nmeas
+      TYPE ( measurement ) , POINTER :: cur
+      INTEGER :: i , c , m
+
+      nmeas = 0
+      DO i = 1 , number_of_obs
+         cur => obs(i)%surface
+         DO WHILE ( ASSOCIATED ( cur ) )
+            nmeas = nmeas + 1
+            cur => cur%next
+         END DO
+      END DO
+      ALLOCATE ( meas ( MAX ( nmeas , 1 ) ) )
+
+      m = 0
+      DO i = 1 , number_of_obs
+         reports(i)%latitude  = obs(i)%location%latitude
+         reports(i)%longitude = obs(i)%location%longitude
+         CALL latlon_to_ij ( projd , obs(i)%location%latitude , obs(i)%location%longitude , &
+                             reports(i)%x , reports(i)%y )
+         reports(i)%elevation = obs(i)%info%elevation
+         DO c = 1 , 40
+            reports(i)%platform(c) = obs(i)%info%platform(c:c)
+         END DO
+         DO c = 1 , 14
+            reports(i)%date_char(c) = obs(i)%valid_time%date_char(c:c)
+         END DO
+         reports(i)%discard = MERGE ( 1 , 0 , obs(i)%info%discard )
+         reports(i)%bogus   = MERGE ( 1 , 0 , obs(i)%info%bogus )
+         reports(i)%slp  = to_field ( obs(i)%ground%slp )
+         reports(i)%psfc = to_field ( obs(i)%ground%psfc )
+         reports(i)%first_meas = m                  !  0-based index into meas
+         reports(i)%n_meas = 0
+         cur => obs(i)%surface
+         DO WHILE ( ASSOCIATED ( cur ) )
+            m = m + 1
+            meas(m)%pressure    = to_field ( cur%meas%pressure )
+            meas(m)%height      = to_field ( cur%meas%height )
+            meas(m)%temperature = to_field ( cur%meas%temperature )
+            meas(m)%dew_point   = to_field ( cur%meas%dew_point )
+            meas(m)%speed       = to_field ( cur%meas%speed )
+            meas(m)%direction   = to_field ( cur%meas%direction )
+            meas(m)%u           = to_field ( cur%meas%u )
+            meas(m)%v           = to_field ( cur%meas%v )
+            meas(m)%rh          = to_field ( cur%meas%rh )
+            meas(m)%thickness   = to_field ( cur%meas%thickness )
+            reports(i)%n_meas = reports(i)%n_meas + 1
+            cur => cur%next
+         END DO
+      END DO
+   END SUBROUTINE og_flatten_reports
+
+   !  What the QC and OA of a time period change in the list: flags (every field of every
+   !  measurement), the dew point the DEWPOINT slabs derive, ground%slp%qc, info%discard.
+   SUBROUTINE og_unflatten_reports ( obs , number_of_obs , reports , meas )
+      TYPE ( report ) , INTENT ( INOUT ) , DIMENSION ( : ) :: obs
+      INTEGER , INTENT ( IN ) :: number_of_obs
+      TYPE ( og_report ) , INTENT ( IN ) , DIMENSION ( : ) :: reports
+      TYPE ( og_meas ) , INTENT ( IN ) , DIMENSION ( : ) :: meas
+      TYPE ( measurement ) , POINTER :: cur
+      INTEGER :: i , m
+
+      DO i = 1 , number_of_obs
+         obs(i)%info%discard  = reports(i)%discard .NE. 0
+         obs(i)%ground%slp%qc = reports(i)%slp%qc
+         m = reports(i)%first_meas
+         cur => obs(i)%surface
+         DO WHILE ( ASSOCIATED ( cur ) )
+            m = m + 1
+            cur%meas%pressure%qc    = meas(m)%pressure%qc
+            cur%meas%height%qc      = meas(m)%height%qc
+            cur%meas%temperature%qc = meas(m)%temperature%qc
+            cur%meas%dew_point%data = meas(m)%dew_point%data
+            cur%meas%dew_point%qc   = meas(m)%dew_point%qc
+            cur%meas%speed%qc       = meas(m)%speed%qc
+            cur%meas%direction%qc   = meas(m)%direction%qc
+            cur%meas%u%qc           = meas(m)%u%qc
+            cur%meas%v%qc           = meas(m)%v%qc
+            cur%meas%rh%qc          = meas(m)%rh%qc
+            cur => cur%next
+         END DO
+      END DO
+   END SUBROUTINE og_unflatten_reports
+
+END MODULE obsgrid_gpu_reports

@@ -133,9 +133,18 @@ __global__ void put_kernel(const PutSlab* slabs, int ns, const int* oqc, const i
     const int r = oidx[S.ob_off + li];
     // the RH row is written by two slabs (RH and DEWPOINT): each ORs its bits in
     atomicOr(&S.qc[r], oqc[S.ob_off + li]);
-    // store_ob 'DEWPOINT' (ob_access_module.F90:645-657 / :771-774): the derived dew point and the
-    // slab's output flag become the measurement's dew point
-    if (S.td_val) { S.td_val[r] = oval[S.ob_off + li]; S.td_qc[r] = oqc[S.ob_off + li]; }
+    // store_ob 'DEWPOINT' (ob_access_module.F90:645-657 / :771-774): the derived dew point becomes the
+    // measurement's dew point; its flag is the slab's output flag, which in the reference's order (RH,
+    // then DEWPOINT from RH's output) is the merged RH row: put_td_kernel copies it once it is complete
+    if (S.td_val) S.td_val[r] = oval[S.ob_off + li];
+}
+__global__ void put_td_kernel(const PutSlab* slabs, int ns, const int* oidx)
+{
+    const PutSlab S = slabs[slab_of_block(slabs, ns, (int)blockIdx.x)];
+    const int li = ((int)blockIdx.x - S.blk_off) * (int)blockDim.x + (int)threadIdx.x;
+    if (li >= S.n || !S.td_qc) return;
+    const int r = oidx[S.ob_off + li];
+    S.td_qc[r] = S.qc[r];
 }
 
 // qc_consistency (qc0_module.F90:371-404) on the table rows of the levels in range;
@@ -494,6 +503,10 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, const Level
                 OG_TRY(c->put_small(d_put, puts.data(), sizeof(PutSlab) * puts.size()));
                 put_kernel<<<nblk_ob, 256, 0, c->stream>>>(d_put, (int)puts.size(), SA.oqc, SA.oidx, SA.oval);
                 c->count_launch();
+                if (T.ob_td && T.qc_td && p->qc_dewpoint) {
+                    put_td_kernel<<<nblk_ob, 256, 0, c->stream>>>(d_put, (int)puts.size(), SA.oidx);
+                    c->count_launch();
+                }
             }
         }
     }
