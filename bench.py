@@ -262,6 +262,95 @@ def bind_to_gpu_numa_node(local_rank: int) -> str:
     return "unbound"
 
 
+def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stream):
+    """Strong scaling of ONE analysis time of configuration `cfg` over the `world` ranks, resident:
+    (level, variable) slabs dealt out by cost (obsgrid_b200/shard.py), the surface flag rows
+    OR-combined with one NCCL all-reduce between QC and OA.  Rank 0 also times the whole time period
+    on its own GPU, so that the line carries its own 1-GPU denominator."""
+    import torch
+    from obsgrid_b200 import shard
+    case = synth.make_case(cfg, time_index=0)
+    names = FIELD_NAMES + FLAG_NAMES + TABLE_NAMES
+    pristine = {nm: torch.from_numpy(getattr(case, nm)).to(dev) for nm in names}
+    work = {nm: (pristine[nm].clone() if nm in FIELD_NAMES + FLAG_NAMES else pristine[nm]) for nm in names}
+    d = case.desc()
+    for nm in names:
+        setattr(d, nm, work[nm].data_ptr())
+    plan = shard.plan_slabs(case, world)[rank]
+    lev = ([0] if plan["sfc_mask"] else []) + list(range(plan["k0"], plan["k1"]))
+    msk = ([plan["sfc_mask"]] if plan["sfc_mask"] else []) + [0] * (plan["k1"] - plan["k0"])
+    sfc_oa = plan["sfc_mask"] & 0x1f
+    oa_lev = ([0] if sfc_oa else []) + list(range(plan["k0"], plan["k1"]))
+    oa_msk = ([sfc_oa] if sfc_oa else []) + [0] * (plan["k1"] - plan["k0"])
+
+    def restore():
+        torch.cuda.synchronize(dev)
+        for nm in FIELD_NAMES + FLAG_NAMES:
+            work[nm].copy_(pristine[nm])
+        torch.cuda.synchronize(dev)
+
+    ev_x = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def step_sharded():
+        ctx.dev_proc_qc_items(d, case.qc_params, lev, msk, True)
+        with torch.cuda.stream(lib_stream):
+            ev_x[0].record(lib_stream)
+            rows = torch.stack([work["qc_u"][0], work["qc_v"][0], work["qc_t"][0], work["qc_rh"][0], work["qc_slp"]])
+            shard.allreduce_or(dist, rows)
+            for i_, nm_ in enumerate(("qc_u", "qc_v", "qc_t", "qc_rh")):
+                work[nm_][0].copy_(rows[i_])
+            work["qc_slp"].copy_(rows[4])
+            ev_x[1].record(lib_stream)
+        ctx.dev_qc_consistency(d, 0, 1)
+        ctx.dev_proc_oa_items(d, case.oa_params, oa_lev, oa_msk)
+
+    def step_alone():
+        ctx.dev_proc_qc(d, case.qc_params, 0, case.kbu, True)
+        ctx.dev_proc_oa(d, case.oa_params, 0, case.kbu)
+
+    def timed(step, n):
+        tot, xch = 0.0, 0.0
+        for _ in range(n):
+            restore()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(lib_stream); step(); b.record(lib_stream)
+            ctx.sync()
+            tot += a.elapsed_time(b)
+            if step is step_sharded:
+                xch += ev_x[0].elapsed_time(ev_x[1])
+        return tot / n, xch / n
+
+    n = max(2, min(args.steps, 3))
+    for _ in range(2):
+        restore(); step_sharded(); ctx.sync()
+    ms_n, ms_x = timed(step_sharded, n)
+    v = torch.tensor([ms_n, ms_x], device=dev, dtype=torch.float64)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    ms_n, ms_x = float(v[0]), float(v[1])
+    ms_1 = 0.0
+    if rank == 0:
+        for _ in range(2):
+            restore(); step_alone(); ctx.sync()
+        tot = 0.0
+        for _ in range(n):
+            restore()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(lib_stream); step_alone(); b.record(lib_stream)
+            ctx.sync()
+            tot += a.elapsed_time(b)
+        ms_1 = tot / n
+    dist.barrier()
+    del work, pristine
+    torch.cuda.empty_cache()
+    return {"workload": case.label, "n_gpus": world, "ms_per_time": ms_n, "ms_per_time_1gpu": ms_1,
+            "speedup": (ms_1 / ms_n) if ms_n > 0 else None,
+            "efficiency": (ms_1 / (world * ms_n)) if ms_n > 0 else None,
+            "or_exchange_ms": ms_x, "steps": n,
+            "parallelism": "(level, variable) slabs of one analysis time dealt to the ranks by cost; surface flag rows "
+                           "OR-combined by one NCCL all-reduce between QC and OA"}
+
+
 def run_gpu(args, rank: int, world: int, local_rank: int):
     import torch
     from obsgrid_b200.api import Context
@@ -510,7 +599,30 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         st_e = {k_: sum(c_.stats()[k_] for c_ in lanes) for k_ in ("h2d_bytes", "d2h_bytes")}
         for c_ in lanes[1:]:
             c_.close()
+    # ---- the per-slab drop-in path: what an unmodified proc_qc / proc_oa costs -----------------------
+    per_slab = None
+    if args.per_slab and world == 1:
+        from obsgrid_b200 import perslab
+        pc = case.copy()
+        perslab.proc_qc_per_slab(ctx, pc); perslab.proc_oa_per_slab(ctx, pc)        # warm-up, and parity
+        same = all(np.array_equal(getattr(pc, nm), work[nm].cpu().numpy()) for nm in FIELD_NAMES + FLAG_NAMES)
+        assert same, "per-slab drop-ins and the batched path disagree"
+        pc = case.copy()
+        t0 = time.perf_counter()
+        n_calls = perslab.proc_qc_per_slab(ctx, pc) + perslab.proc_oa_per_slab(ctx, pc)
+        ps_ms = (time.perf_counter() - t0) * 1e3
+        per_slab = {"value": updates / (ps_ms * 1e-3), "unit": UNIT, "ms_per_step": ps_ms, "library_calls": n_calls,
+                    "api": "the reference's slab loops over og_error_max / og_buddy_check / og_innovation / og_cressman, "
+                           "host arrays, one blocking call per slab and stage (obsgrid_b200/perslab.py)"}
     clocks = sampler.stop()
+
+    # ---- strong scaling of single analysis times, inside the same line (N > 1, weak runs) ---------
+    strong = None
+    if dist is not None and args.scaling == "weak" and args.strong_configs:
+        strong = []
+        for cfg_ in [int(x) for x in args.strong_configs.split(",") if x]:
+            r_ = strong_block(args, ctx, cfg_, rank, world, dist, dev, lib_stream)
+            strong.append(r_)
 
     # ---- reduce over ranks: max time, summed work ------------------------------------------------
     vec = torch.tensor([step_ms, e2e_ms, qc_ms, oa_ms, scan_ms / args.steps], device=dev, dtype=torch.float64)
@@ -593,6 +705,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                      "blocking_call_ms": e2e_blocking_ms,
                      "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
                      "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps} if do_e2e else None),
+            "e2e_per_slab": per_slab,
+            "strong": strong,
             "gpu_launches": int(g_launch),
             "clocks": clocks,
             "roofline": roofline,
@@ -624,6 +738,8 @@ def main():
     ap.add_argument("--arith", default="exact", choices=["exact", "contracted"],
                     help="scan-kernel arithmetic (og_set_arithmetic); exact = bit-identical to the reference's")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-per-slab", dest="per_slab", action="store_false",
+                    help="skip the e2e_per_slab leg (the per-slab drop-ins called slab by slab)")
     ap.add_argument("--no-e2e", action="store_true",
                     help="skip the host-pointer leg (e2e: null); for auxiliary scaling runs of the largest "
                          "configuration, whose pinned host copies would not fit eight times into one box")
@@ -631,6 +747,9 @@ def main():
                     help="weak: one analysis time per rank; strong: one time, levels sharded over the ranks")
     ap.add_argument("--shard", default="slabs", choices=["slabs", "levels"],
                     help="strong scaling: deal out the surface level's variable slabs (slabs) or whole levels only")
+    ap.add_argument("--strong-configs", default="3",
+                    help="N > 1: configurations whose single analysis time is also strong-scaled over the ranks "
+                         "(the `strong` block of the line); empty string: none")
     ap.add_argument("--e2e-lanes", type=int, default=0,
                     help="contexts (each on its own host thread) of the e2e leg; 0: two when the case is small")
     ap.add_argument("--pipeline-groups", type=int, default=0,

@@ -376,6 +376,28 @@ int og_time_compute(og_ctx* ctx, const og_time_desc* d, const og_qc_params* qp,
 int og_time_download(og_ctx* ctx, const og_time_desc* d_out, int k_begin, int k_end, int slot);
 int og_time_wait(og_ctx* ctx, int slot);
 
+/* The observation rows of a time period in sparse form.  Upper-air levels hold a value for the
+ * soundings only (a tenth of the reports): [kbu * nrep] rows are ~90 % OG_MISSING_R there, and on a
+ * box whose eight GPUs share the host's PCIe / memory fabric those bytes are what limits a run over
+ * many analysis times.  Per level k the entries [lev_start[k], lev_start[k+1]) name, in ascending
+ * report index, the reports that have a measurement at that level (og_reports_to_table's
+ * meas_index >= 0); an absent entry means every variable missing and every flag 0.  The dense rows
+ * of the og_time_desc passed alongside (ob_u .. qc_rh, ob_td, qc_td) are then ignored and may be NULL;
+ * ob_slp / qc_slp, the per-report arrays and the fields are used as usual. */
+typedef struct og_obs_csr {
+    int   nnz;
+    const int* lev_start;               /* [kbu + 1]                                   */
+    const int* rep;                     /* [nnz] report index, 0-based                 */
+    const float *u, *v, *t, *rh, *td;   /* [nnz]; td nullable (with qc_td)             */
+    int *qc_u, *qc_v, *qc_t, *qc_rh, *qc_td;   /* [nnz] in (upload) / out (download)   */
+} og_obs_csr;
+/* og_time_upload / og_time_download with the observation rows in that form: the upload expands them
+ * into the slot's dense device mirror, the download packs the flag rows (and the dew points the
+ * DEWPOINT slabs derived, when td is present: obs->td must then be writable) back into `obs`.
+ * og_time_compute and og_time_wait are used unchanged. */
+int og_time_upload_csr(og_ctx* ctx, const og_time_desc* d, const og_obs_csr* obs, int k_begin, int k_end, int slot);
+int og_time_download_csr(og_ctx* ctx, const og_time_desc* d_out, og_obs_csr* obs_out, int k_begin, int k_end, int slot);
+
 /* ---- resident (device-pointer) API ---------------------------------------------- */
 /* Same semantics as og_qc_time / og_oa_time but every pointer inside `d` is a DEVICE
  * pointer on the context's device and nothing is copied; used to time the kernels with

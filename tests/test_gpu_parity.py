@@ -433,6 +433,22 @@ def test_time_level_sharding_is_exact(ctx):
         np.testing.assert_array_equal(getattr(full, nm), getattr(parts, nm), err_msg=nm)
 
 
+@pytest.mark.parametrize("scale_rh,sfc_mult", [(False, 1.0), (True, 0.8)])
+def test_per_slab_drop_ins_equal_the_batched_time(ctx, scale_rh, sfc_mult):
+    """The reference's own slab loops calling og_error_max / og_buddy_check / og_innovation / og_cressman
+    one slab and stage at a time (obsgrid_b200/perslab.py: what an unmodified proc_qc / proc_oa does
+    over the Fortran wrappers) give the batched per-time result bit for bit."""
+    from obsgrid_b200 import perslab
+    base = synth.small_case(iew=60, jns=52, kbu=5, n_sfc=400, n_snd=100, radii=(6, 4, 2), scale_rh=scale_rh,
+                            sfc_mult=sfc_mult)
+    a, b = base.copy(), base.copy()
+    ctx.proc_qc(a); ctx.proc_oa(a)
+    calls = perslab.proc_qc_per_slab(ctx, b) + perslab.proc_oa_per_slab(ctx, b)
+    assert calls > 100
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
+        np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=nm)
+
+
 def test_time_cfg1(ctx, oracle):
     """BASELINE.json configs[0]: 100x100, 27 levels, 2k reports, 4 scans + qc1/qc2."""
     base = synth.make_case(1)
