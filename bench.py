@@ -529,16 +529,21 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         # kernels keep the SMs busy.  Lane 0 is `ctx`; every lane has NS slots of its own.
         case_bytes = sum(getattr(case, nm).nbytes for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES)
         n_lanes = args.e2e_lanes if args.e2e_lanes > 0 else (2 if case_bytes < (4 << 30) else 1)
-        NS = 3 if n_lanes == 1 else 2
+        NS = 3 if (n_lanes == 1 or case_bytes < (1 << 30)) else 2
         lanes = [ctx] + [Context(local_rank) for _ in range(n_lanes - 1)]
         for c_ in lanes[1:]:
             c_.set_arithmetic(args.arith)
-        ocase = []
+        pinned = lambda a: torch.from_numpy(np.ascontiguousarray(a).copy()).pin_memory().numpy()
+        ocase, ocsr = [], []
         for s_ in range(NS * n_lanes):
             oc = case.copy()
             for nm in FIELD_NAMES + FLAG_NAMES + TABLE_NAMES:
-                setattr(oc, nm, torch.from_numpy(getattr(case, nm).copy()).pin_memory().numpy())
+                setattr(oc, nm, pinned(getattr(case, nm)))
             ocase.append(oc)
+            ocsr.append(synth.CsrObs(case, alloc=pinned) if not args.e2e_dense else None)
+        # the observation rows travel in sparse form (og_obs_csr: per level the reports that have a
+        # measurement there) unless --e2e-dense: upper-air rows are ~90 % "missing"
+        hcsr = synth.CsrObs(case, alloc=pinned) if not args.e2e_dense else None
         restore_host()
 
         lane_errors = []
@@ -554,13 +559,18 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             c_, outs = lanes[l_], ocase[l_ * NS:(l_ + 1) * NS]
             if nsteps <= 0:
                 return
-            c_.time_upload(hcase, 0, K0, KR)
+            csrs = ocsr[l_ * NS:(l_ + 1) * NS]
+            up = (lambda slot: c_.time_upload(hcase, slot, K0, KR)) if hcsr is None else \
+                 (lambda slot: c_.time_upload_csr(hcase, hcsr, slot, K0, KR))
+            down = (lambda slot: c_.time_download(outs[slot], slot, K0, KR)) if hcsr is None else \
+                   (lambda slot: c_.time_download_csr(outs[slot], csrs[slot], slot, K0, KR))
+            up(0)
             for i in range(nsteps):
                 s_ = i % NS
                 if i + 1 < nsteps:
-                    c_.time_upload(hcase, (i + 1) % NS, K0, KR)
+                    up((i + 1) % NS)
                 c_.time_compute(hcase, s_, K0, KR)
-                c_.time_download(outs[s_], s_, K0, KR)
+                down(s_)
             for s_ in range(NS):
                 c_.time_wait(s_)
             c_.sync()
@@ -586,6 +596,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         e2e_blocking_ms = float(np.mean(blocking[1:]))
         restore_host()
         run_e2e((NS + 1) * n_lanes)   # touches every slot of every lane: no allocation is left for the timed steps
+        if hcsr is not None:
+            for oc_, cs_ in zip(ocase, ocsr):
+                cs_.scatter_flags(oc_)      # (outside the timed region: the compact flag rows are the result)
         same = all(np.array_equal(ref_out[nm], getattr(oc_, nm)) for nm in FIELD_NAMES + FLAG_NAMES for oc_ in ocase)
         assert same, "blocking and asynchronous host-pointer paths disagree"
         for c_ in lanes:
@@ -700,7 +713,8 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                                     else f"{world} x independent analysis time"),
                     "cpu_affinity": affinity},
             "e2e": ({"value": g_updates / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                     "api": (f"og_time_upload/_compute/_download/_wait, pinned host arrays, {n_lanes} context(s) x "
+                     "api": (f"og_time_upload{'' if args.e2e_dense else '_csr'}/_compute/_download{'' if args.e2e_dense else '_csr'}/_wait, "
+                             f"pinned host arrays, observation rows {'dense' if args.e2e_dense else 'sparse (og_obs_csr)'}, {n_lanes} context(s) x "
                              f"{NS} time periods in flight" + (", one host thread per context" if n_lanes > 1 else "")),
                      "blocking_call_ms": e2e_blocking_ms,
                      "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
@@ -750,6 +764,8 @@ def main():
     ap.add_argument("--strong-configs", default="3",
                     help="N > 1: configurations whose single analysis time is also strong-scaled over the ranks "
                          "(the `strong` block of the line); empty string: none")
+    ap.add_argument("--e2e-dense", action="store_true",
+                    help="e2e leg: dense [kbu*nrep] observation rows (og_time_upload) instead of the sparse form")
     ap.add_argument("--e2e-lanes", type=int, default=0,
                     help="contexts (each on its own host thread) of the e2e leg; 0: two when the case is small")
     ap.add_argument("--pipeline-groups", type=int, default=0,

@@ -75,6 +75,13 @@ class OgTimeDesc(C.Structure):
                 ("ob_td", C.c_void_p), ("qc_td", C.c_void_p), ("bogus", C.c_void_p)]
 
 
+class OgObsCsr(C.Structure):
+    _fields_ = [("nnz", C.c_int), ("lev_start", C.c_void_p), ("rep", C.c_void_p),
+                ("u", C.c_void_p), ("v", C.c_void_p), ("t", C.c_void_p), ("rh", C.c_void_p), ("td", C.c_void_p),
+                ("qc_u", C.c_void_p), ("qc_v", C.c_void_p), ("qc_t", C.c_void_p), ("qc_rh", C.c_void_p),
+                ("qc_td", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/obsgrid_gpu.h declares.
 _vp = C.c_void_p
 SIGNATURES = {
@@ -130,6 +137,8 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int]),
     "og_time_download": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.c_int, C.c_int, C.c_int]),
     "og_time_wait": (C.c_int, [_vp, C.c_int]),
+    "og_time_upload_csr": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgObsCsr), C.c_int, C.c_int, C.c_int]),
+    "og_time_download_csr": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgObsCsr), C.c_int, C.c_int, C.c_int]),
     "og_qc_time_levels": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.c_int,
                                     C.c_int, C.c_int]),
     "og_dev_qc_time": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), C.c_int,

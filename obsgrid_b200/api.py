@@ -295,6 +295,17 @@ class Context:
                                          case_out.kbu if k_end is None else k_end, slot),
               "og_time_download")
 
+    def time_upload_csr(self, case, csr, slot, k_begin=0, k_end=None):
+        """og_time_upload with the observation rows in sparse form (synth.CsrObs)."""
+        d, o = case.desc(), csr.struct()
+        check(self._lib.og_time_upload_csr(self._h, C.byref(d), C.byref(o), k_begin,
+                                           case.kbu if k_end is None else k_end, slot), "og_time_upload_csr")
+
+    def time_download_csr(self, case_out, csr_out, slot, k_begin=0, k_end=None):
+        d, o = case_out.desc(), csr_out.struct()
+        check(self._lib.og_time_download_csr(self._h, C.byref(d), C.byref(o), k_begin,
+                                             case_out.kbu if k_end is None else k_end, slot), "og_time_download_csr")
+
     def time_wait(self, slot):
         check(self._lib.og_time_wait(self._h, slot), "og_time_wait")
 

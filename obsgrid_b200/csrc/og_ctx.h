@@ -43,7 +43,11 @@ struct og_ctx {
     cudaStream_t stream_in = nullptr, stream_out = nullptr;   // copy streams of og_qc_oa_time
     cudaStream_t stream_aux = nullptr;                        // second compute stream (scan kernels)
     std::vector<cudaEvent_t> pipe_events;
-    struct Slot { cudaEvent_t up = nullptr, comp = nullptr, down = nullptr; bool down_pending = false; };
+    struct Slot {
+        cudaEvent_t up = nullptr, comp = nullptr, down = nullptr;
+        bool down_pending = false;
+        bool has_td = false, has_bogus = false;      // optional rows the last upload brought (ABI 3)
+    };
     Slot slots[OG_SLOTS];
     og_stats stats{};
     int counting = 0;

@@ -203,6 +203,49 @@ __global__ void clamp_fg_rh_kernel(float* rh, int iew, int jns, int nlev)
 
 inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
+// ---- observation rows in sparse form (og_obs_csr) ------------------------------------------------
+struct CsrRows {
+    const int* lev_start;    // [kbu + 1] (device)
+    const int* rep;          // [nnz]
+    const float* v[5];       // compact u, v, t, rh, td (td nullable)
+    int* q[5];               // compact flags
+    float* dv[5];            // dense rows of the slot's mirror ([kbu * nrep]; td nullable)
+    int* dq[5];
+    int kbu, nrep, k0, k1;
+};
+// dense rows of the levels in range := "no measurement" everywhere
+__global__ void csr_clear_kernel(CsrRows C)
+{
+    const size_t n = (size_t)(C.k1 - C.k0) * C.nrep, off = (size_t)C.k0 * C.nrep;
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+        if (C.dv[a]) { C.dv[a][off + q] = OG_MISSING_R; C.dq[a][off + q] = 0; }
+}
+__device__ __forceinline__ int csr_level_of(const CsrRows& C, int e)
+{
+    int lo = 0, hi = C.kbu - 1;          // last k with lev_start[k] <= e
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (C.lev_start[mid] <= e) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+// to_dense != 0: compact -> dense (values and flags); else dense -> compact (flags, and td values)
+__global__ void csr_move_kernel(CsrRows C, int e0, int e1, int to_dense)
+{
+    const int e = e0 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (e >= e1) return;
+    const size_t d = (size_t)csr_level_of(C, e) * C.nrep + C.rep[e];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        if (!C.dv[a]) continue;
+        if (to_dense) { C.dv[a][d] = C.v[a][e]; C.dq[a][d] = C.q[a][e]; }
+        else { C.q[a][e] = C.dq[a][d]; if (a == 4) const_cast<float*>(C.v[a])[e] = C.dv[a][d]; }
+    }
+}
+
 // Device-resident view of one time (every pointer a device pointer, reference layouts).
 struct TimeDev {
     int iew, jns, kbu, nrep;
@@ -537,15 +580,15 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, int k0, int
     return qc_time_core(c, T, p, range_items(k0, k1), run_consistency);
 }
 
-int check_desc(const og_time_desc* d, int k0, int k1, bool qc)
+int check_desc(const og_time_desc* d, int k0, int k1, bool qc, bool obs_rows = true)
 {
     if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
     if (d->iew < 4 || d->jns < 4 || d->kbu < 1 || d->nrep < 0) { set_error("bad dimensions in og_time_desc"); return OG_ERR_INVALID; }
     if (k0 < 0 || k1 > d->kbu || k0 > k1) { set_error("bad level range [%d,%d) of %d", k0, k1, d->kbu); return OG_ERR_INVALID; }
     if (!d->pressure || !d->t || !d->u || !d->v || !d->rh || !d->slp) { set_error("null field pointer in og_time_desc"); return OG_ERR_INVALID; }
-    if (d->nrep > 0 && (!d->xob || !d->yob || !d->ob_u || !d->ob_v || !d->ob_t || !d->ob_rh || !d->ob_slp ||
+    if (obs_rows && d->nrep > 0 && (!d->xob || !d->yob || !d->ob_u || !d->ob_v || !d->ob_t || !d->ob_rh || !d->ob_slp ||
                         !d->qc_u || !d->qc_v || !d->qc_t || !d->qc_rh || !d->qc_slp)) { set_error("null observation pointer in og_time_desc"); return OG_ERR_INVALID; }
-    if (qc && d->nrep > 0 && (!d->lon || !d->elev)) { set_error("QC needs lon and elev"); return OG_ERR_INVALID; }
+    if (obs_rows && qc && d->nrep > 0 && (!d->lon || !d->elev)) { set_error("QC needs lon and elev"); return OG_ERR_INVALID; }
     return OG_OK;
 }
 
@@ -891,11 +934,12 @@ void* host_of(const og_time_desc* d, int i)
 // Device mirror of one slot (full [kbu] extent so that row offsets match the host arrays).
 int slot_mirror(og_ctx* c, const og_time_desc* d, int slot, TimeDev& T, void* dev[kNMirror])
 {
+    const bool has_td = c->slots[slot].has_td, has_bogus = c->slots[slot].has_bogus;
     const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep;
     char name[32];
     for (int i = 0; i < kNMirror; ++i) {
         dev[i] = nullptr;
-        if (!host_of(d, i)) continue;        // an optional row the caller does not have
+        if (i >= 15 && !has_td) continue;    // an optional row the slot's upload did not bring
         const size_t row = kMirror[i].row ? nrep : per;
         snprintf(name, sizeof name, "s%d.%s", slot, kMirror[i].name);
         OG_TRY(c->reserve(name, std::max<size_t>(row * (kMirror[i].sfc_only ? 1 : d->kbu), 1) * 4, &dev[i]));
@@ -904,7 +948,7 @@ int slot_mirror(og_ctx* c, const og_time_desc* d, int slot, TimeDev& T, void* de
     const char* tn[5] = {"x", "y", "lon", "elev", "bogus"};
     for (int i = 0; i < 5; ++i) {
         f4[i] = nullptr;
-        if (i == 4 && !d->bogus) continue;
+        if (i == 4 && !has_bogus) continue;
         snprintf(name, sizeof name, "s%d.%s", slot, tn[i]);
         OG_TRY(c->reserve_t(name, std::max<size_t>(nrep, 1), &f4[i]));
     }
@@ -937,6 +981,8 @@ extern "C" int og_time_upload(og_ctx* c, const og_time_desc* d, int k0, int k1, 
     REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
     OG_TRY(check_desc(d, k0, k1, true));
     OG_TRY(slot_events(c, slot));
+    c->slots[slot].has_td = d->ob_td && d->qc_td;
+    c->slots[slot].has_bogus = d->bogus != nullptr;
     TimeDev T; void* dev[kNMirror];
     OG_TRY(slot_mirror(c, d, slot, T, dev));
     og_ctx::Slot& s = c->slots[slot];
@@ -955,7 +1001,7 @@ extern "C" int og_time_upload(og_ctx* c, const og_time_desc* d, int k0, int k1, 
     OG_TRY(h2d((void*)T.lon, d->lon, nrep * 4)); OG_TRY(h2d((void*)T.elev, d->elev, nrep * 4));
     if (T.bogus) OG_TRY(h2d((void*)T.bogus, d->bogus, nrep * 4));
     for (int i = 0; i < kNMirror; ++i) {
-        if (!dev[i]) continue;
+        if (!dev[i] || !host_of(d, i)) continue;
         const size_t row = kMirror[i].row ? nrep : per;
         if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(h2d(dev[i], host_of(d, i), row * 4)); continue; }
         OG_TRY(h2d((char*)dev[i] + row * k0 * 4, (const char*)host_of(d, i) + row * k0 * 4, row * nlev * 4));
@@ -969,7 +1015,7 @@ extern "C" int og_time_compute(og_ctx* c, const og_time_desc* d, const og_qc_par
 {
     OG_BIND(c);
     REQUIRE(c && qp && op && slot >= 0 && slot < OG_SLOTS, "bad argument");
-    OG_TRY(check_desc(d, k0, k1, true));
+    OG_TRY(check_desc(d, k0, k1, true, false));      // dimensions and pressure only: the data are in the slot
     OG_TRY(slot_events(c, slot));
     TimeDev T; void* dev[kNMirror];
     OG_TRY(slot_mirror(c, d, slot, T, dev));
@@ -1003,7 +1049,7 @@ extern "C" int og_time_download(og_ctx* c, const og_time_desc* d, int k0, int k1
         return OG_OK;
     };
     for (int i = 0; i < kNMirror; ++i) {
-        if (!kMirror[i].out || !dev[i]) continue;
+        if (!kMirror[i].out || !dev[i] || !host_of(d, i)) continue;
         const size_t row = kMirror[i].row ? nrep : per;
         if (kMirror[i].sfc_only) { if (k0 == 0) OG_TRY(d2h(host_of(d, i), dev[i], row * 4)); continue; }
         OG_TRY(d2h((char*)host_of(d, i) + row * k0 * 4, (const char*)dev[i] + row * k0 * 4, row * nlev * 4));
@@ -1056,4 +1102,150 @@ extern "C" int og_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* 
     OG_BIND(c);
     if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
     return og_qc_time_levels(c, d, p, 0, d->kbu, 1);
+}
+
+// ---- asynchronous per-time API, observation rows in sparse form ------------------------------------
+namespace {
+
+int check_csr(const og_time_desc* d, const og_obs_csr* o, int k0, int k1)
+{
+    if (!d) { set_error("null og_time_desc"); return OG_ERR_INVALID; }
+    if (!o || o->nnz < 0 || !o->lev_start) { set_error("null or malformed og_obs_csr"); return OG_ERR_INVALID; }
+    if (d->iew < 4 || d->jns < 4 || d->kbu < 1 || d->nrep < 0 || k0 < 0 || k1 > d->kbu || k0 > k1) { set_error("bad dimensions / level range"); return OG_ERR_INVALID; }
+    if (!d->pressure || !d->t || !d->u || !d->v || !d->rh || !d->slp) { set_error("null field pointer in og_time_desc"); return OG_ERR_INVALID; }
+    if (d->nrep > 0 && (!d->xob || !d->yob || !d->lon || !d->elev || !d->ob_slp || !d->qc_slp)) { set_error("null per-report pointer in og_time_desc"); return OG_ERR_INVALID; }
+    if (o->nnz > 0 && (!o->rep || !o->u || !o->v || !o->t || !o->rh || !o->qc_u || !o->qc_v || !o->qc_t || !o->qc_rh)) { set_error("null row in og_obs_csr"); return OG_ERR_INVALID; }
+    if (o->lev_start[0] != 0 || o->lev_start[d->kbu] != o->nnz) { set_error("og_obs_csr: lev_start does not span [0, nnz]"); return OG_ERR_INVALID; }
+    for (int k = 0; k < d->kbu; ++k)
+        if (o->lev_start[k] > o->lev_start[k + 1]) { set_error("og_obs_csr: lev_start is not ascending"); return OG_ERR_INVALID; }
+    return OG_OK;
+}
+
+int csr_device_rows(og_ctx* c, const og_obs_csr* o, int kbu, int slot, CsrRows& C, int** d_lev, int** d_rep)
+{
+    char name[40];
+    const size_t nz = std::max<size_t>((size_t)o->nnz, 1);
+    snprintf(name, sizeof name, "s%d.csr.lev", slot);
+    OG_TRY(c->reserve_t(name, (size_t)kbu + 1, d_lev));
+    snprintf(name, sizeof name, "s%d.csr.rep", slot);
+    OG_TRY(c->reserve_t(name, nz, d_rep));
+    const char* vn[5] = {"u", "v", "t", "rh", "td"};
+    for (int a = 0; a < 5; ++a) {
+        float* fv; int* iq;
+        snprintf(name, sizeof name, "s%d.csr.v%s", slot, vn[a]);
+        OG_TRY(c->reserve_t(name, nz, &fv));
+        snprintf(name, sizeof name, "s%d.csr.q%s", slot, vn[a]);
+        OG_TRY(c->reserve_t(name, nz, &iq));
+        C.v[a] = fv; C.q[a] = iq;
+    }
+    C.lev_start = *d_lev; C.rep = *d_rep;
+    return OG_OK;
+}
+
+} // namespace
+
+extern "C" int og_time_upload_csr(og_ctx* c, const og_time_desc* d, const og_obs_csr* o, int k0, int k1, int slot)
+{
+    OG_BIND(c);
+    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
+    OG_TRY(check_csr(d, o, k0, k1));
+    OG_TRY(slot_events(c, slot));
+    c->slots[slot].has_td = o->td && o->qc_td;
+    c->slots[slot].has_bogus = d->bogus != nullptr;
+    TimeDev T; void* dev[kNMirror];
+    OG_TRY(slot_mirror(c, d, slot, T, dev));
+    CsrRows C{};
+    int *d_lev, *d_rep;
+    OG_TRY(csr_device_rows(c, o, d->kbu, slot, C, &d_lev, &d_rep));
+    og_ctx::Slot& s = c->slots[slot];
+    OG_CUDA(cudaEventRecord(s.up, c->stream));
+    OG_CUDA(cudaStreamWaitEvent(c->stream_in, s.up, 0));
+    if (s.down_pending) OG_CUDA(cudaStreamWaitEvent(c->stream_in, s.down, 0));
+    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
+    auto h2d = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!bytes) return OG_OK;
+        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream_in));
+        c->stats.h2d_bytes += (int64_t)bytes;
+        return OG_OK;
+    };
+    OG_TRY(h2d((void*)T.xob, d->xob, nrep * 4)); OG_TRY(h2d((void*)T.yob, d->yob, nrep * 4));
+    OG_TRY(h2d((void*)T.lon, d->lon, nrep * 4)); OG_TRY(h2d((void*)T.elev, d->elev, nrep * 4));
+    if (T.bogus) OG_TRY(h2d((void*)T.bogus, d->bogus, nrep * 4));
+    // fields and the per-report sea-level-pressure rows: dense, as in og_time_upload
+    OG_TRY(h2d(T.t + per * k0, d->t + per * k0, per * nlev * 4)); OG_TRY(h2d(T.u + per * k0, d->u + per * k0, per * nlev * 4));
+    OG_TRY(h2d(T.v + per * k0, d->v + per * k0, per * nlev * 4)); OG_TRY(h2d(T.rh + per * k0, d->rh + per * k0, per * nlev * 4));
+    if (k0 == 0) {
+        OG_TRY(h2d(T.slp, d->slp, per * 4));
+        OG_TRY(h2d((void*)T.ob_slp, d->ob_slp, nrep * 4)); OG_TRY(h2d(T.qc_slp, d->qc_slp, nrep * 4));
+    }
+    // the entries of the levels in range, compact
+    const int e0 = o->lev_start[k0], e1 = o->lev_start[k1];
+    const size_t ne = (size_t)(e1 - e0);
+    OG_TRY(h2d(d_lev, o->lev_start, ((size_t)d->kbu + 1) * 4));
+    OG_TRY(h2d(d_rep + e0, o->rep + e0, ne * 4));
+    const float* hv[5] = {o->u, o->v, o->t, o->rh, o->td};
+    int* hq[5] = {o->qc_u, o->qc_v, o->qc_t, o->qc_rh, o->qc_td};
+    float* dv[5] = {(float*)T.ob_u, (float*)T.ob_v, (float*)T.ob_t, (float*)T.ob_rh, T.ob_td};
+    int* dq[5] = {T.qc_u, T.qc_v, T.qc_t, T.qc_rh, T.qc_td};
+    for (int a = 0; a < 5; ++a) {
+        C.dv[a] = dv[a]; C.dq[a] = dq[a];
+        if (!dv[a]) continue;
+        OG_TRY(h2d(const_cast<float*>(C.v[a]) + e0, hv[a] + e0, ne * 4));
+        OG_TRY(h2d(C.q[a] + e0, hq[a] + e0, ne * 4));
+    }
+    C.kbu = d->kbu; C.nrep = d->nrep; C.k0 = k0; C.k1 = k1;
+    if (nlev * nrep) {
+        csr_clear_kernel<<<nblk(nlev * nrep), 256, 0, c->stream_in>>>(C);
+        c->count_launch();
+    }
+    if (ne) {
+        csr_move_kernel<<<nblk(ne), 256, 0, c->stream_in>>>(C, e0, e1, 1);
+        c->count_launch();
+    }
+    OG_CUDA(cudaGetLastError());
+    OG_CUDA(cudaEventRecord(s.up, c->stream_in));
+    return OG_OK;
+}
+
+extern "C" int og_time_download_csr(og_ctx* c, const og_time_desc* d, og_obs_csr* o, int k0, int k1, int slot)
+{
+    OG_BIND(c);
+    REQUIRE(c && slot >= 0 && slot < OG_SLOTS, "bad slot");
+    OG_TRY(check_csr(d, o, k0, k1));
+    OG_TRY(slot_events(c, slot));
+    TimeDev T; void* dev[kNMirror];
+    OG_TRY(slot_mirror(c, d, slot, T, dev));
+    CsrRows C{};
+    int *d_lev, *d_rep;
+    OG_TRY(csr_device_rows(c, o, d->kbu, slot, C, &d_lev, &d_rep));
+    og_ctx::Slot& s = c->slots[slot];
+    OG_CUDA(cudaStreamWaitEvent(c->stream_out, s.comp, 0));
+    const size_t per = (size_t)d->iew * d->jns, nrep = (size_t)d->nrep, nlev = (size_t)(k1 - k0);
+    auto d2h = [&](void* dst, const void* src, size_t bytes) -> int {
+        if (!bytes) return OG_OK;
+        OG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream_out));
+        c->stats.d2h_bytes += (int64_t)bytes;
+        return OG_OK;
+    };
+    float* dv[5] = {(float*)T.ob_u, (float*)T.ob_v, (float*)T.ob_t, (float*)T.ob_rh, T.ob_td};
+    int* dq[5] = {T.qc_u, T.qc_v, T.qc_t, T.qc_rh, T.qc_td};
+    for (int a = 0; a < 5; ++a) { C.dv[a] = dv[a]; C.dq[a] = dq[a]; }
+    C.kbu = d->kbu; C.nrep = d->nrep; C.k0 = k0; C.k1 = k1;
+    const int e0 = o->lev_start[k0], e1 = o->lev_start[k1];
+    const size_t ne = (size_t)(e1 - e0);
+    if (ne) {
+        csr_move_kernel<<<nblk(ne), 256, 0, c->stream_out>>>(C, e0, e1, 0);
+        c->count_launch();
+        OG_CUDA(cudaGetLastError());
+    }
+    OG_TRY(d2h(d->t + per * k0, T.t + per * k0, per * nlev * 4)); OG_TRY(d2h(d->u + per * k0, T.u + per * k0, per * nlev * 4));
+    OG_TRY(d2h(d->v + per * k0, T.v + per * k0, per * nlev * 4)); OG_TRY(d2h(d->rh + per * k0, T.rh + per * k0, per * nlev * 4));
+    if (k0 == 0) { OG_TRY(d2h(d->slp, T.slp, per * 4)); OG_TRY(d2h(d->qc_slp, T.qc_slp, nrep * 4)); }
+    int* hq[5] = {o->qc_u, o->qc_v, o->qc_t, o->qc_rh, o->qc_td};
+    for (int a = 0; a < 5; ++a)
+        if (dv[a] && hq[a]) OG_TRY(d2h(hq[a] + e0, C.q[a] + e0, ne * 4));
+    if (dv[4] && o->td) OG_TRY(d2h(const_cast<float*>(o->td) + e0, C.v[4] + e0, ne * 4));
+    OG_CUDA(cudaEventRecord(s.down, c->stream_out));
+    s.down_pending = true;
+    return OG_OK;
 }

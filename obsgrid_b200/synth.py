@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ._capi import OG_MAX_SCAN, OG_MISSING_R, OgOaParams, OgQcParams, OgTimeDesc
+from ._capi import OG_MAX_SCAN, OG_MISSING_R, OgObsCsr, OgOaParams, OgQcParams, OgTimeDesc
 
 # name -> (iew, jns, dx_m, kbu, n_surface, n_sounding, radii, n_times)
 CONFIGS = {
@@ -177,6 +177,60 @@ class TimeCase:
         return sum(getattr(self, n).nbytes for n in
                    ("xob", "yob", "lon", "elev", "ob_u", "ob_v", "ob_t", "ob_rh", "ob_slp") +
                    self._FLAGS)
+
+
+class CsrObs:
+    """The observation rows of a TimeCase in sparse form (og_obs_csr): per level the reports that
+    have any value there, ascending.  `alloc` maps a numpy array to the array to keep (e.g. a pinned copy)."""
+
+    ROWS = ("u", "v", "t", "rh", "td")
+
+    def __init__(self, case: "TimeCase", alloc=lambda a: a):
+        K, n = case.kbu, case.nrep
+        miss = np.float32(OG_MISSING_R)
+        present = np.zeros((K, n), bool)
+        for nm in ("ob_u", "ob_v", "ob_t", "ob_rh"):
+            present |= np.abs(getattr(case, nm) - miss) > 1.0
+        has_td = case.ob_td is not None and case.qc_td is not None
+        if has_td:
+            present |= np.abs(case.ob_td - miss) > 1.0
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh"):
+            present |= getattr(case, nm) != 0
+        k_idx, r_idx = np.nonzero(present)                   # row-major: level, then ascending report
+        self.kbu, self.nrep, self.has_td = K, n, has_td
+        self.lev_start = alloc(np.concatenate([[0], np.cumsum(present.sum(axis=1))]).astype(np.int32))
+        self.rep = alloc(r_idx.astype(np.int32))
+        self._k = k_idx
+        self.nnz = int(r_idx.size)
+        for nm in self.ROWS:
+            if nm == "td" and not has_td:
+                setattr(self, "td", None); setattr(self, "qc_td", None)
+                continue
+            setattr(self, nm, alloc(np.ascontiguousarray(getattr(case, "ob_" + nm)[k_idx, r_idx])))
+            setattr(self, "qc_" + nm, alloc(np.ascontiguousarray(getattr(case, "qc_" + nm)[k_idx, r_idx])))
+
+    def struct(self) -> OgObsCsr:
+        s = OgObsCsr()
+        s.nnz = self.nnz
+        s.lev_start, s.rep = self.lev_start.ctypes.data, self.rep.ctypes.data
+        for nm in self.ROWS:
+            a, q = getattr(self, nm), getattr(self, "qc_" + nm)
+            setattr(s, nm, a.ctypes.data if a is not None else None)
+            setattr(s, "qc_" + nm, q.ctypes.data if q is not None else None)
+        return s
+
+    def scatter_flags(self, case: "TimeCase"):
+        """Write the (downloaded) compact flag rows into the dense rows of `case`."""
+        for nm in self.ROWS:
+            q = getattr(self, "qc_" + nm)
+            if q is not None:
+                getattr(case, "qc_" + nm)[self._k, self.rep] = q
+        if self.has_td:
+            case.ob_td[self._k, self.rep] = self.td
+
+    def nbytes_up(self) -> int:
+        return sum(a.nbytes for a in [self.lev_start, self.rep] + [getattr(self, n) for n in self.ROWS if getattr(self, n) is not None]
+                   + [getattr(self, "qc_" + n) for n in self.ROWS if getattr(self, "qc_" + n) is not None])
 
 
 def default_qc_params(time_hhmmss: int = 120000) -> OgQcParams:

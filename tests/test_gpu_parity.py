@@ -418,6 +418,40 @@ def test_async_time_slots_pipeline(ctx):
             np.testing.assert_array_equal(getattr(times[i], nm), getattr(pristine[i], nm))
 
 
+@pytest.mark.parametrize("with_td", [False, True])
+def test_sparse_observation_rows_equal_the_dense_slot_path(ctx, with_td):
+    """og_time_upload_csr / og_time_download_csr (the observation rows as per-level lists of the reports
+    that have a measurement there) == og_time_upload / og_time_download, for level sub-ranges too."""
+    times = [synth.small_case(iew=48, jns=40, kbu=6, n_sfc=300, n_snd=80, seed=40 + t, radii=(5, 3)) for t in range(3)]
+    if with_td:
+        rng = np.random.default_rng(1)
+        for c in times:
+            c.ob_td = np.where(np.abs(c.ob_t + 888888.0) > 1, c.ob_t - rng.uniform(-2, 10, c.ob_t.shape), -888888.0).astype(np.float32)
+            c.qc_td = np.zeros_like(c.qc_t)
+            c.bogus = (rng.random(c.nrep) < 0.05).astype(np.int32)
+    want = [c.copy() for c in times]
+    for c in want:
+        ctx.proc_qc(c); ctx.proc_oa(c)
+    for (k0, k1) in ((0, 6), (2, 5)):
+        for i, c in enumerate(times):
+            csr_in, out = synth.CsrObs(c), c.copy()
+            csr_out = synth.CsrObs(c)
+            slot = i % 2
+            ctx.time_upload_csr(c, csr_in, slot, k0, k1)
+            ctx.time_compute(c, slot, k0, k1)
+            ctx.time_download_csr(out, csr_out, slot, k0, k1)
+            ctx.time_wait(slot)
+            csr_out.scatter_flags(out)
+            names = ("qc_u", "qc_v", "qc_t", "qc_rh", "t", "u", "v", "rh") + (("qc_td", "ob_td") if with_td else ())
+            for nm in names:
+                np.testing.assert_array_equal(getattr(out, nm)[k0:k1], getattr(want[i], nm)[k0:k1], err_msg=f"{i}:{nm}")
+                np.testing.assert_array_equal(getattr(out, nm)[:k0], getattr(c, nm)[:k0], err_msg=f"{i}:{nm} below the range")
+            if k0 == 0:
+                np.testing.assert_array_equal(out.qc_slp, want[i].qc_slp)
+                np.testing.assert_array_equal(out.slp, want[i].slp)
+            assert csr_in.nnz < c.kbu * c.nrep // 2
+
+
 def test_time_level_sharding_is_exact(ctx):
     """Levels are independent: ranges and variable masks compose to the full run."""
     base = synth.small_case(iew=50, jns=44, kbu=7, n_sfc=300, n_snd=100, radii=(5, 3))
