@@ -627,6 +627,37 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         per_slab = {"value": updates / (ps_ms * 1e-3), "unit": UNIT, "ms_per_step": ps_ms, "library_calls": n_calls,
                     "api": "the reference's slab loops over og_error_max / og_buddy_check / og_innovation / og_cressman, "
                            "host arrays, one blocking call per slab and stage (obsgrid_b200/perslab.py)"}
+    # ---- BASELINE configs[3] as the pipeline it is: the surface-FDDA chain, resident -----------------
+    fdda_line = None
+    if args.config == 4 and world == 1 and args.fdda_times > 1:
+        from obsgrid_b200 import fdda
+        cases3d, hourly = fdda.synthetic_chain(4, args.fdda_times, 6)
+        be = fdda.DeviceBackend(ctx, torch, dev)
+        for c_ in cases3d + hourly:
+            be.upload(c_)
+        keep = {id(c_): {nm: be.tensors(c_)[nm].clone() for nm in FIELD_NAMES + FLAG_NAMES} for c_ in cases3d + hourly}
+
+        def chain_once():
+            torch.cuda.synchronize(dev)
+            for c_ in cases3d + hourly:
+                for nm, src in keep[id(c_)].items():
+                    be.tensors(c_)[nm].copy_(src)
+            torch.cuda.synchronize(dev)
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(lib_stream)
+            fdda.run_chain(be, cases3d, hourly, 6)
+            b_.record(lib_stream)
+            ctx.sync()
+            return a_.elapsed_time(b_)
+
+        chain_once()
+        ms_chain = float(np.mean([chain_once() for _ in range(2)]))
+        fdda_line = {"traditional_times": len(cases3d), "fdda_times": len(hourly), "ms_per_chain": ms_chain,
+                     "ms_per_analysis_time": ms_chain / (len(cases3d) + len(hourly)),
+                     "what": "3-D analyses (27 levels) of the traditional times, store_fa, temporal_interp, proc_qc with "
+                             "ob_density / obs_distance and surface-only proc_oa of every FDDA time in between; every "
+                             "field resident in HBM (obsgrid_b200/fdda.py, driver.F90:107-113,306-341,561-563)"}
+        del keep, be
     clocks = sampler.stop()
 
     # ---- strong scaling of single analysis times, inside the same line (N > 1, weak runs) ---------
@@ -720,6 +751,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                      "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
                      "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps} if do_e2e else None),
             "e2e_per_slab": per_slab,
+            "fdda_chain": fdda_line,
             "strong": strong,
             "gpu_launches": int(g_launch),
             "clocks": clocks,
@@ -764,6 +796,9 @@ def main():
     ap.add_argument("--strong-configs", default="3",
                     help="N > 1: configurations whose single analysis time is also strong-scaled over the ranks "
                          "(the `strong` block of the line); empty string: none")
+    ap.add_argument("--fdda-times", type=int, default=5,
+                    help="--config 4: traditional (6-hourly, 3-D) analysis times of the surface-FDDA chain; "
+                         "5 of them bracket 20 hourly surface analyses (0 or 1: skip the chain)")
     ap.add_argument("--e2e-dense", action="store_true",
                     help="e2e leg: dense [kbu*nrep] observation rows (og_time_upload) instead of the sparse form")
     ap.add_argument("--e2e-lanes", type=int, default=0,

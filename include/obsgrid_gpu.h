@@ -406,6 +406,20 @@ int og_dev_qc_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p,
                    int k_begin, int k_end, int run_consistency);
 int og_dev_oa_time(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
                    int k_begin, int k_end);
+/* Device-resident forms of og_temporal_interp and og_qc_time_fdda (every array a device pointer):
+ * with og_dev_qc_time / og_dev_oa_time they compose the surface-FDDA chain of driver.F90:107-113,
+ * :306-341, :561-563 without a field leaving HBM between its phases -- the 3-D analyses of the
+ * bracketing times, store_fa, temporal_interp to every FDDA time, proc_qc with the observation
+ * density and the surface-only proc_oa (obsgrid_b200/fdda.py composes them). */
+int og_dev_temporal_interp(og_ctx* ctx, const float* first, const float* second, float* out,
+                           int jns, int iew, int nlev, int icount_fdda, int icount_1, int icount_2,
+                           int cross);
+int og_dev_qc_time_fdda(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p, float* tobbox,
+                        float* odis);
+/* field(j,i) *= factor on a (jns,iew) device array; interior_only: (1:jns-1, 1:iew-1) only -- store_fa
+ * keeps PMSL in Pa (slp_x * 100., tinterp_module.F90:45) and the driver brings the interpolated field
+ * back with slp_x(:jns-1,:iew-1) * 0.01 (driver.F90:322, :336). */
+int og_dev_scale_field(og_ctx* ctx, float* field, int jns, int iew, float factor, int interior_only);
 /* Stream all library work is issued on (a cudaStream_t), for event timing by the caller. */
 void* og_stream(og_ctx* ctx);
 int   og_sync(og_ctx* ctx);

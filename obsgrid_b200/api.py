@@ -320,6 +320,17 @@ class Context:
             check(rc, "og_dev_oa_time")
         return rc
 
+    def dev_temporal_interp(self, first_ptr, second_ptr, out_ptr, jns, iew, nlev, icount_fdda, icount_1, icount_2, cross):
+        check(self._lib.og_dev_temporal_interp(self._h, first_ptr, second_ptr, out_ptr, jns, iew, nlev,
+                                               icount_fdda, icount_1, icount_2, int(cross)), "og_dev_temporal_interp")
+
+    def dev_scale_field(self, ptr_, jns, iew, factor, interior_only=False):
+        check(self._lib.og_dev_scale_field(self._h, ptr_, jns, iew, factor, int(interior_only)), "og_dev_scale_field")
+
+    def dev_proc_qc_fdda(self, desc, qc_params, tobbox_ptr, odis_ptr):
+        check(self._lib.og_dev_qc_time_fdda(self._h, C.byref(desc), C.byref(qc_params), tobbox_ptr, odis_ptr),
+              "og_dev_qc_time_fdda")
+
     def dev_proc_qc_items(self, desc, qc_params, levels, masks, run_consistency=True):
         lv, mk = i32(levels), i32(masks)
         check(self._lib.og_dev_qc_time_items(self._h, C.byref(desc), C.byref(qc_params), ptr(lv), ptr(mk),

@@ -410,6 +410,21 @@ extern "C" int og_temporal_interp(og_ctx* c, const float* first, const float* se
     return OG_OK;
 }
 
+// device-resident form: first / second / out are device pointers (the surface-FDDA chain keeps the
+// analysed 3-D times in HBM between its phases)
+extern "C" int og_dev_temporal_interp(og_ctx* c, const float* first, const float* second, float* out,
+                                      int jns, int iew, int nlev, int icount_fdda, int icount_1,
+                                      int icount_2, int cross)
+{
+    OG_BIND(c);
+    REQUIRE(c && first && second && out && jns >= 2 && iew >= 2 && nlev >= 1, "bad argument");
+    REQUIRE(iew <= 65535 && nlev <= 65535, "too many columns or levels");
+    int w1 = icount_2 - icount_fdda, w2 = icount_fdda - icount_1;
+    if (w1 == 0 && w2 == 0) w1 = 1;
+    if (w1 + w2 == 0) { set_error("temporal_interp: weights sum to zero (tinterp_module.F90:112)"); return OG_ERR_INVALID; }
+    return temporal_interp_device(c, first, second, out, jns, iew, nlev, (float)w1, (float)w2, (float)(w1 + w2), cross);
+}
+
 extern "C" int og_pres_sfc_from_slp(og_ctx* c, const float* pres_sfc, const float* slp_C,
                                     const float* slp_x, float* out, int jns, int iew)
 {

@@ -1097,6 +1097,39 @@ extern "C" int og_qc_time_fdda(og_ctx* c, const og_time_desc* d, const og_qc_par
     return OG_OK;
 }
 
+// a(j,i) *= f on a (jns,iew) field, j fastest; interior != 0: only (1:jns-1, 1:iew-1), as the driver
+// rescales slp_x after temporal_interp (driver.F90:322, :336)
+__global__ void scale2d_kernel(float* __restrict__ a, int jns, int iew, float f, int interior)
+{
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (size_t)jns * iew) return;
+    const int j = (int)(q % jns), i = (int)(q / jns);
+    if (interior && (j >= jns - 1 || i >= iew - 1)) return;
+    a[q] = fmul(a[q], f);
+}
+extern "C" int og_dev_scale_field(og_ctx* c, float* field, int jns, int iew, float factor, int interior_only)
+{
+    OG_BIND(c);
+    REQUIRE(c && field && jns >= 1 && iew >= 1, "bad argument");
+    scale2d_kernel<<<nblk((size_t)jns * iew), 256, 0, c->stream>>>(field, jns, iew, factor, interior_only);
+    c->count_launch();
+    OG_CUDA(cudaGetLastError());
+    return OG_OK;
+}
+
+// device-resident form of og_qc_time_fdda: every pointer of `d` and tobbox / odis are device pointers
+extern "C" int og_dev_qc_time_fdda(og_ctx* c, const og_time_desc* d, const og_qc_params* p, float* tobbox,
+                                   float* odis)
+{
+    OG_BIND(c);
+    REQUIRE(c && p && tobbox && odis, "null argument");
+    OG_TRY(check_desc(d, 0, d ? d->kbu : 0, true));
+    REQUIRE(d->iew <= 32000 && d->jns <= 32000, "grid larger than 32000 points per edge");
+    TimeDev T = view_of(d);
+    T.tobbox = tobbox; T.odis = odis;
+    return qc_time_core(c, T, p, 0, d->kbu, 1);
+}
+
 extern "C" int og_qc_time(og_ctx* c, const og_time_desc* d, const og_qc_params* p)
 {
     OG_BIND(c);

@@ -47,14 +47,14 @@ static void civil_from_days(long long z, int* y, int* m, int* d)
     *m = mp + (mp < 10 ? 3 : -9);
     *y = (int)(yoe + era * 400 + (*m <= 2));
 }
-static void newdate(char out[40], int date, int time, int ds)
+static void newdate(char out[64], int date, int time, int ds)
 {
     long long s = civil_days(date / 10000, (date / 100) % 100, date % 100) * 86400LL +
                   (time / 10000) * 3600 + ((time / 100) % 100) * 60 + time % 100 + ds;
     long long day = s >= 0 ? s / 86400 : -((-s + 86399) / 86400);
     int sec = (int)(s - day * 86400), y, m, d;
     civil_from_days(day, &y, &m, &d);
-    snprintf(out, 40, "%04d-%02d-%02d_%02d:%02d:%02d", y, m, d, sec / 3600, (sec / 60) % 60, sec % 60);
+    snprintf(out, 64, "%04d-%02d-%02d_%02d:%02d:%02d", y, m, d, sec / 3600, (sec / 60) % 60, sec % 60);
 }
 
 static int window_ds(const char* platform)         /* ob_access_module.F90:88-112 */
@@ -84,7 +84,7 @@ static float dewpoint_of(float t_value, float rh_value)     /* ob_access_module.
 void ogo_query_ob(og_report* obs, og_meas* meas, int date, int time, int var, float request_level,
                   int request_qc_max, int request_p_diff, float* value, int* qc)
 {
-    char obs_date[20], p1[40], m1[40];
+    char obs_date[20], p1[64], m1[64];
     const char* c = obs->date_char;
     snprintf(obs_date, sizeof obs_date, "%.4s-%.2s-%.2s_%.2s:%.2s:%.2s", c, c + 4, c + 6, c + 8, c + 10, c + 12);
     int ds = window_ds(obs->platform);

@@ -636,6 +636,64 @@ def test_qc_time_fdda_density_bit_exact(ctx, oracle):
             np.testing.assert_array_equal(getattr(cpu, nm), getattr(gpu, nm))
 
 
+class _OracleProc:
+    """The oracle behind the interface fdda.HostBackend drives."""
+
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def proc_qc_fdda(self, case, tob):
+        return self.o.qc_time_fdda(case, tob)
+
+    def proc_oa(self, case):
+        return self.o.oa_time(case)
+
+    def temporal_interp(self, a, b, cf, c1, c2, cross):
+        rc, out = self.o.temporal_interp(a, b, cf, c1, c2, cross)
+        assert rc == 0
+        return out
+
+
+def test_surface_fdda_chain(ctx, oracle):
+    """BASELINE configs[3] as the pipeline it is (driver.F90:107-113, :306-341, :561-563): 3-D analyses of
+    the traditional times -> store_fa -> temporal_interp -> proc_qc with the observation density ->
+    surface-only proc_oa for every FDDA time in between, tobbox handed on from call to call.  The GPU
+    with host arrays, the GPU with everything resident (fdda.DeviceBackend) and the oracle composition
+    agree: flags bit for bit, t / slp bit for bit, u / v / rh within the north-star tolerance."""
+    import torch
+    from obsgrid_b200 import fdda
+    small = dict(iew=72, jns=60, kbu=5, n_sfc=500, n_snd=60, radii=(6, 4), dx_m=60000.0)
+    ratio = 3
+    runs = {}
+    for name in ("oracle", "host", "device"):
+        cases3d, hourly = fdda.synthetic_chain(None, 3, ratio, **small)
+        if name == "device":
+            be = fdda.DeviceBackend(ctx, torch, torch.device("cuda", 0))
+            for c in cases3d + hourly:
+                be.upload(c)
+        else:
+            be = fdda.HostBackend(_OracleProc(oracle) if name == "oracle" else ctx)
+        fdda.run_chain(be, cases3d, hourly, ratio)
+        if name == "device":
+            ctx.sync()
+            for c in cases3d + hourly:
+                be.download(c)
+        runs[name] = (cases3d, hourly)
+    assert len(runs["oracle"][1]) == 2 * (ratio - 1)
+    for other in ("host", "device"):
+        for a, b in zip(runs["oracle"][0] + runs["oracle"][1], runs[other][0] + runs[other][1]):
+            for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "slp"):
+                np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=f"{other}:{nm}")
+            for nm in ("u", "v", "rh"):
+                np.testing.assert_allclose(getattr(b, nm), getattr(a, nm), rtol=RTOL, atol=ATOL, err_msg=f"{other}:{nm}")
+    for nm in ("t", "u", "v", "rh", "slp", "qc_t"):      # host-array and resident GPU chains: the same bits
+        for a, b in zip(runs["host"][1], runs["device"][1]):
+            np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=nm)
+    h0 = runs["oracle"][1][0]
+    fresh = fdda.synthetic_chain(None, 3, ratio, **small)[1][0]
+    assert np.any(h0.t != fresh.t) and np.count_nonzero(h0.qc_t) > 0
+
+
 @pytest.mark.parametrize("shape", [(3, 6, 5), (27, 120, 97), (64, 51)])
 def test_temporal_interp_bit_exact(ctx, oracle, shape):
     """tinterp_module.F90:53-215, every weight pattern of a 6-hour bracket, both grid kinds."""
