@@ -101,6 +101,9 @@ class DeviceBackend:
     def __init__(self, ctx, torch, device):
         self.ctx, self.torch, self.device = ctx, torch, device
         self._dev = {}
+        # torch's own kernels (clone, zeros) must queue on the library's stream: the chain is one
+        # stream-ordered sequence, nothing synchronises in between
+        self.stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
 
     def upload(self, case):
         names = ("t", "u", "v", "rh", "slp", "qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "xob", "yob", "lon", "elev",
@@ -116,8 +119,9 @@ class DeviceBackend:
         return self._dev[id(case)][0]
 
     def zeros2d(self, case):
-        self.odis = self.torch.zeros((case.iew, case.jns), dtype=self.torch.float32, device=self.device)
-        return self.torch.zeros((case.iew, case.jns), dtype=self.torch.float32, device=self.device)
+        with self.torch.cuda.stream(self.stream):
+            self.odis = self.torch.zeros((case.iew, case.jns), dtype=self.torch.float32, device=self.device)
+            return self.torch.zeros((case.iew, case.jns), dtype=self.torch.float32, device=self.device)
 
     def analyse_3d(self, case, tob):
         t, d = self._dev[id(case)]
@@ -127,8 +131,9 @@ class DeviceBackend:
 
     def store_fa(self, case):
         t, _ = self._dev[id(case)]
-        s = {nm: t[nm][0].clone() for nm in FIELDS3}
-        s["slp"] = t["slp"].clone()
+        with self.torch.cuda.stream(self.stream):
+            s = {nm: t[nm][0].clone() for nm in FIELDS3}
+            s["slp"] = t["slp"].clone()
         self.ctx.dev_scale_field(s["slp"].data_ptr(), case.jns, case.iew, 100.0, False)
         return s
 

@@ -657,13 +657,28 @@ class _OracleProc:
 def test_surface_fdda_chain(ctx, oracle):
     """BASELINE configs[3] as the pipeline it is (driver.F90:107-113, :306-341, :561-563): 3-D analyses of
     the traditional times -> store_fa -> temporal_interp -> proc_qc with the observation density ->
-    surface-only proc_oa for every FDDA time in between, tobbox handed on from call to call.  The GPU
-    with host arrays, the GPU with everything resident (fdda.DeviceBackend) and the oracle composition
-    agree: flags bit for bit, t / slp bit for bit, u / v / rh within the north-star tolerance."""
+    surface-only proc_oa for every FDDA time in between, tobbox handed on from call to call.
+      * the GPU chain with host arrays and the GPU chain with everything resident (fdda.DeviceBackend)
+        give the same bits;
+      * against the oracle composition: every flag, t and slp bit for bit along the whole chain;
+      * u / v / rh within the north-star tolerance stage by stage -- each FDDA time re-analysed by the
+        GPU from the oracle's own interpolated first guess (a tolerance-level difference of a wind field
+        that is then interpolated, checked and re-analysed can flip a circle / ellipse / banana
+        decision further down the chain, so the end-to-end comparison of those fields is not a
+        per-stage bound)."""
     import torch
     from obsgrid_b200 import fdda
     small = dict(iew=72, jns=60, kbu=5, n_sfc=500, n_snd=60, radii=(6, 4), dx_m=60000.0)
     ratio = 3
+
+    class Recording(fdda.HostBackend):
+        """Keeps every FDDA time's input state (first guess, flags, tobbox) of the oracle chain."""
+        def __init__(self, proc):
+            super().__init__(proc); self.inputs = []
+        def analyse_surface(self, hc, tob):
+            self.inputs.append((hc.copy(), tob.copy()))
+            return super().analyse_surface(hc, tob)
+
     runs = {}
     for name in ("oracle", "host", "device"):
         cases3d, hourly = fdda.synthetic_chain(None, 3, ratio, **small)
@@ -671,8 +686,10 @@ def test_surface_fdda_chain(ctx, oracle):
             be = fdda.DeviceBackend(ctx, torch, torch.device("cuda", 0))
             for c in cases3d + hourly:
                 be.upload(c)
+        elif name == "oracle":
+            be = rec = Recording(_OracleProc(oracle))
         else:
-            be = fdda.HostBackend(_OracleProc(oracle) if name == "oracle" else ctx)
+            be = fdda.HostBackend(ctx)
         fdda.run_chain(be, cases3d, hourly, ratio)
         if name == "device":
             ctx.sync()
@@ -680,15 +697,23 @@ def test_surface_fdda_chain(ctx, oracle):
                 be.download(c)
         runs[name] = (cases3d, hourly)
     assert len(runs["oracle"][1]) == 2 * (ratio - 1)
-    for other in ("host", "device"):
-        for a, b in zip(runs["oracle"][0] + runs["oracle"][1], runs[other][0] + runs[other][1]):
-            for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "slp"):
-                np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=f"{other}:{nm}")
-            for nm in ("u", "v", "rh"):
-                np.testing.assert_allclose(getattr(b, nm), getattr(a, nm), rtol=RTOL, atol=ATOL, err_msg=f"{other}:{nm}")
-    for nm in ("t", "u", "v", "rh", "slp", "qc_t"):      # host-array and resident GPU chains: the same bits
-        for a, b in zip(runs["host"][1], runs["device"][1]):
-            np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=nm)
+    for a, b in zip(runs["host"][0] + runs["host"][1], runs["device"][0] + runs["device"][1]):
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
+            np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=f"host vs device:{nm}")
+    for a, b in zip(runs["oracle"][0] + runs["oracle"][1], runs["host"][0] + runs["host"][1]):
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "slp"):
+            np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm), err_msg=f"oracle vs gpu:{nm}")
+    for a, b in zip(runs["oracle"][0], runs["host"][0]):            # the 3-D times: same inputs on both sides
+        for nm in ("u", "v", "rh"):
+            np.testing.assert_allclose(getattr(b, nm), getattr(a, nm), rtol=RTOL, atol=ATOL, err_msg=nm)
+    for (inp, tob), want in zip(rec.inputs, runs["oracle"][1]):     # the FDDA times: stage by stage
+        got = inp.copy()
+        tb, _ = ctx.proc_qc_fdda(got, tob)
+        ctx.proc_oa(got)
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "slp"):
+            np.testing.assert_array_equal(getattr(got, nm), getattr(want, nm), err_msg=nm)
+        for nm in ("u", "v", "rh"):
+            np.testing.assert_allclose(getattr(got, nm), getattr(want, nm), rtol=RTOL, atol=ATOL, err_msg=nm)
     h0 = runs["oracle"][1][0]
     fresh = fdda.synthetic_chain(None, 3, ratio, **small)[1][0]
     assert np.any(h0.t != fresh.t) and np.count_nonzero(h0.qc_t) > 0
