@@ -406,6 +406,30 @@ int og_dev_qc_time(og_ctx* ctx, const og_time_desc* d, const og_qc_params* p,
                    int k_begin, int k_end, int run_consistency);
 int og_dev_oa_time(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
                    int k_begin, int k_end);
+/* ---- one (level, variable) slab over several GPUs ----------------------------------------------
+ * The buddy check of a dense surface network is the largest indivisible unit of a time period (2 M
+ * reports: tens of milliseconds), so a run that strong-scales one analysis time has to cut inside the
+ * slab.  With an exchange function installed, og_*qc_time* on a context of rank r of `world`:
+ *   - every rank prepares every observation of the batch (error_max, difmax: O(N));
+ *   - the buddy check's cells are dealt to the ranks (cell index mod world): a rank builds the
+ *     candidate lists of its own cells only and runs the pair kernels for the observations sitting
+ *     in them -- each target's count and index-ordered sum are computed by exactly one rank, with
+ *     the very operations of the unsharded run;
+ *   - the relaxation mask of qc2_module.F90:327 is combined after every pass of the fix-point
+ *     (exchange, OG_XCHG_MAX on bytes), the flags once at the end (OG_XCHG_MAX on int32: only the
+ *     owner of an observation adds bits to the common starting value, so MAX is the bitwise OR).
+ * The result on every rank is bit-identical to the single-GPU result.
+ *
+ * exchange(user, buf, count, dtype, op, stream): all-reduce `count` elements at device pointer `buf`
+ * in place over the ranks, ordered on the CUDA stream `stream` (a cudaStream_t); must return 0.
+ * NCCL: ncclAllReduce(buf, buf, count, dtype, op, comm, stream); obsgrid_b200/shard.py wraps
+ * torch.distributed. */
+enum { OG_XCHG_INT32 = 0, OG_XCHG_UINT8 = 1 };
+enum { OG_XCHG_SUM = 0, OG_XCHG_MAX = 1 };
+typedef int (*og_exchange_fn)(void* user, void* buf, size_t count, int dtype, int op, void* stream);
+/* world <= 1 or fn == NULL: back to single-GPU behaviour. */
+int og_set_exchange(og_ctx* ctx, int rank, int world, og_exchange_fn fn, void* user);
+
 /* Device-resident forms of og_temporal_interp and og_qc_time_fdda (every array a device pointer):
  * with og_dev_qc_time / og_dev_oa_time they compose the surface-FDDA chain of driver.F90:107-113,
  * :306-341, :561-563 without a field leaving HBM between its phases -- the 3-D analyses of the

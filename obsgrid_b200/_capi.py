@@ -75,6 +75,12 @@ class OgTimeDesc(C.Structure):
                 ("ob_td", C.c_void_p), ("qc_td", C.c_void_p), ("bogus", C.c_void_p)]
 
 
+# og_exchange_fn(user, buf, count, dtype, op, stream)
+OG_EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p)
+OG_XCHG_INT32, OG_XCHG_UINT8 = 0, 1
+OG_XCHG_SUM, OG_XCHG_MAX = 0, 1
+
+
 class OgObsCsr(C.Structure):
     _fields_ = [("nnz", C.c_int), ("lev_start", C.c_void_p), ("rep", C.c_void_p),
                 ("u", C.c_void_p), ("v", C.c_void_p), ("t", C.c_void_p), ("rh", C.c_void_p), ("td", C.c_void_p),
@@ -151,6 +157,7 @@ SIGNATURES = {
     "og_dev_temporal_interp": (C.c_int, [_vp, _vp, _vp, _vp] + [C.c_int] * 7),
     "og_dev_qc_time_fdda": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), _vp, _vp]),
     "og_dev_scale_field": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, C.c_int]),
+    "og_set_exchange": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "og_stream": (_vp, [_vp]),
     "og_sync": (C.c_int, [_vp]),
     "og_last_kernel_ms": (C.c_int, [_vp, fp, fp]),

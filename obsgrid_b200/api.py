@@ -324,6 +324,13 @@ class Context:
         check(self._lib.og_dev_temporal_interp(self._h, first_ptr, second_ptr, out_ptr, jns, iew, nlev,
                                                icount_fdda, icount_1, icount_2, int(cross)), "og_dev_temporal_interp")
 
+    def set_exchange(self, rank, world, fn=None):
+        """One slab over several GPUs (og_set_exchange): `fn` is a _capi.OG_EXCHANGE_FN (shard.make_exchange
+        builds one over torch.distributed); the context keeps it alive.  fn None / world 1: off."""
+        self._exchange_fn = fn
+        check(self._lib.og_set_exchange(self._h, rank, world, C.cast(fn, C.c_void_p) if fn is not None else None, None),
+              "og_set_exchange")
+
     def dev_scale_field(self, ptr_, jns, iew, factor, interior_only=False):
         check(self._lib.og_dev_scale_field(self._h, ptr_, jns, iew, factor, int(interior_only)), "og_dev_scale_field")
 

@@ -24,6 +24,7 @@ constexpr int NB_MAX = 4096;         // value buckets of the long-list sorter
 struct BinDev {
     const BinSlab* slabs;
     int ns;
+    int own_rank, own_world;   // cells dealt to ranks: (local cell index) % own_world == own_rank are built
     const short4* box;
     int* cell_count;
     int* cell_cursor;
@@ -35,13 +36,17 @@ struct BinDev {
 };
 
 template <class F>
-__device__ __forceinline__ void for_each_cell(const BinSlab& S, short4 b, F f)
+__device__ __forceinline__ void for_each_cell(const BinDev& A, const BinSlab& S, short4 b, F f)
 {
     if (b.x > b.y || b.z > b.w) return;
     const int cx0 = max((b.x - 1) / S.cell, 0), cx1 = min((b.y - 1) / S.cell, S.ncx - 1);
     const int cy0 = max((b.z - 1) / S.cell, 0), cy1 = min((b.w - 1) / S.cell, S.ncy - 1);
     for (int cy = cy0; cy <= cy1; ++cy)
-        for (int cx = cx0; cx <= cx1; ++cx) f(S.cell_off + cy * S.ncx + cx);
+        for (int cx = cx0; cx <= cx1; ++cx) {
+            const int lc = cy * S.ncx + cx;
+            if (A.own_world > 1 && lc % A.own_world != A.own_rank) continue;
+            f(S.cell_off + lc);
+        }
 }
 
 // Slabs with at most HCAP cells histogram in shared memory first, so that the global atomics
@@ -56,13 +61,13 @@ __global__ void __launch_bounds__(256) bin_count_kernel(BinDev A)
     const int nc = S.ncx * S.ncy;
     const short4 box = (li < S.n) ? A.box[S.ob_off + li] : make_short4(1, 0, 1, 0);
     if (nc > HCAP) {
-        for_each_cell(S, box, [&](int c) { atomicAdd(&A.cell_count[c], 1); });
+        for_each_cell(A, S, box, [&](int c) { atomicAdd(&A.cell_count[c], 1); });
         return;
     }
     __shared__ int s_hist[HCAP];
     for (int q = threadIdx.x; q < nc; q += blockDim.x) s_hist[q] = 0;
     __syncthreads();
-    for_each_cell(S, box, [&](int c) { atomicAdd(&s_hist[c - S.cell_off], 1); });
+    for_each_cell(A, S, box, [&](int c) { atomicAdd(&s_hist[c - S.cell_off], 1); });
     __syncthreads();
     for (int q = threadIdx.x; q < nc; q += blockDim.x) {
         const int v = s_hist[q];
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
     const int nc = S.ncx * S.ncy;
     const short4 box = (li < S.n) ? A.box[S.ob_off + li] : make_short4(1, 0, 1, 0);
     if (nc > HCAP) {
-        for_each_cell(S, box, [&](int c) {
+        for_each_cell(A, S, box, [&](int c) {
             const int pos = atomicAdd(&A.cell_cursor[c], 1);
             A.cell_list[A.cell_start[c] + pos] = li;
         });
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
     __shared__ int s_base[HCAP];    // first slot of the block in the cell's list
     for (int q = threadIdx.x; q < nc; q += blockDim.x) s_hist[q] = 0;
     __syncthreads();
-    for_each_cell(S, box, [&](int c) { atomicAdd(&s_hist[c - S.cell_off], 1); });
+    for_each_cell(A, S, box, [&](int c) { atomicAdd(&s_hist[c - S.cell_off], 1); });
     __syncthreads();
     for (int q = threadIdx.x; q < nc; q += blockDim.x) {
         const int v = s_hist[q];
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
         s_hist[q] = 0;
     }
     __syncthreads();
-    for_each_cell(S, box, [&](int c) {
+    for_each_cell(A, S, box, [&](int c) {
         const int q = c - S.cell_off;
         A.cell_list[s_base[q] + atomicAdd(&s_hist[q], 1)] = li;
     });
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A)
 } // namespace
 
 int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, const short4* d_box,
-              bool sorted, BinLists* out)
+              bool sorted, BinLists* out, int own_rank, int own_world)
 {
     const int ns = (int)slabs.size();
     cudaStream_t st = ctx->stream;
@@ -392,6 +397,7 @@ int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, c
     OG_TRY(ctx->reserve_t((t + ".cursor").c_str(), (size_t)ncells + 1, &A.cell_cursor));
     OG_TRY(ctx->reserve_t((t + ".start").c_str(), (size_t)ncells + 1, &A.cell_start));
     A.slabs = d_slabs; A.ns = ns; A.box = d_box;
+    A.own_rank = own_rank; A.own_world = own_world;
     std::vector<BinSlab> hs(slabs);
     int nblk = 0;
     for (BinSlab& q : hs) { q.blk_off = nblk; nblk += (q.n + 255) / 256; }

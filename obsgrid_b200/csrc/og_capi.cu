@@ -147,6 +147,14 @@ extern "C" int og_selftest_div(og_ctx* c, int n, unsigned seed, int rmax, long l
     if (!c || !bad || n <= 0 || rmax <= 0) return OG_ERR_INVALID;
     return div_selftest(c, n, seed, rmax, bad);
 }
+extern "C" int og_set_exchange(og_ctx* c, int rank, int world, og_exchange_fn fn, void* user)
+{
+    if (!c) return OG_ERR_INVALID;
+    if (world <= 1 || !fn) { c->shard_rank = 0; c->shard_world = 1; c->exchange = nullptr; c->exchange_user = nullptr; return OG_OK; }
+    if (rank < 0 || rank >= world) { set_error("og_set_exchange: rank %d of %d", rank, world); return OG_ERR_INVALID; }
+    c->shard_rank = rank; c->shard_world = world; c->exchange = fn; c->exchange_user = user;
+    return OG_OK;
+}
 extern "C" int og_selftest_logf(og_ctx* c, const float* x, int n, float* out)
 {
     OG_BIND(c);

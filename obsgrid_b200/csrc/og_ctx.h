@@ -50,6 +50,10 @@ struct og_ctx {
     };
     Slot slots[OG_SLOTS];
     og_stats stats{};
+    // a slab over several GPUs (og_set_exchange): the buddy check's cells are dealt cell % world
+    int shard_rank = 0, shard_world = 1;
+    og_exchange_fn exchange = nullptr;
+    void* exchange_user = nullptr;
     int counting = 0;
     int arithmetic = OG_ARITH_EXACT;            // og_set_arithmetic
     unsigned long long* d_counters = nullptr;   // [0] updates, [1] candidates
@@ -182,8 +186,10 @@ struct BinLists {
 };
 // box: device, one 1-based inclusive {i0,i1,j0,j1} per ob (i0>i1 = not binned).  Synchronises
 // the stream once (the list size comes back to the host to size the lists).
+// own_rank / own_world: build the lists of the cells with (cell index within the slab) % own_world ==
+// own_rank only (the other cells get empty lists); 0 / 1: every cell.
 int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, const short4* d_box,
-              bool sorted, BinLists* out);
+              bool sorted, BinLists* out, int own_rank = 0, int own_world = 1);
 
 // ---- density / distance (og_density.cu) -------------------------------------------------
 int ob_density_device(og_ctx* ctx, const float* d_x, const float* d_y, float grid_dist, int n,

@@ -70,6 +70,7 @@ struct QcDev {
     const int* home_count; const int* home_start; const int* home_list;      // targets of a cell
     const int* range_count; const int* range_start; const int* range_list;  // its candidates
     unsigned long long* pairs_examined;
+    int sharded;         // og_set_exchange: only the obs of this rank's cells have cnt / kob / err
     // diagnostics (nullable)
     float* d_aob; float* d_err_max; float* d_thr_max; float* d_err_buddy; float* d_difmax;
     int* d_bnf;
@@ -316,7 +317,16 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass2_kernel(QcDev A)
     A.err[gi] = err;
     const unsigned char m = (bnf == 2) ? 1 : 0;
     A.mod_out[gi] = m;
-    if (m != A.mod_in[gi]) *A.changed = 1;
+    if (!A.sharded && m != A.mod_in[gi]) *A.changed = 1;
+}
+
+// Sharded run: "did the relaxation mask move" over the combined mask, identically on every rank.
+__global__ void __launch_bounds__(256) mask_moved_kernel(const unsigned char* __restrict__ a,
+                                                         const unsigned char* __restrict__ b, int n, int* changed)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool d = (i < n) && (a[i] != b[i]);
+    if (__ballot_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) *changed = 1;
 }
 
 // Flags: error_max (2**16), no_buddies (2**14), buddy (2**17), in the reference's order.
@@ -328,7 +338,7 @@ __global__ void __launch_bounds__(256) qc_flag_kernel(QcDev A)
     const int gi = S.ob_off + li;
     int q = A.qc[gi];
     if (A.do_error_max && A.emax_fail[gi]) q = qc_add_flag(q, OG_FAILS_ERROR_MAX);
-    if (A.do_buddy) {
+    if (A.do_buddy && !(A.sharded && A.kob[gi] == -1)) {   // -1: another rank's observation
         const int cnt = A.cnt[gi], bnf = A.kob[gi];
         const float err = A.err[gi];
         float dm = A.q4[gi].w;
@@ -513,6 +523,14 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         OG_TRY(ctx->reserve_t("qc.range_box", tot, &A.range_box));
     }
     A.pairs_examined = ctx->d_counters + 3;
+    const bool sharded = ctx->shard_world > 1 && ctx->exchange && b.do_buddy;
+    A.sharded = sharded ? 1 : 0;
+    auto exchange = [&](void* p, size_t n, int dtype, int op) -> int {
+        if (ctx->exchange(ctx->exchange_user, p, n, dtype, op, (void*)st) != 0) {
+            set_error("exchange callback failed"); return OG_ERR_CUDA;
+        }
+        return OG_OK;
+    };
     A.d_aob = b.aob; A.d_err_max = b.err_max; A.d_thr_max = b.thr_max;
     A.d_err_buddy = b.err_buddy; A.d_difmax = b.difmax; A.d_bnf = b.buddy_num_final;
 
@@ -523,8 +541,11 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         // targets of a cell: the obs sitting in it (any order); candidates: the obs within reach
         // of it, in ascending index -- the order the reference sums in
         BinLists home, range;
-        OG_TRY(bin_build(ctx, "qc.home", bslabs, A.home_box, false, &home));
-        OG_TRY(bin_build(ctx, "qc.range", bslabs, A.range_box, true, &range));
+        // sharded: this rank's cells only, so the targets (and their candidate lists) are dealt out
+        const int orank = sharded ? ctx->shard_rank : 0, oworld = sharded ? ctx->shard_world : 1;
+        OG_TRY(bin_build(ctx, "qc.home", bslabs, A.home_box, false, &home, orank, oworld));
+        OG_TRY(bin_build(ctx, "qc.range", bslabs, A.range_box, true, &range, orank, oworld));
+        if (sharded) OG_CUDA(cudaMemsetAsync(A.kob, 0xff, tot * sizeof(int), st));
         A.home_count = home.cell_count; A.home_start = home.cell_start; A.home_list = home.cell_list;
         A.range_count = range.cell_count; A.range_start = range.cell_start; A.range_list = range.cell_list;
         OG_TRY(ctx->reserve_t("qc.susp_list", (size_t)std::max(range.list_total, 1), &A.susp_list));
@@ -545,8 +566,14 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         int iters = 0;
         for (;;) {
             OG_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
+            if (sharded) OG_CUDA(cudaMemsetAsync(A.mod_out, 0, tot, st));
             buddy_pass2_kernel<<<(unsigned)max_items, BP_THREADS, 0, st>>>(A);
             ctx->count_launch();
+            if (sharded) {   // qc2_module.F90:327's mask of every observation, whoever owns it
+                OG_TRY(exchange(A.mod_out, tot, OG_XCHG_UINT8, OG_XCHG_MAX));
+                mask_moved_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(A.mod_in, A.mod_out, (int)tot, A.changed);
+                ctx->count_launch();
+            }
             void* h_changed = nullptr;
             OG_TRY(ctx->get_small(ctx->d_flag, sizeof(int), &h_changed));
             OG_CUDA(cudaStreamSynchronize(st));
@@ -561,6 +588,8 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     }
     qc_flag_kernel<<<nblk_ob, 256, 0, st>>>(A);
     ctx->count_launch();
+    // every rank started from the same flags and only the owner of an observation added buddy bits
+    if (sharded) OG_TRY(exchange(b.qc, tot, OG_XCHG_INT32, OG_XCHG_MAX));
     OG_CUDA(cudaGetLastError());
     return OG_OK;
 }

@@ -296,3 +296,51 @@ def run_time_sharded_slabs(case, rank: int, world: int, proc_qc: Callable, proc_
                 dist.recv(t, src=owner)
                 a[...] = t.cpu().numpy()
     return plan
+
+
+# ---- inside one slab: the buddy check's cells over the ranks ---------------------------------
+# The buddy check of a dense surface network (cfg4: 2 M reports, ~27 of the 38 ms of its time
+# period) is one slab, so level / variable sharding cannot cut it.  The library deals its cells to
+# the ranks and combines the relaxation mask of every fix-point pass and the final flags through an
+# exchange callback (include/obsgrid_gpu.h: og_set_exchange); this is that callback over
+# torch.distributed.  The all-reduce is queued on the library's stream, so the call stays
+# stream-ordered: nothing synchronises with the host here.
+class _RawBuffer:
+    """A device (or host) buffer the library hands to the callback, as something torch can wrap."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def make_exchange(dist, torch, device=None, group=None, counter=None):
+    """An og_exchange_fn (ctypes callback object; keep it referenced while the context uses it).
+
+    device None: the buffers are host memory (the CPU tests drive the callback directly with
+    numpy buffers over gloo); otherwise a torch cuda device, the buffers are device pointers.
+    counter: optional dict, gets 'calls' and 'bytes' incremented (bench.py reports them)."""
+    import ctypes as C
+
+    from ._capi import OG_EXCHANGE_FN, OG_XCHG_MAX, OG_XCHG_UINT8
+
+    def fn(_user, buf, count, dtype, op, stream):
+        try:
+            tdt, npdt, ts, size = ((torch.uint8, np.uint8, "|u1", 1) if dtype == OG_XCHG_UINT8
+                                   else (torch.int32, np.int32, "<i4", 4))
+            rop = dist.ReduceOp.MAX if op == OG_XCHG_MAX else dist.ReduceOp.SUM
+            if counter is not None:
+                counter["calls"] = counter.get("calls", 0) + 1
+                counter["bytes"] = counter.get("bytes", 0) + count * size
+            if device is None:
+                a = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_uint8 if size == 1 else C.c_int32)), shape=(count,))
+                dist.all_reduce(torch.from_numpy(a), op=rop, group=group)
+                return 0
+            t = torch.as_tensor(_RawBuffer(buf, count, ts), device=device)
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream or 0, device=device)):
+                dist.all_reduce(t, op=rop, group=group)
+            return 0
+        except Exception as e:          # an exception must not unwind through the C frames
+            import sys
+            print(f"obsgrid_b200.shard exchange failed: {e!r}", file=sys.stderr)
+            return 1
+
+    return OG_EXCHANGE_FN(fn)

@@ -894,3 +894,116 @@ def test_context_on_another_device_from_a_fresh_thread(oracle):
     for nm in ("qc_u", "qc_v", "qc_t", "qc_slp"):
         assert np.all((getattr(got, nm) & getattr(ref, nm)) == getattr(ref, nm)), nm
     assert np.any(got.t != base.t)
+
+
+class _ThreadRanks:
+    """`world` contexts on one GPU standing in for `world` ranks: the exchange callback combines the
+    buffers of the threads through host memory (barrier, reduce, barrier)."""
+
+    def __init__(self, world):
+        import threading
+        import torch
+        from obsgrid_b200 import _capi
+        self.torch, self.capi, self.world = torch, _capi, world
+        self.barrier = threading.Barrier(world)
+        self.stage = [None] * world
+        self.calls = [0] * world
+
+    def callback(self, rank):
+        torch, capi = self.torch, self.capi
+        from obsgrid_b200.shard import _RawBuffer
+
+        def fn(_user, buf, count, dtype, op, stream):
+            try:
+                ts = "|u1" if dtype == capi.OG_XCHG_UINT8 else "<i4"
+                t = torch.as_tensor(_RawBuffer(buf, count, ts), device="cuda:0")
+                s = torch.cuda.ExternalStream(stream, device="cuda:0")
+                with torch.cuda.stream(s):
+                    self.stage[rank] = t.cpu()
+                s.synchronize()
+                self.barrier.wait(timeout=60)
+                stack = torch.stack(self.stage)
+                red = stack.max(dim=0).values if op == capi.OG_XCHG_MAX else stack.sum(dim=0).to(t.dtype)
+                self.barrier.wait(timeout=60)
+                with torch.cuda.stream(s):
+                    t.copy_(red.to("cuda:0"))
+                s.synchronize()
+                self.calls[rank] += 1
+                return 0
+            except BaseException as e:   # noqa: BLE001
+                print("exchange failed", repr(e))
+                self.barrier.abort()
+                return 1
+        return capi.OG_EXCHANGE_FN(fn)
+
+    def run(self, work):
+        """work(ctx, rank) -> result, one thread per rank; returns the results."""
+        import threading
+        from obsgrid_b200.api import Context
+        out, err = [None] * self.world, []
+
+        def body(r):
+            try:
+                c = Context(0)
+                c.set_exchange(r, self.world, self.callback(r))
+                out[r] = work(c, r)
+                c.sync()
+                c.close()
+            except BaseException as e:   # noqa: BLE001
+                err.append(e)
+                self.barrier.abort()
+        th = [threading.Thread(target=body, args=(r,)) for r in range(self.world)]
+        [t.start() for t in th]; [t.join() for t in th]
+        assert not err, err
+        return out
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_buddy_cells_dealt_to_ranks_equal_one_gpu(ctx, oracle, world):
+    """og_set_exchange: the buddy check of ONE slab with its cells dealt to `world` ranks (threads on
+    one GPU here; tests/test_shard_gpu.py runs real ranks over NCCL).  A sparse network that needs
+    several passes of the relaxation fix-point: every rank must end with the flags of the
+    single-GPU run -- which are the oracle's."""
+    rng = np.random.default_rng(8)
+    iew, jns, n = 400, 400, 1500
+    g = np.zeros((jns, iew), np.float32)
+    x, y = rng_obs(rng, n, iew, jns)
+    ob = rng.normal(0, 6, n).astype(np.float32)
+    ob[rng.random(n) < 0.3] += 11.0
+    z = np.zeros(n, np.float32)
+    q0 = (rng.integers(0, 2, n) * (1 << 13)).astype(np.int32)
+    args = (ob, x, y, q0, z, g, 5, 500.0, 30.0, 1.0, 8.0)
+    a = oracle.buddy_check(*args)
+    one = ctx.buddy_check(*args)
+    np.testing.assert_array_equal(a[0], one[0])
+    ranks = _ThreadRanks(world)
+    got = ranks.run(lambda c, r: (c.buddy_check(*args), c.stats()))
+    for r in range(world):
+        np.testing.assert_array_equal(got[r][0][0], a[0], err_msg=f"rank {r}")
+        assert got[r][1]["buddy_fixpoint_iters"] >= 2
+    # the pair work was dealt out, not replicated
+    pe = [got[r][1]["buddy_pairs_examined"] for r in range(world)]
+    assert sum(pe) == ctx_pairs(ctx, args) and max(pe) < sum(pe)
+    assert all(c >= 3 for c in ranks.calls)        # a mask exchange per pass + the flags
+
+
+def ctx_pairs(ctx, args):
+    ctx.reset_stats()
+    ctx.buddy_check(*args)
+    return ctx.stats()["buddy_pairs_examined"]
+
+
+def test_time_with_buddy_cells_dealt_to_ranks(ctx):
+    """The batched time path under og_set_exchange: every (level, variable) slab's buddy check is cut
+    over the ranks; flags and analysed fields on every rank equal the single-GPU run bit for bit."""
+    base = synth.small_case(iew=60, jns=50, kbu=5, n_sfc=900, n_snd=150, seed=4, radii=(6, 3))
+    ref = base.copy()
+    ctx.proc_qc_oa(ref)
+
+    def work(c, r):
+        got = base.copy()
+        c.proc_qc_oa(got)
+        return got
+    for r, got in enumerate(_ThreadRanks(2).run(work)):
+        for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
+            np.testing.assert_array_equal(getattr(got, nm), getattr(ref, nm), err_msg=f"rank {r} {nm}")

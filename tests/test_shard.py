@@ -216,3 +216,40 @@ def test_allreduce_or_bit_planes_equal_bitwise_or():
     t = torch.from_numpy(a.copy())
     shard.allreduce_or(Stub(torch.from_numpy(b)), t)
     np.testing.assert_array_equal(t.numpy(), a | b)
+
+
+def _worker_exchange(rank, world, port, tmp):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from obsgrid_b200 import _capi
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    counter = {}
+    fn = shard.make_exchange(dist, torch, device=None, counter=counter)
+    mask = np.zeros(1000, np.uint8); mask[rank::3] = 1
+    flags = np.full(1000, 1 << 13, np.int32); flags[rank::2] += 1 << 17
+    rc1 = fn(None, mask.ctypes.data, mask.size, _capi.OG_XCHG_UINT8, _capi.OG_XCHG_MAX, None)
+    rc2 = fn(None, flags.ctypes.data, flags.size, _capi.OG_XCHG_INT32, _capi.OG_XCHG_MAX, None)
+    np.savez(f"{tmp}.{rank}.npz", mask=mask, flags=flags, rc=np.array([rc1, rc2]), calls=counter["calls"], nbytes=counter["bytes"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_exchange_callback_over_gloo(tmp_path):
+    """The og_exchange_fn of shard.make_exchange, driven the way the library drives it (raw pointer,
+    count, dtype, op), on host buffers over gloo: in-place MAX over two ranks."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "xchg")
+    mp.spawn(_worker_exchange, args=(2, _free_port(), out), nprocs=2, join=True)
+    want_mask = np.zeros(1000, np.uint8); want_mask[0::3] = 1; want_mask[1::3] = 1
+    want_flags = np.full(1000, (1 << 13) + (1 << 17), np.int32)
+    for r in range(2):
+        got = np.load(f"{out}.{r}.npz")
+        assert list(got["rc"]) == [0, 0]
+        assert np.array_equal(got["mask"], want_mask) and np.array_equal(got["flags"], want_flags)
+        assert int(got["calls"]) == 2 and int(got["nbytes"]) == 1000 + 4000
