@@ -304,51 +304,118 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
         ctx.dev_qc_consistency(d, 0, 1)
         ctx.dev_proc_oa_items(d, case.oa_params, oa_lev, oa_msk)
 
+    # second cut: QC of EVERY slab on every rank with the buddy check's cells dealt to the ranks
+    # (og_set_exchange; every rank ends with every flag, no OR step), OA slabs dealt by OA cost alone
+    plan_c = shard.plan_slabs(case, world, oa_only=True)[rank]
+    sfc_c = plan_c["sfc_mask"] & 0x1f
+    oa_lev_c = ([0] if sfc_c else []) + list(range(plan_c["k0"], plan_c["k1"]))
+    oa_msk_c = ([sfc_c] if sfc_c else []) + [0] * (plan_c["k1"] - plan_c["k0"])
+    xcount = {}
+    xfn = shard.make_exchange(dist, torch, dev, counter=xcount)
+
+    def step_cells():
+        ctx.dev_proc_qc(d, case.qc_params, 0, case.kbu, True)
+        if oa_lev_c:
+            ctx.dev_proc_oa_items(d, case.oa_params, oa_lev_c, oa_msk_c)
+
+    # third cut: only the surface level -- every report, the one level worth more than a rank's share --
+    # has its QC cut inside the slabs; upper levels stay whole (QC + OA) on one rank each, so the
+    # O(N) work of their QC (selection, transposes, lists) is not replicated
+    plan_h = shard.plan_slabs(case, world, sfc_qc_shared=True)[rank]
+    sfc_h = plan_h["sfc_mask"] & 0x1f
+    up_h = list(range(plan_h["k0"], plan_h["k1"]))
+    oa_lev_h = ([0] if sfc_h else []) + up_h
+    oa_msk_h = ([sfc_h] if sfc_h else []) + [0] * len(up_h)
+    ev_h = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step_hybrid():
+        ev_h[0].record(lib_stream)
+        ctx.set_exchange(rank, world, xfn)
+        ctx.dev_proc_qc_items(d, case.qc_params, [0], [0], True)
+        ctx.set_exchange(0, 1, None)
+        ev_h[1].record(lib_stream)
+        if up_h:
+            ctx.dev_proc_qc_items(d, case.qc_params, up_h, [0] * len(up_h), True)
+        ev_h[2].record(lib_stream)
+        if oa_lev_h:
+            ctx.dev_proc_oa_items(d, case.oa_params, oa_lev_h, oa_msk_h)
+        ev_h[3].record(lib_stream)
+
     def step_alone():
         ctx.dev_proc_qc(d, case.qc_params, 0, case.kbu, True)
         ctx.dev_proc_oa(d, case.oa_params, 0, case.kbu)
 
-    def timed(step, n):
+    phases_h = [0.0, 0.0, 0.0]
+
+    def timed(step, n, collective=True):
         tot, xch = 0.0, 0.0
         for _ in range(n):
             restore()
-            dist.barrier()
+            if collective:
+                dist.barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(lib_stream); step(); b.record(lib_stream)
             ctx.sync()
             tot += a.elapsed_time(b)
             if step is step_sharded:
                 xch += ev_x[0].elapsed_time(ev_x[1])
+            if step is step_hybrid:
+                for i_ in range(3):
+                    phases_h[i_] += ev_h[i_].elapsed_time(ev_h[i_ + 1]) / n
         return tot / n, xch / n
 
     n = max(2, min(args.steps, 3))
     for _ in range(2):
         restore(); step_sharded(); ctx.sync()
     ms_n, ms_x = timed(step_sharded, n)
-    v = torch.tensor([ms_n, ms_x], device=dev, dtype=torch.float64)
+    ctx.set_exchange(rank, world, xfn)
+    for _ in range(2):
+        restore(); step_cells(); ctx.sync()
+    xcount.clear()
+    ms_c, _ = timed(step_cells, n)
+    ctx.set_exchange(0, 1, None)
+    xcells = dict(xcount)
+    for _ in range(2):
+        restore(); step_hybrid(); ctx.sync()
+    xcount.clear()
+    ms_h, _ = timed(step_hybrid, n)
+    v = torch.tensor([ms_n, ms_x, ms_c, ms_h], device=dev, dtype=torch.float64)
     dist.all_reduce(v, op=dist.ReduceOp.MAX)
-    ms_n, ms_x = float(v[0]), float(v[1])
+    ms_n, ms_x, ms_c, ms_h = float(v[0]), float(v[1]), float(v[2]), float(v[3])
+    ph = torch.tensor(phases_h, device=dev, dtype=torch.float64)
+    ph_all = [torch.zeros_like(ph) for _ in range(world)]
+    dist.all_gather(ph_all, ph)
+    ph_all = [[round(float(x), 3) for x in t_] for t_ in ph_all]
     ms_1 = 0.0
     if rank == 0:
         for _ in range(2):
             restore(); step_alone(); ctx.sync()
-        tot = 0.0
-        for _ in range(n):
-            restore()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(lib_stream); step_alone(); b.record(lib_stream)
-            ctx.sync()
-            tot += a.elapsed_time(b)
-        ms_1 = tot / n
+        ms_1, _ = timed(step_alone, n, collective=False)
     dist.barrier()
     del work, pristine
     torch.cuda.empty_cache()
-    return {"workload": case.label, "n_gpus": world, "ms_per_time": ms_n, "ms_per_time_1gpu": ms_1,
-            "speedup": (ms_1 / ms_n) if ms_n > 0 else None,
-            "efficiency": (ms_1 / (world * ms_n)) if ms_n > 0 else None,
-            "or_exchange_ms": ms_x, "steps": n,
-            "parallelism": "(level, variable) slabs of one analysis time dealt to the ranks by cost; surface flag rows "
-                           "OR-combined by one NCCL all-reduce between QC and OA"}
+    best = min(ms_n, ms_c, ms_h)
+    return {"workload": case.label, "n_gpus": world, "ms_per_time": best, "ms_per_time_1gpu": ms_1,
+            "speedup": (ms_1 / best) if best > 0 else None,
+            "efficiency": (ms_1 / (world * best)) if best > 0 else None,
+            "steps": n,
+            "cuts": {
+                "slabs": {"ms_per_time": ms_n, "or_exchange_ms": ms_x,
+                          "what": "(level, variable) slabs of one analysis time dealt to the ranks by cost; surface "
+                                  "flag rows OR-combined by one NCCL all-reduce between QC and OA"},
+                "cells": {"ms_per_time": ms_c, "exchanges_per_time": xcells.get("calls", 0) / n,
+                          "exchange_bytes_per_time": xcells.get("bytes", 0) / n,
+                          "what": "QC of every slab on every rank with the buddy check's cells dealt to the ranks "
+                                  "(og_set_exchange: relaxation mask per fix-point pass and the flags combined by NCCL "
+                                  "all-reduce MAX on the library's stream); OA slabs dealt by OA cost"},
+                "surface_cells": {"ms_per_time": ms_h, "exchanges_per_time": xcount.get("calls", 0) / n,
+                                  "exchange_bytes_per_time": xcount.get("bytes", 0) / n,
+                                  "phase_ms_per_rank": {"qc_surface_shared": [p_[0] for p_ in ph_all],
+                                                        "qc_upper_levels": [p_[1] for p_ in ph_all],
+                                                        "oa": [p_[2] for p_ in ph_all]},
+                                  "what": "surface level: QC of its slabs on every rank with the buddy check's cells dealt "
+                                          "to the ranks, OA slabs dealt by OA cost; upper levels whole (QC + OA) on one "
+                                          "rank each"}}}
 
 
 def run_gpu(args, rank: int, world: int, local_rank: int):

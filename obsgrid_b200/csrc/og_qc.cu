@@ -485,9 +485,14 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         d.reach = (d.t_hi >= 0.f) ? std::min(sqrtf(d.t_hi) * 1.0001f + 0.01f, reach_max) : 0.f;
         // cells one reach wide (9 cells per ob) where stations are sparse, half a reach wide
         // (25 cells per ob, a third fewer pair tests) where a half-reach cell still fills a warp
-        const float dens = (float)h.n / ((float)b.iew * (float)b.jns);
-        const float edge = (dens * 0.25f * d.reach * d.reach >= 32.f) ? 0.5f * d.reach : d.reach;
-        const int cell = std::max(8, (int)ceilf(edge));
+        // cells one reach wide (9 cells per ob) where stations are sparse, half a reach wide (25 cells
+        // per ob, a third fewer pair tests) where a half-reach cell still fills a warp.  Finer cells do
+        // not pay: a third / a quarter of a reach examine 11 % / 16 % fewer pairs (cfg4: pass 1 26.6 ->
+        // 24.9 ms) but the index-ordered lists grow 2x / 3.2x (QC stage 30.5 -> 31.2 / 34.3 ms;
+        // profiles/exp/celldiv.sh)
+        const float per_reach2 = (float)h.n / ((float)b.iew * (float)b.jns) * d.reach * d.reach;
+        const int div = (per_reach2 / 4.f >= 32.f) ? 2 : 1;
+        const int cell = std::max(8, (int)ceilf(d.reach / (float)div));
         d.ncx = (b.iew + cell - 1) / cell; d.ncy = (b.jns + cell - 1) / cell;
         d.cell_off = ncells_all;
         d.blk_off = nblk_ob;

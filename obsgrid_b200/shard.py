@@ -32,10 +32,11 @@ PAIR_PER_UPDATE = 0.12
 LEVEL_FIXED_UPDATES = 1.2e7
 
 
-def level_costs(case) -> np.ndarray:
+def level_costs(case, oa_only: bool = False) -> np.ndarray:
     """Relative cost of each level, in units of one Cressman update: obs x Cressman reach, plus
     the pairs the binned buddy check examines (candidates within a 3 x 3 block of range-wide
-    cells), plus the per-level fixed work."""
+    cells), plus the per-level fixed work.  oa_only: without the buddy pairs (the plan of the OA
+    phase when the QC phase is cut inside the slabs, og_set_exchange)."""
     radii = [int(r) for r in case.oa_params.radius_influence if r >= 0]
     r2 = float(sum(r * r for r in radii)) or 1.0
     cost = np.zeros(case.kbu, np.float64)
@@ -51,7 +52,7 @@ def level_costs(case) -> np.ndarray:
         rc = rng_km / float(case.dx_km)
         per_var = n / 4.0
         pairs = 4.0 * per_var * per_var * min(9.0 * rc * rc / area, 1.0)
-        cost[k] = n * np.pi * r2 + PAIR_PER_UPDATE * pairs + LEVEL_FIXED_UPDATES
+        cost[k] = n * np.pi * r2 + (0.0 if oa_only else PAIR_PER_UPDATE * pairs) + LEVEL_FIXED_UPDATES
     return cost
 
 
@@ -187,7 +188,7 @@ def allreduce_or(dist, t):
     return t
 
 
-def surface_unit_costs(case) -> list[float]:
+def surface_unit_costs(case, oa_only: bool = False) -> list[float]:
     """Cost of each surface unit of SFC_VARS, same unit as level_costs."""
     radii = [int(r) for r in case.oa_params.radius_influence if r >= 0]
     r2 = float(sum(r * r for r in radii)) or 1.0
@@ -204,11 +205,14 @@ def surface_unit_costs(case) -> list[float]:
         pairs = n * n * min(9.0 * rc * rc / area, 1.0)
         shape = ANISO_COST if nm in ("u", "v", "rh") else 1.0
         oa = 0.0 if nm == "dew" else n * np.pi * r2 * shape
-        out.append(oa + PAIR_PER_UPDATE * pairs + LEVEL_FIXED_UPDATES / 6.0)
+        if oa_only:
+            out.append(0.0 if nm == "dew" else oa + LEVEL_FIXED_UPDATES / 6.0)
+        else:
+            out.append(oa + PAIR_PER_UPDATE * pairs + LEVEL_FIXED_UPDATES / 6.0)
     return out
 
 
-def plan_slabs(case, world: int) -> list[dict]:
+def plan_slabs(case, world: int, oa_only: bool = False, sfc_qc_shared: bool = False) -> list[dict]:
     """One entry per rank: {'sfc_mask': variable bits (bit v-1 of variable v; bit 6 = DEWPOINT, QC
     only) of the surface slabs it owns (0: none), 'k0', 'k1': its contiguous range of upper
     levels (k0 >= 1)}."""
@@ -216,10 +220,12 @@ def plan_slabs(case, world: int) -> list[dict]:
     K = case.kbu
     if world == 1:
         return [{"sfc_mask": sum(b for _, b in SFC_VARS), "k0": 1, "k1": K}]
-    up = level_costs(case)[1:]
+    up = level_costs(case, oa_only)[1:]
     loads = [0.0] * world
     masks = [0] * world
-    units = sorted(zip(surface_unit_costs(case), (b for _, b in SFC_VARS)), reverse=True)
+    # sfc_qc_shared: the surface level's QC is cut inside its slabs over all ranks (og_set_exchange),
+    # an equal share for everyone -- only its OA slabs are dealt here; upper levels keep QC + OA
+    units = sorted(zip(surface_unit_costs(case, oa_only or sfc_qc_shared), (b for _, b in SFC_VARS)), reverse=True)
     for cost, bits in units:                        # longest processing time first
         r = int(np.argmin(loads))
         loads[r] += cost
