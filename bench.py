@@ -321,9 +321,37 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
     # third cut: only the surface level -- every report, the one level worth more than a rank's share --
     # has its QC cut inside the slabs; upper levels stay whole (QC + OA) on one rank each, so the
     # O(N) work of their QC (selection, transposes, lists) is not replicated
-    plan_h = shard.plan_slabs(case, world, sfc_qc_shared=True)[rank]
+    # The units are dealt on MEASURED costs -- what a run over many analysis times has from the
+    # previous time (the network hardly changes from one time to the next); here a calibration pass,
+    # the units spread over the ranks, each timed alone on its GPU.
+    def unit_ms(fn):
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn(); ctx.sync()
+        a_.record(lib_stream); fn(); b_.record(lib_stream); ctx.sync()
+        return a_.elapsed_time(b_)
+
+    sfc_bits = [b_ for _, b_ in shard.SFC_VARS if b_ & 0x1f]
+    unit_list = [("s", b_) for b_ in sfc_bits] + [("k", k_) for k_ in range(1, case.kbu)]
+    costs = torch.zeros(len(unit_list), device=dev, dtype=torch.float64)
+    restore()
+    mine_u = [i_ for i_ in range(len(unit_list)) if i_ % world == rank]
+    if any(unit_list[i_][0] == "s" for i_ in mine_u):
+        ctx.dev_proc_qc_items(d, case.qc_params, [0], [0], True)     # surface OA runs on checked flags
+    for i_ in mine_u:
+        kind, ident = unit_list[i_]
+        if kind == "s":
+            costs[i_] = unit_ms(lambda: ctx.dev_proc_oa_items(d, case.oa_params, [0], [ident]))
+        else:
+            def lev(k_=ident):
+                ctx.dev_proc_qc_items(d, case.qc_params, [k_], [0], True)
+                ctx.dev_proc_oa_items(d, case.oa_params, [k_], [0])
+            costs[i_] = unit_ms(lev)
+    dist.all_reduce(costs, op=dist.ReduceOp.SUM)
+    costs = [float(c_) for c_ in costs]
+    plans_h = shard.plan_units_measured({b_: costs[i_] for i_, b_ in enumerate(sfc_bits)}, costs[len(sfc_bits):], world)
+    plan_h = plans_h[rank]
     sfc_h = plan_h["sfc_mask"] & 0x1f
-    up_h = list(range(plan_h["k0"], plan_h["k1"]))
+    up_h = plan_h["levels"]
     oa_lev_h = ([0] if sfc_h else []) + up_h
     oa_msk_h = ([sfc_h] if sfc_h else []) + [0] * len(up_h)
     ev_h = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -413,9 +441,11 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
                                   "phase_ms_per_rank": {"qc_surface_shared": [p_[0] for p_ in ph_all],
                                                         "qc_upper_levels": [p_[1] for p_ in ph_all],
                                                         "oa": [p_[2] for p_ in ph_all]},
+                                  "planned_load_ms_per_rank": [round(p_["load"], 3) for p_ in plans_h],
                                   "what": "surface level: QC of its slabs on every rank with the buddy check's cells dealt "
-                                          "to the ranks, OA slabs dealt by OA cost; upper levels whole (QC + OA) on one "
-                                          "rank each"}}}
+                                          "to the ranks, OA slabs dealt out; upper levels whole (QC + OA) on one rank "
+                                          "each; units dealt longest-first on costs measured in a calibration pass (a "
+                                          "production run has them from the previous analysis time)"}}}
 
 
 def run_gpu(args, rank: int, world: int, local_rank: int):

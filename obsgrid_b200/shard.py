@@ -304,6 +304,31 @@ def run_time_sharded_slabs(case, rank: int, world: int, proc_qc: Callable, proc_
     return plan
 
 
+def plan_units_measured(sfc_costs: dict, upper_costs: Sequence[float], world: int) -> list[dict]:
+    """Plan from MEASURED unit costs (milliseconds of the previous analysis time, or of a calibration
+    pass): sfc_costs maps a variable bit of SFC_VARS to the cost of that surface slab's unit,
+    upper_costs[k - 1] is the cost of upper level k.  Longest processing time first; a rank's upper
+    levels need not be contiguous (og_dev_*_time_items take any increasing list).
+    Returns per rank {'sfc_mask', 'levels'}."""
+    world = max(int(world), 1)
+    units = [(float(c), 0, int(b)) for b, c in sfc_costs.items()] + \
+            [(float(c), 1, k + 1) for k, c in enumerate(upper_costs)]
+    units.sort(key=lambda u: (-u[0], u[1], u[2]))
+    loads = [0.0] * world
+    out = [{"sfc_mask": 0, "levels": []} for _ in range(world)]
+    for cost, kind, ident in units:
+        r = min(range(world), key=lambda q: (loads[q], q))
+        loads[r] += cost
+        if kind == 0:
+            out[r]["sfc_mask"] |= ident
+        else:
+            out[r]["levels"].append(ident)
+    for o, l in zip(out, loads):
+        o["levels"].sort()
+        o["load"] = l
+    return out
+
+
 # ---- inside one slab: the buddy check's cells over the ranks ---------------------------------
 # The buddy check of a dense surface network (cfg4: 2 M reports, ~27 of the 38 ms of its time
 # period) is one slab, so level / variable sharding cannot cut it.  The library deals its cells to

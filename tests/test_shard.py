@@ -253,3 +253,20 @@ def test_exchange_callback_over_gloo(tmp_path):
         assert list(got["rc"]) == [0, 0]
         assert np.array_equal(got["mask"], want_mask) and np.array_equal(got["flags"], want_flags)
         assert int(got["calls"]) == 2 and int(got["nbytes"]) == 1000 + 4000
+
+
+def test_plan_units_measured_deals_every_unit_once_and_balances():
+    rng = np.random.default_rng(5)
+    sfc = {b: float(c) for b, c in zip((1, 2, 4, 8, 16), rng.uniform(20, 45, 5))}
+    up = rng.uniform(3, 12, 49)
+    for world in (1, 2, 3, 8):
+        plan = shard.plan_units_measured(sfc, up, world)
+        assert len(plan) == world
+        masks = [p["sfc_mask"] for p in plan]
+        assert sum(masks) == 31 and all(a & b == 0 for i, a in enumerate(masks) for b in masks[i + 1:])
+        levels = sorted(k for p in plan for k in p["levels"])
+        assert levels == list(range(1, 50))
+        assert all(p["levels"] == sorted(p["levels"]) for p in plan)
+        loads = [p["load"] for p in plan]
+        assert abs(sum(loads) - (sum(sfc.values()) + up.sum())) < 1e-9
+        assert max(loads) - min(loads) <= max(max(sfc.values()), up.max())      # the LPT bound
