@@ -342,10 +342,10 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
         if kind == "s":
             costs[i_] = unit_ms(lambda: ctx.dev_proc_oa_items(d, case.oa_params, [0], [ident]))
         else:
-            def lev(k_=ident):
+            def one_level(k_=ident):
                 ctx.dev_proc_qc_items(d, case.qc_params, [k_], [0], True)
                 ctx.dev_proc_oa_items(d, case.oa_params, [k_], [0])
-            costs[i_] = unit_ms(lev)
+            costs[i_] = unit_ms(one_level)
     dist.all_reduce(costs, op=dist.ReduceOp.SUM)
     costs = [float(c_) for c_ in costs]
     plans_h = shard.plan_units_measured({b_: costs[i_] for i_, b_ in enumerate(sfc_bits)}, costs[len(sfc_bits):], world)
@@ -890,7 +890,7 @@ def main():
                     help="weak: one analysis time per rank; strong: one time, levels sharded over the ranks")
     ap.add_argument("--shard", default="slabs", choices=["slabs", "levels"],
                     help="strong scaling: deal out the surface level's variable slabs (slabs) or whole levels only")
-    ap.add_argument("--strong-configs", default="3",
+    ap.add_argument("--strong-configs", default="3,5",
                     help="N > 1: configurations whose single analysis time is also strong-scaled over the ranks "
                          "(the `strong` block of the line); empty string: none")
     ap.add_argument("--fdda-times", type=int, default=5,

@@ -278,6 +278,7 @@ int run_selection(og_ctx* c, const TimeDev& T, std::vector<SelSlab>& sel, bool q
     const int ns = (int)sel.size();
     const int nchunk = (T.nrep + SEL_THREADS - 1) / SEL_THREADS;
     A = SelDev{};
+    if (ns == 0) { n_out.clear(); total = 0; return OG_OK; }   // e.g. upper levels under surface_only
     A.nrep = T.nrep; A.nchunk = nchunk; A.iew = T.iew; A.jns = T.jns;
     A.xob = T.xob; A.yob = T.yob; A.elev = qc_outputs ? T.elev : nullptr; A.lt_rep = lt_rep;
     A.bogus = qc_outputs ? T.bogus : nullptr;

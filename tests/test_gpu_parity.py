@@ -864,6 +864,19 @@ def test_dev_item_lists_equal_the_range_calls(ctx):
         ctx.dev_proc_qc_items(d, base.qc_params, [3, 2], [0, 0])
 
 
+def test_upper_levels_under_surface_only_are_a_no_op(ctx):
+    """proc_oa.F90:365: with fdda_loop > 1 only the surface level is analysed.  A batch that holds
+    upper levels only then has no slab at all -- it must come back clean, fields untouched."""
+    base = synth.small_case(iew=40, jns=36, kbu=4, n_sfc=120, n_snd=30, radii=(5, 3))
+    base.oa_params.surface_only = 1
+    got = base.copy()
+    ctx.proc_oa(got, 1, 4)
+    for nm in ("t", "u", "v", "rh", "slp"):
+        np.testing.assert_array_equal(getattr(got, nm), getattr(base, nm), err_msg=nm)
+    ctx.proc_oa(got, 0, 4)
+    assert np.any(got.t[0] != base.t[0]) and np.array_equal(got.t[1:], base.t[1:])
+
+
 def test_context_on_another_device_from_a_fresh_thread(oracle):
     """A host thread that never touched CUDA has device 0 current; a context on another GPU must
     still work from it (every entry point binds the context's device).  Needs two GPUs."""
