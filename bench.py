@@ -314,7 +314,9 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
     xfn = shard.make_exchange(dist, torch, dev, counter=xcount)
 
     def step_cells():
+        ctx.set_exchange(rank, world, xfn)
         ctx.dev_proc_qc(d, case.qc_params, 0, case.kbu, True)
+        ctx.set_exchange(0, 1, None)          # the OA slabs below differ from rank to rank: no exchange
         if oa_lev_c:
             ctx.dev_proc_oa_items(d, case.oa_params, oa_lev_c, oa_msk_c)
 
@@ -369,11 +371,32 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
             ctx.dev_proc_oa_items(d, case.oa_params, oa_lev_h, oa_msk_h)
         ev_h[3].record(lib_stream)
 
+    # fourth cut: the surface level entirely inside its slabs -- QC as above and the Cressman cells of its
+    # five slabs dealt to the ranks too (the slab summed over the ranks after every scan); upper levels
+    # dealt whole on their measured costs
+    plans_g = shard.plan_units_measured({}, costs[len(sfc_bits):], world)
+    up_g = plans_g[rank]["levels"]
+    ev_g = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def step_surface_inside():
+        ev_g[0].record(lib_stream)
+        ctx.set_exchange(rank, world, xfn)
+        ctx.dev_proc_qc_items(d, case.qc_params, [0], [0], True)
+        ev_g[1].record(lib_stream)
+        ctx.dev_proc_oa_items(d, case.oa_params, [0], [0])
+        ctx.set_exchange(0, 1, None)
+        ev_g[2].record(lib_stream)
+        if up_g:
+            ctx.dev_proc_qc_items(d, case.qc_params, up_g, [0] * len(up_g), True)
+            ctx.dev_proc_oa_items(d, case.oa_params, up_g, [0] * len(up_g))
+        ev_g[3].record(lib_stream)
+
     def step_alone():
         ctx.dev_proc_qc(d, case.qc_params, 0, case.kbu, True)
         ctx.dev_proc_oa(d, case.oa_params, 0, case.kbu)
 
     phases_h = [0.0, 0.0, 0.0]
+    phases_g = [0.0, 0.0, 0.0]
 
     def timed(step, n, collective=True):
         tot, xch = 0.0, 0.0
@@ -390,30 +413,40 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
             if step is step_hybrid:
                 for i_ in range(3):
                     phases_h[i_] += ev_h[i_].elapsed_time(ev_h[i_ + 1]) / n
+            if step is step_surface_inside:
+                for i_ in range(3):
+                    phases_g[i_] += ev_g[i_].elapsed_time(ev_g[i_ + 1]) / n
         return tot / n, xch / n
 
     n = max(2, min(args.steps, 3))
     for _ in range(2):
         restore(); step_sharded(); ctx.sync()
     ms_n, ms_x = timed(step_sharded, n)
-    ctx.set_exchange(rank, world, xfn)
     for _ in range(2):
         restore(); step_cells(); ctx.sync()
     xcount.clear()
     ms_c, _ = timed(step_cells, n)
-    ctx.set_exchange(0, 1, None)
     xcells = dict(xcount)
     for _ in range(2):
         restore(); step_hybrid(); ctx.sync()
     xcount.clear()
     ms_h, _ = timed(step_hybrid, n)
-    v = torch.tensor([ms_n, ms_x, ms_c, ms_h], device=dev, dtype=torch.float64)
+    xhyb = dict(xcount)
+    for _ in range(2):
+        restore(); step_surface_inside(); ctx.sync()
+    xcount.clear()
+    ms_g, _ = timed(step_surface_inside, n)
+    v = torch.tensor([ms_n, ms_x, ms_c, ms_h, ms_g], device=dev, dtype=torch.float64)
     dist.all_reduce(v, op=dist.ReduceOp.MAX)
-    ms_n, ms_x, ms_c, ms_h = float(v[0]), float(v[1]), float(v[2]), float(v[3])
-    ph = torch.tensor(phases_h, device=dev, dtype=torch.float64)
-    ph_all = [torch.zeros_like(ph) for _ in range(world)]
-    dist.all_gather(ph_all, ph)
-    ph_all = [[round(float(x), 3) for x in t_] for t_ in ph_all]
+    ms_n, ms_x, ms_c, ms_h, ms_g = (float(x_) for x_ in v)
+
+    def per_rank(vals):
+        t_ = torch.tensor(vals, device=dev, dtype=torch.float64)
+        all_ = [torch.zeros_like(t_) for _ in range(world)]
+        dist.all_gather(all_, t_)
+        return [[round(float(x), 3) for x in q_] for q_ in all_]
+    ph_all = per_rank(phases_h)
+    pg_all = per_rank(phases_g)
     ms_1 = 0.0
     if rank == 0:
         for _ in range(2):
@@ -422,7 +455,7 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
     dist.barrier()
     del work, pristine
     torch.cuda.empty_cache()
-    best = min(ms_n, ms_c, ms_h)
+    best = min(ms_n, ms_c, ms_h, ms_g)
     return {"workload": case.label, "n_gpus": world, "ms_per_time": best, "ms_per_time_1gpu": ms_1,
             "speedup": (ms_1 / best) if best > 0 else None,
             "efficiency": (ms_1 / (world * best)) if best > 0 else None,
@@ -436,8 +469,16 @@ def strong_block(args, ctx, cfg: int, rank: int, world: int, dist, dev, lib_stre
                           "what": "QC of every slab on every rank with the buddy check's cells dealt to the ranks "
                                   "(og_set_exchange: relaxation mask per fix-point pass and the flags combined by NCCL "
                                   "all-reduce MAX on the library's stream); OA slabs dealt by OA cost"},
-                "surface_cells": {"ms_per_time": ms_h, "exchanges_per_time": xcount.get("calls", 0) / n,
-                                  "exchange_bytes_per_time": xcount.get("bytes", 0) / n,
+                "surface_inside": {"ms_per_time": ms_g, "exchanges_per_time": xcount.get("calls", 0) / n,
+                                   "exchange_bytes_per_time": xcount.get("bytes", 0) / n,
+                                   "phase_ms_per_rank": {"qc_surface_shared": [p_[0] for p_ in pg_all],
+                                                         "oa_surface_shared": [p_[1] for p_ in pg_all],
+                                                         "upper_levels_qc_oa": [p_[2] for p_ in pg_all]},
+                                   "what": "surface level: buddy-check cells AND Cressman cells of its slabs dealt to the "
+                                           "ranks (slab summed over the ranks as int32 after every scan); upper levels "
+                                           "whole on one rank each, dealt on measured costs"},
+                "surface_cells": {"ms_per_time": ms_h, "exchanges_per_time": xhyb.get("calls", 0) / n,
+                                  "exchange_bytes_per_time": xhyb.get("bytes", 0) / n,
                                   "phase_ms_per_rank": {"qc_surface_shared": [p_[0] for p_ in ph_all],
                                                         "qc_upper_levels": [p_[1] for p_ in ph_all],
                                                         "oa": [p_[2] for p_ in ph_all]},

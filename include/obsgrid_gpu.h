@@ -418,7 +418,16 @@ int og_dev_oa_time(og_ctx* ctx, const og_time_desc* d, const og_oa_params* p,
  *   - the relaxation mask of qc2_module.F90:327 is combined after every pass of the fix-point
  *     (exchange, OG_XCHG_MAX on bytes), the flags once at the end (OG_XCHG_MAX on int32: only the
  *     owner of an observation adds bits to the common starting value, so MAX is the bitwise OR).
- * The result on every rank is bit-identical to the single-GPU result.
+ * and og_*oa_time*, og_oa_slab, og_cressman:
+ *   - the 32x32-point cells of every slab are dealt the same way (cell index mod world): a rank
+ *     builds the lists of its own cells and scans them; other cells are written as zero bits, and
+ *     after every scan the slab (or, on the smoothing path, the perturbation) is summed over the
+ *     ranks as int32 (OG_XCHG_SUM: x + 0 + ... + 0 is exact), so that the innovations of the next
+ *     scan (proc_oa.F90:751-763) are interpolated from the complete field on every rank:
+ *     iew * jns * 4 bytes per slab and scan.
+ * The result on every rank is bit-identical to the single-GPU result.  Worth it for the few big
+ * slabs that whole-slab dealing cannot balance (the surface level); a batch of many small slabs is
+ * better dealt slab by slab (one exchange call per slab and scan is issued here).
  *
  * exchange(user, buf, count, dtype, op, stream): all-reduce `count` elements at device pointer `buf`
  * in place over the ranks, ordered on the CUDA stream `stream` (a cudaStream_t); must return 0.

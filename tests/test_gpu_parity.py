@@ -1006,10 +1006,19 @@ def ctx_pairs(ctx, args):
     return ctx.stats()["buddy_pairs_examined"]
 
 
-def test_time_with_buddy_cells_dealt_to_ranks(ctx):
-    """The batched time path under og_set_exchange: every (level, variable) slab's buddy check is cut
-    over the ranks; flags and analysed fields on every rank equal the single-GPU run bit for bit."""
-    base = synth.small_case(iew=60, jns=50, kbu=5, n_sfc=900, n_snd=150, seed=4, radii=(6, 3))
+@pytest.mark.parametrize("world,smooth", [(2, 0), (3, 0), (2, 2)])
+def test_time_with_cells_dealt_to_ranks(ctx, world, smooth):
+    """The batched time path under og_set_exchange: every (level, variable) slab is cut over the ranks
+    -- the buddy check's cells (relaxation mask and flags combined by MAX) and the Cressman cells (the
+    slab summed as int32 after every scan, so that every rank interpolates the next innovations from
+    the complete field); with smoothing the perturbation is what travels.  Flags and analysed fields
+    on every rank equal the single-GPU run bit for bit."""
+    base = synth.small_case(iew=70, jns=50, kbu=5, n_sfc=900, n_snd=150, seed=4, radii=(6, 3))
+    if smooth:
+        p = base.oa_params
+        p.smooth_type = 1
+        p.smooth_sfc_wind = p.smooth_sfc_temp = p.smooth_sfc_rh = p.smooth_sfc_slp = smooth
+        p.smooth_upper_wind = p.smooth_upper_temp = p.smooth_upper_rh = 1
     ref = base.copy()
     ctx.proc_qc_oa(ref)
 
@@ -1017,6 +1026,9 @@ def test_time_with_buddy_cells_dealt_to_ranks(ctx):
         got = base.copy()
         c.proc_qc_oa(got)
         return got
-    for r, got in enumerate(_ThreadRanks(2).run(work)):
+    ranks = _ThreadRanks(world)
+    for r, got in enumerate(ranks.run(work)):
         for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp", "t", "u", "v", "rh", "slp"):
             np.testing.assert_array_equal(getattr(got, nm), getattr(ref, nm), err_msg=f"rank {r} {nm}")
+    assert np.any(ref.t != base.t) and np.any(ref.u != base.u)
+    assert all(c > 4 for c in ranks.calls)
