@@ -887,7 +887,12 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                              f"{NS} time periods in flight" + (", one host thread per context" if n_lanes > 1 else "")),
                      "blocking_call_ms": e2e_blocking_ms,
                      "h2d_bytes_per_step": st_e["h2d_bytes"] / args.steps,
-                     "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps} if do_e2e else None),
+                     "d2h_bytes_per_step": st_e["d2h_bytes"] / args.steps,
+                     # what one rank moved over PCIe, both directions together, while the e2e steps ran; the
+                     # ceiling of the box (profiles/r1/pcie_diag_8gpu.txt): ~49 GB/s per direction for one
+                     # GPU alone, 8-11 GB/s per GPU and direction when all eight move data both ways
+                     "pcie_gbs_per_gpu": (st_e["h2d_bytes"] + st_e["d2h_bytes"]) / args.steps / (e2e_ms * 1e-3) / 1e9}
+                    if do_e2e else None),
             "e2e_per_slab": per_slab,
             "fdda_chain": fdda_line,
             "strong": strong,

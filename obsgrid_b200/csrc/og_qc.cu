@@ -164,11 +164,13 @@ __global__ void __launch_bounds__(256) qc_prep_kernel(QcDev A)
     }
 }
 
-// Work items of the two pair passes: (slab, cell, group of BP_THREADS targets of the cell).
-// Cells differ wildly in weight (targets x candidates grows with the square of the local
-// station density), so the passes run one CTA per item instead of one per cell.
-constexpr int BP_THREADS = 128;
-constexpr int BP_CHUNK = 512;
+// Work items of the two pair passes: (slab, cell, group of 32 targets of the cell), one WARP per item.
+// Cells differ wildly in weight (targets x candidates grows with the square of the local station
+// density): upper-air cells hold a dozen targets, a dense surface network hundreds -- with a warp as
+// the unit neither leaves lanes idle, and the passes need no block barrier.
+constexpr int BP_THREADS = 128;               // four items per CTA
+constexpr int BP_WARPS = BP_THREADS / 32;
+constexpr int BP_CHUNK = 128;                 // candidates staged per warp and round
 __global__ void __launch_bounds__(128) buddy_items_kernel(QcDev A)
 {
     const QcSlabDev& S = A.slabs[blockIdx.y];
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(128) buddy_items_kernel(QcDev A)
     const int c = S.cell_off + lc;
     const int T = A.home_count[c];
     if (T == 0) return;
-    const int G = (T + BP_THREADS - 1) / BP_THREADS;
+    const int G = (T + 31) / 32;
     const int base = atomicAdd(A.n_items, G);
     for (int g = 0; g < G; ++g) A.items[base + g] = make_int4((int)blockIdx.y, c, g, 0);
     atomicAdd(A.pairs_examined, (unsigned long long)T * (unsigned long long)A.range_count[c]);
@@ -185,32 +187,50 @@ __global__ void __launch_bounds__(128) buddy_items_kernel(QcDev A)
 
 // station_loop_2/3, first half (qc2_module.F90:223-256): buddy count and index-ordered sum.
 // Targets: obs sitting in the cell; candidates: the index-ordered list of the obs within
-// reach of the cell.
+// reach of the cell.  The four warps of a CTA take four consecutive items: where they are four
+// target groups of ONE cell (a dense network) the candidates are staged once for the block; where
+// they belong to different cells (upper-air slabs: a dozen targets per cell) every warp stages its
+// own.
 __global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
 {
-    if ((int)blockIdx.x >= *A.n_items) return;
-    const int4 it = A.items[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = (int)blockIdx.x * BP_WARPS + warp;
+    const int n_items = *A.n_items;
+    __shared__ float4 tile_all[BP_WARPS * BP_CHUNK];
+    __shared__ int s_cell[BP_WARPS];
+    const bool live = item < n_items;
+    const int4 it = live ? A.items[item] : make_int4(0, -1, 0, 0);
+    if (lane == 0) s_cell[warp] = it.y;
+    __syncthreads();
+    const bool together = (s_cell[0] >= 0) && (s_cell[0] == s_cell[1]) && (s_cell[1] == s_cell[2]) && (s_cell[2] == s_cell[3]);
+    if (!live && !together) return;
     const QcSlabDev& S = A.slabs[it.x];
-    const int c = it.y, t0 = it.z * BP_THREADS;
+    const int c = it.y, t0 = it.z * 32;
     const int T = A.home_count[c], L = A.range_count[c];
     const int* __restrict__ tl = A.home_list + A.home_start[c];
     const int* __restrict__ cl = A.range_list + A.range_start[c];
     const float tlo = S.t_lo, thi = S.t_hi;
-    __shared__ float4 tile[BP_CHUNK];
-    const bool valid = t0 + (int)threadIdx.x < T;
-    const int gi = S.ob_off + (valid ? tl[t0 + threadIdx.x] : 0);
+    const bool valid = t0 + lane < T;
+    const int gi = S.ob_off + (valid ? tl[t0 + lane] : 0);
     const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
     int cnt = 0;
     float sum = 0.f;
-    const bool warp_on = t0 + (int)(threadIdx.x & ~31u) < T;   // warps without a target only stage
-    for (int base = 0; base < L; base += BP_CHUNK) {
-        const int lim = min(BP_CHUNK, L - base);
+    const float4* tile = together ? tile_all : tile_all + warp * BP_CHUNK;
+    const int chunk = together ? BP_WARPS * BP_CHUNK : BP_CHUNK;
+    for (int base = 0; base < L; base += chunk) {
+        const int lim = min(chunk, L - base);
         const int lim8 = (lim + 7) & ~7;
-        __syncthreads();
-        for (int k = threadIdx.x; k < lim8; k += BP_THREADS)
-            tile[k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
-        __syncthreads();
-        if (!warp_on) continue;
+        if (together) {
+            __syncthreads();
+            for (int k = threadIdx.x; k < lim8; k += BP_THREADS)
+                tile_all[k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
+            __syncthreads();
+        } else {
+            __syncwarp();
+            for (int k = lane; k < lim8; k += 32)
+                tile_all[warp * BP_CHUNK + k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
+            __syncwarp();
+        }
 #pragma unroll 8
         for (int q = 0; q < lim8; ++q) {
             const float4 o = tile[q];
@@ -259,13 +279,15 @@ __global__ void __launch_bounds__(128) suspect_kernel(QcDev A)
 // remove_bad_ob + err (qc2_module.F90:269-327) for one relaxation mask.
 __global__ void __launch_bounds__(BP_THREADS) buddy_pass2_kernel(QcDev A)
 {
-    if ((int)blockIdx.x >= *A.n_items) return;
-    const int4 it = A.items[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = (int)blockIdx.x * BP_WARPS + warp;
+    if (item >= *A.n_items) return;
+    const int4 it = A.items[item];
     const QcSlabDev& S = A.slabs[it.x];
-    const int c = it.y, t0 = it.z * BP_THREADS;
+    const int c = it.y, t0 = it.z * 32;
     const int T = A.home_count[c];
-    const bool valid = t0 + (int)threadIdx.x < T;
-    const int li = valid ? A.home_list[A.home_start[c] + t0 + threadIdx.x] : 0;
+    const bool valid = t0 + lane < T;
+    const int li = valid ? A.home_list[A.home_start[c] + t0 + lane] : 0;
     const int gi = S.ob_off + li;
     const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
     const int cnt = valid ? A.cnt[gi] : 0;
@@ -274,19 +296,21 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass2_kernel(QcDev A)
     const float tlo = S.t_lo, thi = S.t_hi;
     const int ns = A.susp_count[c];
     const int* __restrict__ sl = A.susp_list + A.range_start[c];
-    __shared__ float4 tile[BP_THREADS];
-    __shared__ int tidx[BP_THREADS];   // local index, bit 30 = relaxed
+    __shared__ float4 tile_all[BP_WARPS][32];
+    __shared__ int tidx_all[BP_WARPS][32];   // local index, bit 30 = relaxed
+    float4* tile = tile_all[warp];
+    int* tidx = tidx_all[warp];
     int kob = cnt;
-    for (int base = 0; base < ns; base += BP_THREADS) {
-        const int k = base + threadIdx.x;
-        __syncthreads();
+    for (int base = 0; base < ns; base += 32) {
+        const int k = base + lane;
+        __syncwarp();
         if (k < ns) {
             int lk = sl[k];
-            tile[threadIdx.x] = A.q4[S.ob_off + lk];
-            tidx[threadIdx.x] = lk | (A.mod_in[S.ob_off + lk] ? (1 << 30) : 0);
+            tile[lane] = A.q4[S.ob_off + lk];
+            tidx[lane] = lk | (A.mod_in[S.ob_off + lk] ? (1 << 30) : 0);
         }
-        __syncthreads();
-        const int lim = min(BP_THREADS, ns - base);
+        __syncwarp();
+        const int lim = min(32, ns - base);
         if (cnt >= 2) {
             for (int q = 0; q < lim; ++q) {
                 const float4 o = tile[q];
@@ -555,16 +579,17 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         A.range_count = range.cell_count; A.range_start = range.cell_start; A.range_list = range.cell_list;
         OG_TRY(ctx->reserve_t("qc.susp_list", (size_t)std::max(range.list_total, 1), &A.susp_list));
         OG_TRY(ctx->reserve_t("qc.susp_count", (size_t)ncells_all + 1, &A.susp_count));
-        // one work item per (cell, group of BP_THREADS targets): at most one per non-empty cell
-        // plus one per BP_THREADS obs
-        const size_t max_items = (size_t)ncells_all + (size_t)b.total_obs / BP_THREADS + 1;
+        // one work item per (cell, group of 32 targets): at most one per non-empty cell plus one per
+        // 32 obs; BP_WARPS items per CTA
+        const size_t max_items = (size_t)ncells_all + (size_t)b.total_obs / 32 + 1;
+        const unsigned pair_grid = (unsigned)((max_items + BP_WARPS - 1) / BP_WARPS);
         OG_TRY(ctx->reserve_t("qc.items", max_items, &A.items));
         A.n_items = ctx->d_flag + 2;
         OG_CUDA(cudaMemsetAsync(A.n_items, 0, sizeof(int), st));
         dim3 g_ci((max_cells + 127) / 128, ns);
         buddy_items_kernel<<<g_ci, 128, 0, st>>>(A);
         const int tslot = ctx->timer_begin(1);
-        buddy_pass1_kernel<<<(unsigned)max_items, BP_THREADS, 0, st>>>(A);
+        buddy_pass1_kernel<<<pair_grid, BP_THREADS, 0, st>>>(A);
         ctx->timer_end(tslot);
         suspect_kernel<<<dim3(max_cells, ns), 128, 0, st>>>(A);
         ctx->count_launch(3);
@@ -572,7 +597,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         for (;;) {
             OG_CUDA(cudaMemsetAsync(ctx->d_flag, 0, sizeof(int), st));
             if (sharded) OG_CUDA(cudaMemsetAsync(A.mod_out, 0, tot, st));
-            buddy_pass2_kernel<<<(unsigned)max_items, BP_THREADS, 0, st>>>(A);
+            buddy_pass2_kernel<<<pair_grid, BP_THREADS, 0, st>>>(A);
             ctx->count_launch();
             if (sharded) {   // qc2_module.F90:327's mask of every observation, whoever owns it
                 OG_TRY(exchange(A.mod_out, tot, OG_XCHG_UINT8, OG_XCHG_MAX));
