@@ -655,6 +655,29 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     oa_ms = sum(b.elapsed_time(c) for _, b, c in ev) / args.steps
     step_ms = qc_ms + oa_ms
 
+    # ---- the same steps in the other arithmetic mode of the scan kernels (og_set_arithmetic), so that
+    # ---- one line carries both: 'contracted' keeps the summation order and stays within the
+    # ---- north-star tolerance of the fields (tests/test_gpu_parity.py::test_contracted_*), flags are
+    # ---- bit-identical in both modes
+    other_mode = None
+    if world == 1:
+        other = "contracted" if args.arith == "exact" else "exact"
+        ctx.set_arithmetic(other)
+        for _ in range(2):
+            restore_resident(); step_resident()
+        ctx.sync()
+        ctx.set_timing(True); ctx.reset_stats()
+        ev_o = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for i in range(args.steps):
+            restore_resident()
+            ev_o[i][0].record(lib_stream); step_resident(); ev_o[i][1].record(lib_stream)
+        ctx.sync()
+        scan_o, _ = ctx.kernel_ms()
+        ctx.set_timing(False)
+        ctx.set_arithmetic(args.arith)
+        other_mode = {"scan_arithmetic": other, "ms_per_step": sum(a.elapsed_time(b) for a, b in ev_o) / args.steps,
+                      "cressman_scan_kernels_ms": scan_o / args.steps}
+
     e2e_ms, e2e_blocking_ms, st_e = 0.0, None, {"h2d_bytes": 0, "d2h_bytes": 0}
     if do_e2e:
         # ---- timed: e2e --------------------------------------------------------------------------------
@@ -852,6 +875,10 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             "scan_kernel_share_of_oa": scan_ms_step / oa_ms if oa_ms > 0 else None,
         }
         roofline["hbm"]["frac"] = roofline["hbm"]["achieved"] / hbm_peak
+        if other_mode is not None and other_mode["cressman_scan_kernels_ms"] > 0:
+            # same algorithmic work, same peak: the fraction scales with the kernel time
+            other_mode["frac"] = roofline["frac"] * scan_ms_step / other_mode["cressman_scan_kernels_ms"]
+            roofline["other_arithmetic"] = other_mode
         # the buddy check's all-pairs kernel against the same lane-instruction peak: 12 issued
         # instructions per examined pair (2 sub, 2 mul, add, 2 compares, and, count, select, add + the
         # shared-memory load), and how much of the QC stage is that kernel (the rest builds lists)
