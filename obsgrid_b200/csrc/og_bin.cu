@@ -26,6 +26,7 @@ struct BinDev {
     int ns;
     int own_rank, own_world;   // cells dealt to ranks: (local cell index) % own_world == own_rank are built
     const short4* box;
+    const int* key;     // nullable: list entry of an ob instead of its local index
     int* cell_count;
     int* cell_cursor;
     int* cell_start;
@@ -129,9 +130,10 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
     const int nc = S.ncx * S.ncy;
     const short4 box = (li < S.n) ? A.box[S.ob_off + li] : make_short4(1, 0, 1, 0);
     if (nc > HCAP) {
+        const int ent = (A.key && li < S.n) ? A.key[S.ob_off + li] : li;
         for_each_cell(A, S, box, [&](int c) {
             const int pos = atomicAdd(&A.cell_cursor[c], 1);
-            A.cell_list[A.cell_start[c] + pos] = li;
+            A.cell_list[A.cell_start[c] + pos] = ent;
         });
         return;
     }
@@ -147,9 +149,10 @@ __global__ void __launch_bounds__(256) bin_fill_kernel(BinDev A)
         s_hist[q] = 0;
     }
     __syncthreads();
+    const int ent = (A.key && li < S.n) ? A.key[S.ob_off + li] : li;
     for_each_cell(A, S, box, [&](int c) {
         const int q = c - S.cell_off;
-        A.cell_list[s_base[q] + atomicAdd(&s_hist[q], 1)] = li;
+        A.cell_list[s_base[q] + atomicAdd(&s_hist[q], 1)] = ent;
     });
 }
 
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(BIN_THREADS) cell_sort_kernel(BinDev A)
 } // namespace
 
 int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, const short4* d_box,
-              bool sorted, BinLists* out, int own_rank, int own_world)
+              bool sorted, BinLists* out, int own_rank, int own_world, const int* key)
 {
     const int ns = (int)slabs.size();
     cudaStream_t st = ctx->stream;
@@ -397,7 +400,7 @@ int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, c
     OG_TRY(ctx->reserve_t((t + ".cursor").c_str(), (size_t)ncells + 1, &A.cell_cursor));
     OG_TRY(ctx->reserve_t((t + ".start").c_str(), (size_t)ncells + 1, &A.cell_start));
     A.slabs = d_slabs; A.ns = ns; A.box = d_box;
-    A.own_rank = own_rank; A.own_world = own_world;
+    A.own_rank = own_rank; A.own_world = own_world; A.key = key;
     std::vector<BinSlab> hs(slabs);
     int nblk = 0;
     for (BinSlab& q : hs) { q.blk_off = nblk; nblk += (q.n + 255) / 256; }

@@ -188,8 +188,11 @@ struct BinLists {
 // the stream once (the list size comes back to the host to size the lists).
 // own_rank / own_world: build the lists of the cells with (cell index within the slab) % own_world ==
 // own_rank only (the other cells get empty lists); 0 / 1: every cell.
+// key (nullable): per ob (batch-wide index) the value stored in the lists instead of the local index
+// -- with sorted lists, the order of the entries (the buddy check orders a cell's targets in space
+// this way); entries must stay distinct non-negative ints.
 int bin_build(og_ctx* ctx, const char* tag, const std::vector<BinSlab>& slabs, const short4* d_box,
-              bool sorted, BinLists* out, int own_rank = 0, int own_world = 1);
+              bool sorted, BinLists* out, int own_rank = 0, int own_world = 1, const int* key = nullptr);
 
 // ---- density / distance (og_density.cu) -------------------------------------------------
 int ob_density_device(og_ctx* ctx, const float* d_x, const float* d_y, float grid_dist, int n,

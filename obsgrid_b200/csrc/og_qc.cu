@@ -37,6 +37,8 @@ struct QcSlabDev {
     float reach;        // >= the largest |dx| or |dy| (grid cells) a buddy pair can have
     int ncx, ncy, cell_off;   // cells of the slab (edge ~ reach), first cell in the per-cell arrays
     int blk_off;              // first 256-ob block of the slab in the flat per-ob grids
+    int cell;                 // cell edge in grid points
+    int key_shift;            // home-list entry = (Morton code of the ob's place in its cell << key_shift) | index
 };
 
 struct QcDev {
@@ -65,6 +67,7 @@ struct QcDev {
     int* kob;            // buddy_num_final
     float* err;          // buddy err
     int* changed;
+    int* home_key;       // entry of the ob in its cell's target list (see QcSlabDev::key_shift)
     short4* home_box;    // the grid cell an ob sits in
     short4* range_box;   // every grid cell within `reach` of it
     const int* home_count; const int* home_start; const int* home_list;      // targets of a cell
@@ -156,6 +159,12 @@ __global__ void __launch_bounds__(256) qc_prep_kernel(QcDev A)
         const float fi = (float)A.iew, fj = (float)A.jns;
         const int hx = (int)fminf(fmaxf(floorf(x), 1.f), fi), hy = (int)fminf(fmaxf(floorf(y), 1.f), fj);
         A.home_box[gi] = make_short4((short)hx, (short)hx, (short)hy, (short)hy);
+        // where in its cell: an 8 x 8 raster, Z-ordered, so that 32 consecutive targets of the sorted
+        // list sit close together and their common bounding box culls the cell's candidates
+        const int ox = (hx - 1) % S.cell, oy = (hy - 1) % S.cell;
+        const unsigned sx = (unsigned)(ox * 8 / S.cell), sy = (unsigned)(oy * 8 / S.cell);
+        const unsigned z = (sx & 1u) | ((sy & 1u) << 1) | ((sx & 2u) << 1) | ((sy & 2u) << 2) | ((sx & 4u) << 2) | ((sy & 4u) << 3);
+        A.home_key[gi] = (int)(z << S.key_shift) | li;
         const float r = S.reach;
         A.range_box[gi] = make_short4((short)fminf(fmaxf(floorf(x - r) - 1.f, 1.f), fi),
                                       (short)fminf(fmaxf(ceilf(x + r) + 1.f, 1.f), fi),
@@ -182,66 +191,91 @@ __global__ void __launch_bounds__(128) buddy_items_kernel(QcDev A)
     const int G = (T + 31) / 32;
     const int base = atomicAdd(A.n_items, G);
     for (int g = 0; g < G; ++g) A.items[base + g] = make_int4((int)blockIdx.y, c, g, 0);
-    atomicAdd(A.pairs_examined, (unsigned long long)T * (unsigned long long)A.range_count[c]);
 }
 
 // station_loop_2/3, first half (qc2_module.F90:223-256): buddy count and index-ordered sum.
-// Targets: obs sitting in the cell; candidates: the index-ordered list of the obs within
-// reach of the cell.  The four warps of a CTA take four consecutive items: where they are four
-// target groups of ONE cell (a dense network) the candidates are staged once for the block; where
-// they belong to different cells (upper-air slabs: a dozen targets per cell) every warp stages its
-// own.
+// Targets: 32 obs of a cell that sit close together (the cell's target list is Z-ordered in space);
+// candidates: the index-ordered list of the obs within reach of the cell, culled -- in order -- to
+// those within reach of the bounding box of the 32 targets.  The reference tests N - 1 candidates per
+// target; a cell list holds (2.5 reach)^2 of area where the network is dense, the culled list about
+// 3.8 reach^2, against the pi reach^2 that are buddies.
+#ifndef OG_BP_STAGE
+#define OG_BP_STAGE 128
+#endif
+constexpr int BP_STAGE = OG_BP_STAGE;     // candidates fetched per round (four per lane, all in flight)
 __global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = (int)blockIdx.x * BP_WARPS + warp;
-    const int n_items = *A.n_items;
-    __shared__ float4 tile_all[BP_WARPS * BP_CHUNK];
-    __shared__ int s_cell[BP_WARPS];
-    const bool live = item < n_items;
-    const int4 it = live ? A.items[item] : make_int4(0, -1, 0, 0);
-    if (lane == 0) s_cell[warp] = it.y;
-    __syncthreads();
-    const bool together = (s_cell[0] >= 0) && (s_cell[0] == s_cell[1]) && (s_cell[1] == s_cell[2]) && (s_cell[2] == s_cell[3]);
-    if (!live && !together) return;
+    if (item >= *A.n_items) return;
+    const int4 it = A.items[item];
     const QcSlabDev& S = A.slabs[it.x];
     const int c = it.y, t0 = it.z * 32;
     const int T = A.home_count[c], L = A.range_count[c];
     const int* __restrict__ tl = A.home_list + A.home_start[c];
     const int* __restrict__ cl = A.range_list + A.range_start[c];
     const float tlo = S.t_lo, thi = S.t_hi;
+    __shared__ float4 tile_all[BP_WARPS][BP_CHUNK + BP_STAGE];
+    float4* tile = tile_all[warp];
     const bool valid = t0 + lane < T;
-    const int gi = S.ob_off + (valid ? tl[t0 + lane] : 0);
+    const int gi = S.ob_off + (valid ? (tl[t0 + lane] & ((1 << S.key_shift) - 1)) : 0);
     const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
-    int cnt = 0;
+    // bounding box of the group's targets
+    float bx0 = valid ? me.x : 3.e38f, bx1 = valid ? me.x : -3.e38f, by0 = valid ? me.y : 3.e38f, by1 = valid ? me.y : -3.e38f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, o)); bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, o));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, o)); by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, o));
+    }
+    // a candidate farther than this from the box is farther than t_hi from every target in it (the
+    // margin swallows the roundings of both distance computations): it would add 0 to count and sum
+    const float cull = thi * 1.0001f + 1.e-3f;
+    const unsigned lt = (1u << lane) - 1u;
+    const int nvalid = min(32, T - t0);
+    int cnt = 0, fill = 0;
     float sum = 0.f;
-    const float4* tile = together ? tile_all : tile_all + warp * BP_CHUNK;
-    const int chunk = together ? BP_WARPS * BP_CHUNK : BP_CHUNK;
-    for (int base = 0; base < L; base += chunk) {
-        const int lim = min(chunk, L - base);
-        const int lim8 = (lim + 7) & ~7;
-        if (together) {
-            __syncthreads();
-            for (int k = threadIdx.x; k < lim8; k += BP_THREADS)
-                tile_all[k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
-            __syncthreads();
-        } else {
-            __syncwarp();
-            for (int k = lane; k < lim8; k += 32)
-                tile_all[warp * BP_CHUNK + k] = (k < lim) ? A.q4[S.ob_off + cl[base + k]] : make_float4(1.e30f, 1.e30f, 0.f, 0.f);
-            __syncwarp();
+    unsigned long long evaluated = 0;
+    // (requesting the next round's candidates before this round's pairs are evaluated measured 2 %
+    // slower: 74 registers instead of 68 cost more occupancy than the overlap returns)
+    for (int base = 0; base < L; base += BP_STAGE) {
+        float4 o[BP_STAGE / 32];
+        bool keep[BP_STAGE / 32];
+#pragma unroll
+        for (int u = 0; u < BP_STAGE / 32; ++u) {
+            const int k = base + 32 * u + lane;
+            keep[u] = false;
+            if (k < L) {
+                o[u] = A.q4[S.ob_off + cl[k]];
+                const float dxb = fmaxf(fmaxf(bx0 - o[u].x, o[u].x - bx1), 0.f), dyb = fmaxf(fmaxf(by0 - o[u].y, o[u].y - by1), 0.f);
+                keep[u] = dxb * dxb + dyb * dyb <= cull;
+            }
         }
+#pragma unroll
+        for (int u = 0; u < BP_STAGE / 32; ++u) {
+            const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
+            if (keep[u]) tile[fill + __popc(m & lt)] = o[u];
+            fill += __popc(m);
+        }
+        if (fill > BP_CHUNK || base + BP_STAGE >= L) {
+            const int lim8 = (fill + 7) & ~7;
+            if (fill + lane < lim8) tile[fill + lane] = make_float4(1.e30f, 1.e30f, 0.f, 0.f);
+            __syncwarp();
 #pragma unroll 8
-        for (int q = 0; q < lim8; ++q) {
-            const float4 o = tile[q];
-            const float dx = fsub(me.x, o.x), dy = fsub(me.y, o.y);
-            const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
-            const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
-            cnt += b ? 1 : 0;
-            sum = fadd(sum, b ? o.z : 0.f);
+            for (int q = 0; q < lim8; ++q) {
+                const float4 p = tile[q];
+                const float dx = fsub(me.x, p.x), dy = fsub(me.y, p.y);
+                const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
+                const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
+                cnt += b ? 1 : 0;
+                sum = fadd(sum, b ? p.z : 0.f);
+            }
+            evaluated += (unsigned long long)fill;
+            fill = 0;
+            __syncwarp();
         }
     }
     if (valid) { A.cnt[gi] = cnt; A.sum[gi] = sum; }
+    if (lane == 0) atomicAdd(A.pairs_examined, evaluated * (unsigned long long)nvalid);
 }
 
 // Per cell, the index-ordered sub-list of its candidates that can ever be removed from a
@@ -287,7 +321,7 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass2_kernel(QcDev A)
     const int c = it.y, t0 = it.z * 32;
     const int T = A.home_count[c];
     const bool valid = t0 + lane < T;
-    const int li = valid ? A.home_list[A.home_start[c] + t0 + lane] : 0;
+    const int li = valid ? (A.home_list[A.home_start[c] + t0 + lane] & ((1 << S.key_shift) - 1)) : 0;
     const int gi = S.ob_off + li;
     const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
     const int cnt = valid ? A.cnt[gi] : 0;
@@ -518,6 +552,10 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         const int div = (per_reach2 / 4.f >= 32.f) ? 2 : 1;
         const int cell = std::max(8, (int)ceilf(d.reach / (float)div));
         d.ncx = (b.iew + cell - 1) / cell; d.ncy = (b.jns + cell - 1) / cell;
+        d.cell = cell;
+        d.key_shift = 1;
+        while ((1 << d.key_shift) < std::max(h.n, 2)) ++d.key_shift;
+        if (d.key_shift > 25) { set_error("more than 2^25 observations in one buddy-check slab"); return OG_ERR_INVALID; }
         d.cell_off = ncells_all;
         d.blk_off = nblk_ob;
         nblk_ob += (h.n + 255) / 256;
@@ -549,6 +587,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     A.changed = ctx->d_flag;
     if (b.do_buddy) {
         OG_TRY(ctx->reserve_t("qc.home_box", tot, &A.home_box));
+        OG_TRY(ctx->reserve_t("qc.home_key", tot, &A.home_key));
         OG_TRY(ctx->reserve_t("qc.range_box", tot, &A.range_box));
     }
     A.pairs_examined = ctx->d_counters + 3;
@@ -572,7 +611,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
         BinLists home, range;
         // sharded: this rank's cells only, so the targets (and their candidate lists) are dealt out
         const int orank = sharded ? ctx->shard_rank : 0, oworld = sharded ? ctx->shard_world : 1;
-        OG_TRY(bin_build(ctx, "qc.home", bslabs, A.home_box, false, &home, orank, oworld));
+        OG_TRY(bin_build(ctx, "qc.home", bslabs, A.home_box, true, &home, orank, oworld, A.home_key));
         OG_TRY(bin_build(ctx, "qc.range", bslabs, A.range_box, true, &range, orank, oworld));
         if (sharded) OG_CUDA(cudaMemsetAsync(A.kob, 0xff, tot * sizeof(int), st));
         A.home_count = home.cell_count; A.home_start = home.cell_start; A.home_list = home.cell_list;
