@@ -10,8 +10,10 @@ With f4d = .TRUE. the driver, for every traditional analysis time icount (interv
      weights) gives the first guess; proc_qc on the FDDA time's observations with the observation
      density / distance fields; proc_oa of the surface level only (fdda_loop > 1, proc_oa.F90:365).
 
-The observation density tobbox is handed from one proc_qc to the next as the driver does
-(driver.F90:140, :459, :492 -- proc_qc.F90:349-351, :412-420 accumulate and rescale it in place).
+The observation density tobbox and the distance odis start from zero at every analysis time
+(driver.F90:140-141, inside fdda_ish_loop); proc_qc accumulates the five surface variables into
+tobbox, rescales it and derives odis (proc_qc.F90:349-351, :412-420) -- they are outputs for the
+writer (driver.F90:645, :661-666), nothing downstream of the path reads them.
 Only the surface level of an FDDA time is analysed, so the chain interpolates and checks level 0 of
 the 3-D fields (levels are independent slabs).
 
@@ -48,6 +50,7 @@ def run_chain(backend, cases3d, hourly_cases, ratio=6):
     stored = {}
     h = 0
     for icount, case in enumerate(cases3d, start=1):
+        backend.clear2d(tob)                                     # driver.F90:140-141
         tob = backend.analyse_3d(case, tob)                      # fdda_loop == 1
         stored[icount] = backend.store_fa(case)                  # level 0 of t, u, v, rh; PMSL * 100
         stored.pop(icount - 2, None)
@@ -55,6 +58,7 @@ def run_chain(backend, cases3d, hourly_cases, ratio=6):
             _, cf, c1, c2 = times[h]
             hc = hourly_cases[h]
             backend.first_guess(hc, stored[icount - 1], stored[icount], cf, c1, c2)
+            backend.clear2d(tob)
             tob = backend.analyse_surface(hc, tob)
             h += 1
     return hourly_cases
@@ -70,6 +74,9 @@ class HostBackend:
 
     def zeros2d(self, case):
         return np.zeros((case.iew, case.jns), np.float32)
+
+    def clear2d(self, tob):
+        tob[...] = 0
 
     def analyse_3d(self, case, tob):
         tob, _ = self.p.proc_qc_fdda(case, tob)
@@ -122,6 +129,11 @@ class DeviceBackend:
         with self.torch.cuda.stream(self.stream):
             self.odis = self.torch.zeros((case.iew, case.jns), dtype=self.torch.float32, device=self.device)
             return self.torch.zeros((case.iew, case.jns), dtype=self.torch.float32, device=self.device)
+
+    def clear2d(self, tob):
+        with self.torch.cuda.stream(self.stream):
+            tob.zero_()
+            self.odis.zero_()
 
     def analyse_3d(self, case, tob):
         t, d = self._dev[id(case)]

@@ -624,7 +624,7 @@ def test_qc_time_fdda_density_bit_exact(ctx, oracle):
     base = synth.small_case(iew=90, jns=70, kbu=5, n_sfc=60, n_snd=10, radii=(6, 4), seed=23,
                             dx_m=60000.0)      # 250 km = 4.2 cells: boxes with and without obs
     rng = np.random.default_rng(2)
-    tb0 = rng.integers(0, 3, (base.iew, base.jns)).astype(np.float32)   # the driver hands in the previous tobbox
+    tb0 = rng.integers(0, 3, (base.iew, base.jns)).astype(np.float32)   # the driver hands in zeros (driver.F90:140); any start must work
     for tb_in in (np.zeros_like(tb0), tb0):
         cpu, gpu = base.copy(), base.copy()
         tb_c, od_c = oracle.qc_time_fdda(cpu, tb_in)
@@ -657,7 +657,7 @@ class _OracleProc:
 def test_surface_fdda_chain(ctx, oracle):
     """BASELINE configs[3] as the pipeline it is (driver.F90:107-113, :306-341, :561-563): 3-D analyses of
     the traditional times -> store_fa -> temporal_interp -> proc_qc with the observation density ->
-    surface-only proc_oa for every FDDA time in between, tobbox handed on from call to call.
+    surface-only proc_oa for every FDDA time in between, tobbox / odis cleared at every time (driver.F90:140-141).
       * the GPU chain with host arrays and the GPU chain with everything resident (fdda.DeviceBackend)
         give the same bits;
       * against the oracle composition: every flag, t and slp bit for bit along the whole chain;
