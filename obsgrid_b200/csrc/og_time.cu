@@ -475,7 +475,9 @@ int qc_time_core(og_ctx* c, const TimeDev& T, const og_qc_params* p, const Level
     // row.  That is the same value: selection only asks qc < 2**20, which no flag set here can
     // change, no test reads the flags, and modify_qc_flag / add_to_qc_flag set one bit of a
     // non-negative integer (qc0_module.F90:27-31, :55-72), so (q | rh_bits) | dew_bits either way.
-    {
+    // any_checks_to_do (proc_qc.F90:237): with both tests off the reference skips the level x variable
+    // loop altogether -- no selection, no 'put', no observation density -- and still runs what follows
+    if (p->qc_test_error_max || p->qc_test_buddy) {
         if (p->qc_dewpoint) {
             OG_TRY(c->reserve_t("qc.w_dew", per * nlev, &w_dew));
             dewfield_kernel<<<nblk(per * nlev), 256, 0, c->stream>>>(w_t, w_rh, w_dew, per * nlev);

@@ -62,7 +62,7 @@ def proc_qc_per_slab(ctx, case):
     dom = _in_domain(case)
     bogus = case.bogus if case.bogus is not None else np.zeros(case.nrep, np.int32)
     calls = 0
-    for k in range(case.kbu):
+    for k in range(case.kbu if (p.qc_test_error_max or p.qc_test_buddy) else 0):     # any_checks_to_do, proc_qc.F90:237
         pk = float(case.pressure[k])
         for ivar in (1, 2, 3, 4, 5, 7):
             if k > 0 and ivar == 5:

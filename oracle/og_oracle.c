@@ -1051,6 +1051,7 @@ static void qc_level_density(const og_time_desc* d, const og_qc_params* p, int k
 {
     const int iew = d->iew, jns = d->jns, nrep = d->nrep;
     const size_t npts = (size_t)iew * jns;
+    if (!p->qc_test_error_max && !p->qc_test_buddy) return;      /* any_checks_to_do, proc_qc.F90:237 */
     float* gridded = (float*)malloc(sizeof(float) * npts);
     float* gt = NULL;
     size_t nn = (size_t)(nrep > 0 ? nrep : 1);

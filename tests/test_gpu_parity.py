@@ -864,6 +864,29 @@ def test_dev_item_lists_equal_the_range_calls(ctx):
         ctx.dev_proc_qc_items(d, base.qc_params, [3, 2], [0, 0])
 
 
+def test_no_qc_test_selected_leaves_only_the_consistency_pass(ctx, oracle):
+    """any_checks_to_do (proc_qc.F90:237): with error_max and buddy_check both off the level x variable
+    loop is skipped -- no flags from the tests, no dew point stored, no observation density -- while
+    tobbox / 5, obs_distance and qc_consistency still run."""
+    from obsgrid_b200 import perslab
+    base = synth.small_case(iew=50, jns=44, kbu=4, n_sfc=200, n_snd=40, radii=(5, 3), seed=31)
+    base.qc_params.qc_test_error_max = 0
+    base.qc_params.qc_test_buddy = 0
+    base.qc_u[0, ::7] |= 1 << 17                     # something for qc_consistency to copy to V
+    cpu, gpu, slab = base.copy(), base.copy(), base.copy()
+    tb0 = np.zeros((base.iew, base.jns), np.float32)
+    tb_c, od_c = oracle.qc_time_fdda(cpu, tb0)
+    tb_g, od_g = ctx.proc_qc_fdda(gpu, tb0)
+    perslab.proc_qc_per_slab(ctx, slab)
+    assert not tb_c.any()
+    np.testing.assert_array_equal(tb_c, tb_g)
+    np.testing.assert_array_equal(od_c, od_g)
+    for nm in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_slp"):
+        np.testing.assert_array_equal(getattr(cpu, nm), getattr(gpu, nm), err_msg=nm)
+        np.testing.assert_array_equal(getattr(cpu, nm), getattr(slab, nm), err_msg="per slab " + nm)
+    assert np.array_equal(gpu.qc_t, base.qc_t) and np.any(gpu.qc_v != base.qc_v)
+
+
 def test_upper_levels_under_surface_only_are_a_no_op(ctx):
     """proc_oa.F90:365: with fdda_loop > 1 only the surface level is analysed.  A batch that holds
     upper levels only then has no slab at all -- it must come back clean, fields untouched."""
