@@ -880,9 +880,10 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             # same algorithmic work, same peak: the fraction scales with the kernel time
             other_mode["frac"] = roofline["frac"] * scan_ms_step / other_mode["cressman_scan_kernels_ms"]
             roofline["other_arithmetic"] = other_mode
-        # the buddy check's all-pairs kernel against the same lane-instruction peak: 12 issued
-        # instructions per examined pair (2 sub, 2 mul, add, 2 compares, and, count, select, add + the
-        # shared-memory load), and how much of the QC stage is that kernel (the rest builds lists)
+        # the buddy check's all-pairs kernel against the same lane-instruction peak: 12 lane operations
+        # per examined pair as the reference writes them (2 sub, 2 mul, add, 2 compares, and, count,
+        # select, add + the load; the kernel issues fewer: two candidates share packed instructions),
+        # and how much of the QC stage is that kernel (the rest builds lists)
         b_ms = buddy_ms / max(args.steps, 1)
         roofline["buddy"] = {
             "kernel": "buddy_pass1_kernel", "bound": "fp32", "instructions_per_examined_pair": 12,

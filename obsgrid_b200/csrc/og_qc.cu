@@ -74,6 +74,7 @@ struct QcDev {
     const int* range_count; const int* range_start; const int* range_list;  // its candidates
     unsigned long long* pairs_examined;
     int sharded;         // og_set_exchange: only the obs of this rank's cells have cnt / kob / err
+    float one;           // 1.0f the compiler cannot see (add2_of_product, og_device.cuh)
     // diagnostics (nullable)
     float* d_aob; float* d_err_max; float* d_thr_max; float* d_err_buddy; float* d_difmax;
     int* d_bnf;
@@ -215,8 +216,14 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
     const int* __restrict__ tl = A.home_list + A.home_start[c];
     const int* __restrict__ cl = A.range_list + A.range_start[c];
     const float tlo = S.t_lo, thi = S.t_hi;
-    __shared__ float4 tile_all[BP_WARPS][BP_CHUNK + BP_STAGE];
-    float4* tile = tile_all[warp];
+    // the kept candidates as three arrays, so that the pair loop reads two candidates per load and
+    // evaluates them with packed arithmetic against the target (the broadcast operand)
+    constexpr int TCAP = BP_CHUNK + BP_STAGE;
+    __shared__ __align__(16) float tile_all[BP_WARPS][3][TCAP];
+    float* tx = tile_all[warp][0];
+    float* ty = tile_all[warp][1];
+    float* tz = tile_all[warp][2];
+    const float one = A.one;
     const bool valid = t0 + lane < T;
     const int gi = S.ob_off + (valid ? (tl[t0 + lane] & ((1 << S.key_shift) - 1)) : 0);
     const float4 me = valid ? A.q4[gi] : make_float4(-1.e30f, -1.e30f, 0.f, 0.f);
@@ -253,21 +260,27 @@ __global__ void __launch_bounds__(BP_THREADS) buddy_pass1_kernel(QcDev A)
 #pragma unroll
         for (int u = 0; u < BP_STAGE / 32; ++u) {
             const unsigned m = __ballot_sync(0xffffffffu, keep[u]);
-            if (keep[u]) tile[fill + __popc(m & lt)] = o[u];
+            if (keep[u]) { const int w = fill + __popc(m & lt); tx[w] = o[u].x; ty[w] = o[u].y; tz[w] = o[u].z; }
             fill += __popc(m);
         }
         if (fill > BP_CHUNK || base + BP_STAGE >= L) {
             const int lim8 = (fill + 7) & ~7;
-            if (fill + lane < lim8) tile[fill + lane] = make_float4(1.e30f, 1.e30f, 0.f, 0.f);
+            if (fill + lane < lim8) { tx[fill + lane] = 1.e30f; ty[fill + lane] = 1.e30f; tz[fill + lane] = 0.f; }
             __syncwarp();
-#pragma unroll 8
-            for (int q = 0; q < lim8; ++q) {
-                const float4 p = tile[q];
-                const float dx = fsub(me.x, p.x), dy = fsub(me.y, p.y);
-                const float d2 = fadd(fmul(dx, dx), fmul(dy, dy));
-                const bool b = (d2 <= thi) && (d2 >= tlo);   // self: d2 = 0 < t_lo
-                cnt += b ? 1 : 0;
-                sum = fadd(sum, b ? p.z : 0.f);
+            const f32x2 MX = bc(me.x), MY = bc(me.y);
+#pragma unroll 4
+            for (int q = 0; q < lim8; q += 2) {
+                const f32x2 X = *reinterpret_cast<const f32x2*>(tx + q), Y = *reinterpret_cast<const f32x2*>(ty + q);
+                const f32x2 DX = sub2(MX, X), DY = sub2(MY, Y);
+                // dx*dx + dy*dy, each operation rounded as in qc2_module.F90:234-236
+                float d0, d1, z0, z1;
+                upk(add2_of_product(mul2(DX, DX), mul2(DY, DY), one), d0, d1);
+                upk(*reinterpret_cast<const f32x2*>(tz + q), z0, z1);
+                const bool b0 = (d0 <= thi) && (d0 >= tlo);   // self: d2 = 0 < t_lo
+                const bool b1 = (d1 <= thi) && (d1 >= tlo);
+                cnt += (b0 ? 1 : 0) + (b1 ? 1 : 0);
+                sum = fadd(sum, b0 ? z0 : 0.f);
+                sum = fadd(sum, b1 ? z1 : 0.f);
             }
             evaluated += (unsigned long long)fill;
             fill = 0;
@@ -593,6 +606,7 @@ int qc_run_batch(og_ctx* ctx, QcBatch& b)
     A.pairs_examined = ctx->d_counters + 3;
     const bool sharded = ctx->shard_world > 1 && ctx->exchange && b.do_buddy;
     A.sharded = sharded ? 1 : 0;
+    A.one = 1.0f;
     auto exchange = [&](void* p, size_t n, int dtype, int op) -> int {
         if (ctx->exchange(ctx->exchange_user, p, n, dtype, op, (void*)st) != 0) {
             set_error("exchange callback failed"); return OG_ERR_CUDA;
