@@ -246,11 +246,24 @@ MODULE obsgrid_gpu
          INTEGER ( C_INT ) , VALUE :: mode
       END FUNCTION og_set_arithmetic
 
+      !  One slab over several GPUs (include/obsgrid_gpu.h): installs the all-reduce callback
+      !     INTEGER(C_INT) FUNCTION fn ( user , buf , count , dtype , op , stream ) BIND ( C )
+      !  (all arguments by VALUE: C_PTR , C_PTR , C_SIZE_T , C_INT , C_INT , C_PTR); pass it as
+      !  C_FUNLOC ( fn ).  An MPI host wraps ncclAllReduce there (INTEGRATION.md, section 5), with
+      !  rank / world = its MPI rank and size.  world <= 1 or C_NULL_FUNPTR: back to one GPU.
+      INTEGER ( C_INT ) FUNCTION og_set_exchange ( ctx , rank , world , fn , user ) BIND ( C , NAME = 'og_set_exchange' )
+         IMPORT :: C_PTR , C_INT , C_FUNPTR
+         TYPE ( C_PTR ) , VALUE :: ctx
+         INTEGER ( C_INT ) , VALUE :: rank , world
+         TYPE ( C_FUNPTR ) , VALUE :: fn
+         TYPE ( C_PTR ) , VALUE :: user
+      END FUNCTION og_set_exchange
+
    END INTERFACE
 
    PUBLIC :: og_cressman , og_error_max , og_buddy_check , og_ob_density , og_obs_distance , og_fail
    PUBLIC :: og_wind_increment_to_c_grid , og_pres_sfc_from_slp , og_mixing_ratio , og_temporal_interp
-   PUBLIC :: og_qc_time , og_qc_time_fdda , og_oa_time , og_qc_oa_time , og_set_arithmetic
+   PUBLIC :: og_qc_time , og_qc_time_fdda , og_oa_time , og_qc_oa_time , og_set_arithmetic , og_set_exchange
 
 CONTAINS
 
