@@ -659,6 +659,13 @@ MODULE obsgrid_gpu_reports
          TYPE ( og_time_desc ) , INTENT ( IN ) :: table
          INTEGER ( C_INT ) , INTENT ( IN ) :: meas_index ( * )
       END FUNCTION og_table_to_reports
+
+      !  table entries whose measurement also answers a lower level (0: the table path is exact)
+      INTEGER ( C_INT ) FUNCTION og_table_shared_levels ( meas_index , kbu , nrep ) BIND ( C , NAME = 'og_table_shared_levels' )
+         IMPORT :: C_INT
+         INTEGER ( C_INT ) , DIMENSION ( * ) , INTENT ( IN ) :: meas_index
+         INTEGER ( C_INT ) , VALUE :: kbu , nrep
+      END FUNCTION og_table_shared_levels
    END INTERFACE
 
 CONTAINS

@@ -82,10 +82,27 @@ typedef struct og_report {
 int og_reports_to_table(og_report* reports, int nrep, og_meas* meas, int nmeas, int date, int time,
                         int request_p_diff, og_time_desc* table, int* meas_index);
 
+/* How many table entries share their measurement with an entry of a lower level of the same report:
+ * with use_p_tolerance_one_lev and a tolerance wider than half the spacing of two analysis levels, one
+ * single-level measurement answers both.  0 -- always so with the namelist defaults (tolerance off, or
+ * 700 Pa against levels at least 2500 Pa apart) -- means the table path reproduces the per-slab calls
+ * of the reference exactly.  Otherwise the reference checks such a measurement level after level, each
+ * time starting from the flags the previous level stored, and qc_consistency's assignments then see a
+ * different history than the batched run, where every level starts from the incoming flags:
+ * og_table_to_reports returns the union of the bits the levels set (identical in all but those
+ * qc_consistency corner cases), and the analysis of one of the two levels does not see the other
+ * level's verdict. */
+int og_table_shared_levels(const int* meas_index, int kbu, int nrep);
+
 /* 'put' of every slab: the flag rows of `table` (after og_qc_time / og_time_download) go back into
  * the measurements (u, v, temperature, rh flags; dew_point data and flag where the DEWPOINT slab
  * ran), qc_slp into ground%slp.  A report that has table entries but lies outside the domain of the
- * analysis (proc_ob_access.F90:231-240) is marked discard, its flags are left alone.  Then
+ * analysis (proc_ob_access.F90:231-240) is marked discard, its flags are left alone.  Flags go back
+ * to the measurement the value was read from.  (One defect of the reference is deliberately not
+ * reproduced: store_ob searches the level on its own, ob_access_module.F90:708-740, and unlike
+ * query_ob, :399-402, does not skip the surface measurement -- for a sounding whose surface pressure
+ * lies within 1 Pa of an analysis level that it also reports, the reference stores that level's
+ * checked value and flag into the SURFACE measurement, overwriting the surface observation.)  Then
  * qc_consistency (qc0_module.F90:313-434) runs over every measurement of every report -- the table
  * rows have been through it on the device and it is idempotent; this covers the levels that are
  * no analysis level and the speed / direction copies of the wind flag -- and reports outside the

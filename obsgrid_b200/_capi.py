@@ -154,6 +154,7 @@ SIGNATURES = {
     "og_reports_to_table": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.POINTER(OgTimeDesc), _vp]),
     "og_table_to_reports": (C.c_int, [_vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(OgTimeDesc), _vp]),
+    "og_table_shared_levels": (C.c_int, [_vp, C.c_int, C.c_int]),
     "og_dev_temporal_interp": (C.c_int, [_vp, _vp, _vp, _vp] + [C.c_int] * 7),
     "og_dev_qc_time_fdda": (C.c_int, [_vp, C.POINTER(OgTimeDesc), C.POINTER(OgQcParams), _vp, _vp]),
     "og_dev_scale_field": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_float, C.c_int]),

@@ -221,6 +221,20 @@ extern "C" int og_reports_to_table(og_report* reports, int nrep, og_meas* meas, 
     return OG_OK;
 }
 
+extern "C" int og_table_shared_levels(const int* meas_index, int kbu, int nrep)
+{
+    if (!meas_index || kbu < 1 || nrep < 0) return 0;
+    int shared = 0;
+    for (int r = 0; r < nrep; ++r)
+        for (int k = 1; k < kbu; ++k) {
+            const int mi = meas_index[(size_t)k * nrep + r];
+            if (mi < 0) continue;
+            for (int kk = 0; kk < k; ++kk)
+                if (meas_index[(size_t)kk * nrep + r] == mi) { ++shared; break; }
+        }
+    return shared;
+}
+
 extern "C" int og_table_to_reports(og_report* reports, int nrep, og_meas* meas, int nmeas, int date, int time,
                                    const og_time_desc* T, const int* meas_index)
 {
@@ -253,13 +267,26 @@ extern "C" int og_table_to_reports(og_report* reports, int nrep, og_meas* meas, 
             const int mi = meas_index[e];
             if (mi < 0) continue;
             og_meas& v = meas[mi];
-            if (not_missing(T->ob_u[e])) v.u.qc = T->qc_u[e];
-            if (not_missing(T->ob_v[e])) v.v.qc = T->qc_v[e];
-            if (not_missing(T->ob_t[e])) v.temperature.qc = T->qc_t[e];
-            if (not_missing(T->ob_rh[e])) v.rh.qc = T->qc_rh[e];
+            // With a pressure tolerance wider than half the spacing of the analysis levels one
+            // single-level measurement answers two of them.  The reference checks it at the lower
+            // level, stores the flags, and checks it again at the next level starting from those
+            // flags; the checks only set bits and do not read them, so the measurement ends with
+            // the union of what its levels set -- here: OR into what an earlier level left.
+            bool again = false;
+            for (int kk = 0; kk < k && !again; ++kk) again = meas_index[(size_t)kk * nrep + r] == mi;
+            // (store_ob looks for the level on its own, ob_access_module.F90:708-740, and does not skip
+            // the surface measurement as query_ob does, :399-402: a sounding whose surface pressure is
+            // within 1 Pa of an analysis level it also reports has that level's checked value and flag
+            // stored into its SURFACE measurement by the reference.  That defect is not reproduced:
+            // flags go back to the measurement the value was read from.  include/obsgrid_reports.h)
+            auto put = [&](og_field& f, int q) { f.qc = again ? (f.qc | q) : q; };
+            if (not_missing(T->ob_u[e])) put(v.u, T->qc_u[e]);
+            if (not_missing(T->ob_v[e])) put(v.v, T->qc_v[e]);
+            if (not_missing(T->ob_t[e])) put(v.temperature, T->qc_t[e]);
+            if (not_missing(T->ob_rh[e])) put(v.rh, T->qc_rh[e]);
             if (T->ob_td && T->qc_td) {                                         // store_ob 'DEWPOINT', :645-657 / :771-774
                 v.dew_point.data = T->ob_td[e];
-                v.dew_point.qc = T->qc_td[e];
+                put(v.dew_point, T->qc_td[e]);
             }
         }
     }

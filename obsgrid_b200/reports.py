@@ -110,6 +110,35 @@ def table_to_reports(t: Table, rl: ReportList, date, time):
                                           t.meas_index.ctypes.data_as(C.c_void_p)), "og_table_to_reports")
 
 
+def shared_levels(t: Table) -> int:
+    """Table entries whose measurement also answers a lower level of the same report
+    (og_table_shared_levels: 0 means the table path is exact, see include/obsgrid_reports.h)."""
+    return int(_capi.lib().og_table_shared_levels(t.meas_index.ctypes.data_as(C.c_void_p), t.kbu, t.nrep))
+
+
+def store_ob_defect_reports(rl: ReportList, pressure) -> list:
+    """Reports that trip the reference's store_ob defect (include/obsgrid_reports.h): at least two
+    measurements, and the FIRST measurement within 1 Pa of some analysis level is not the one query_ob
+    answers that level with (query_ob skips a surface measurement: height within 1 m of the elevation)."""
+    out = []
+    p_pa = [np.float32(p) * np.float32(100.0) for p in np.asarray(pressure, np.float32) if int(round(float(p))) != 1001]
+    for i, r in enumerate(rl.reports):
+        if r.n_meas < 2:
+            continue
+        m = rl.meas[r.first_meas:r.first_meas + r.n_meas]
+        for lv in p_pa:
+            near = np.flatnonzero(np.abs(m["pressure"]["data"] - lv) < np.float32(1.0))
+            if near.size == 0:
+                continue
+            first = near[0]
+            h = m["height"]["data"][first]
+            is_sfc = abs(float(h) - float(r.elevation)) < 1.0 and abs(float(h) - MISSING) >= 1.0
+            if is_sfc and near.size > 1:
+                out.append(i)
+                break
+    return out
+
+
 def _pad(s: str, n: int) -> bytes:
     return s.encode().ljust(n)[:n]
 

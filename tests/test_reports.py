@@ -171,3 +171,70 @@ def test_gpu_qc_oa_pipelines_carry_the_optional_rows(ctx, oracle):
         for n in ("qc_u", "qc_v", "qc_t", "qc_rh", "qc_td", "qc_slp", "ob_td", "t", "slp"):
             np.testing.assert_array_equal(getattr(got, n), getattr(ref, n), err_msg=n)
     assert np.any(ref.qc_td != base.qc_td)
+
+
+def _round_trip_both_ways(oracle, case, rl, date, time, p_diff):
+    a, b = rl.copy(), rl.copy()
+    assert oracle.qc_time_reports(case, a, date, time, p_diff) == 0
+    _use_requests_of_proc_oa(oracle, case, a, date, time, p_diff)
+    t = _qc_through_table(case, b, date, time, p_diff, lambda c: oracle.qc_time(c))
+    return a, b, t
+
+
+def test_the_store_ob_defect_is_detected_not_reproduced(oracle):
+    """ob_access_module.F90:708-740 against :399-402: query_ob skips the surface measurement when it looks
+    for a pressure level, store_ob does not.  A sounding whose surface pressure lies within 1 Pa of an
+    analysis level it also reports gets that level's checked value stored into its SURFACE measurement
+    by the reference (profiles/exp/fuzz_reports.py found the case).  The table path does not reproduce
+    the overwrite: it differs from the as-written calls on exactly those reports, which
+    reports.store_ob_defect_reports names, and on no other."""
+    case = _case(seed=21, kbu=5)
+    rl, date, time = R.synthetic_reports(case, seed=33)
+    for fld in ("u", "v", "temperature", "rh"):
+        rl.meas[fld]["qc"][...] = 0                          # keep the example to the one effect
+    lvl = np.float32(case.pressure[1]) * np.float32(100.0)
+    for rep in rl.reports:
+        if rep.n_meas < 3 or rep.bogus or rep.discard:
+            continue
+        m0, m1 = rep.first_meas, rep.first_meas + 1
+        if abs(float(rl.meas["height"]["data"][m0]) - rep.elevation) > 0.5:
+            continue                                         # no surface measurement first
+        rl.meas["pressure"]["data"][m0] = lvl - np.float32(0.98)   # the surface, a hair off the analysis level
+        rl.meas["pressure"]["data"][m1] = lvl - np.float32(0.9)    # and the sounding's own level there
+        rl.meas["height"]["data"][m1] = rep.elevation + 300.0
+        for f, v in (("u", 11.0), ("v", 7.0), ("temperature", 280.0), ("rh", 60.0)):
+            rl.meas[f]["data"][m1] = v
+    hit = R.store_ob_defect_reports(rl, case.pressure)
+    assert len(hit) > 5
+    a, b, t = _round_trip_both_ways(oracle, case, rl, date, time, 1)
+    # the reference overwrote surface measurements ...
+    over = [i for i in hit if a.meas["u"]["data"][rl.reports[i].first_meas] == np.float32(11.0)]
+    assert len(over) > 3
+    # ... the table path kept them, and agrees with the as-written calls everywhere else
+    for i in hit:
+        r = rl.reports[i]
+        assert b.meas["u"]["data"][r.first_meas] == rl.meas["u"]["data"][r.first_meas]
+    keep = np.ones(rl.meas.size, bool)
+    for i in hit:
+        r = rl.reports[i]
+        keep[r.first_meas:r.first_meas + r.n_meas] = False
+    for fld in ("u", "v", "temperature", "rh", "dew_point", "speed", "direction", "pressure", "height"):
+        np.testing.assert_array_equal(a.meas[fld]["qc"][keep], b.meas[fld]["qc"][keep], err_msg=fld)
+        np.testing.assert_array_equal(a.meas[fld]["data"][keep], b.meas[fld]["data"][keep], err_msg=fld)
+    # without the coincidence there is no such report
+    assert R.store_ob_defect_reports(R.synthetic_reports(_case(seed=5), seed=8)[0], _case(seed=5).pressure) == []
+
+
+def test_one_measurement_answering_two_levels_is_reported(oracle):
+    """use_p_tolerance_one_lev with a tolerance wider than half the spacing of two analysis levels:
+    og_table_shared_levels counts the entries; the flags that come back are the union of what the
+    levels set (exact except for qc_consistency corner cases, include/obsgrid_reports.h)."""
+    case = synth.small_case(iew=60, jns=50, kbu=9, n_sfc=300, n_snd=120, radii=(5, 3), seed=104)
+    assert abs(float(case.pressure[1]) - float(case.pressure[2])) * 100.0 < 2 * 1500
+    rl, date, time = R.synthetic_reports(case, seed=104 * 7 + 1)
+    a, b, t = _round_trip_both_ways(oracle, case, rl, date, time, 1500)
+    assert R.shared_levels(t) > 0
+    _assert_lists_equal(a, b)                      # this case: the union is the reference's result
+    a1, b1, t1 = _round_trip_both_ways(oracle, case, rl, date, time, 1)
+    assert R.shared_levels(t1) == 0
+    _assert_lists_equal(a1, b1)
