@@ -87,11 +87,16 @@ int og_reports_to_table(og_report* reports, int nrep, og_meas* meas, int nmeas, 
  * single-level measurement answers both.  0 -- always so with the namelist defaults (tolerance off, or
  * 700 Pa against levels at least 2500 Pa apart) -- means the table path reproduces the per-slab calls
  * of the reference exactly.  Otherwise the reference checks such a measurement level after level, each
- * time starting from the flags the previous level stored, and qc_consistency's assignments then see a
- * different history than the batched run, where every level starts from the incoming flags:
- * og_table_to_reports returns the union of the bits the levels set (identical in all but those
- * qc_consistency corner cases), and the analysis of one of the two levels does not see the other
- * level's verdict. */
+ * time starting from the flags the previous level stored, and qc_consistency runs once at the end on
+ * what the levels left.  The exact path for that regime defers the consistency pass to the list:
+ *     og_qc_time_levels(ctx, table, qc, 0, kbu, run_consistency = 0);
+ *     og_table_to_reports(...);      -- union of the bits the levels set, then qc_consistency
+ *     og_reports_to_table(...);      -- the rows proc_oa's 'use' requests would read
+ *     og_oa_time(ctx, table, oa, 0, kbu);
+ * (76 of 76 such cases of profiles/exp/fuzz_reports.py identical to the as-written calls.)  With
+ * the per-row consistency of og_qc_time left on, the flags that come back are still the union, but
+ * qc_consistency's assignments (v.qc = qc_u) have then seen each level on its own: 1 of the 76 cases
+ * differed, and the analysis of one of the two levels does not see the other level's verdict. */
 int og_table_shared_levels(const int* meas_index, int kbu, int nrep);
 
 /* 'put' of every slab: the flag rows of `table` (after og_qc_time / og_time_download) go back into

@@ -238,3 +238,31 @@ def test_one_measurement_answering_two_levels_is_reported(oracle):
     a1, b1, t1 = _round_trip_both_ways(oracle, case, rl, date, time, 1)
     assert R.shared_levels(t1) == 0
     _assert_lists_equal(a1, b1)
+
+
+def test_shared_levels_are_exact_with_the_consistency_pass_left_to_the_list(oracle):
+    """The recipe of include/obsgrid_reports.h for that regime: og_qc_time with run_consistency = 0, then
+    og_table_to_reports (union of the levels' bits, qc_consistency once, as the reference runs it).  Seed
+    179 of profiles/exp/fuzz_reports.py is the case where the per-row consistency pass changes a flag."""
+    seed, p_diff = 179, 1500
+    case = synth.small_case(iew=60, jns=50, kbu=int(np.random.default_rng(seed).integers(3, 12)), n_sfc=300, n_snd=120,
+                            radii=(5, 3), seed=seed)
+    rl, date, time = R.synthetic_reports(case, seed=seed * 7 + 1)
+    a, rows, lst = rl.copy(), rl.copy(), rl.copy()
+    assert oracle.qc_time_reports(case, a, date, time, p_diff) == 0
+    _use_requests_of_proc_oa(oracle, case, a, date, time, p_diff)
+    t = _qc_through_table(case, rows, date, time, p_diff, lambda c: oracle.qc_time(c))
+    assert R.shared_levels(t) > 0
+    with pytest.raises(AssertionError):
+        _assert_lists_equal(a, rows)                                   # consistency per row: one flag differs
+    _qc_through_table(case, lst, date, time, p_diff, lambda c: oracle.qc_time(c, run_consistency=False))
+    _assert_lists_equal(a, lst)                                        # consistency on the list: exact
+    # and the table rebuilt from that list is what proc_oa's 'use' requests read
+    t2 = R.reports_to_table(lst.copy(), case.iew, case.jns, case.pressure, date, time, p_diff)
+    for k in range(case.kbu):
+        for var in (1, 2, 3, 4):
+            got = oracle.get_obs(a.copy(), False, var, float(case.pressure[k]), date, time, p_diff, FAILS_ERROR_MAX,
+                                 case.iew, case.jns)
+            idx, v, q = _select_from_table(t2, k, var, FAILS_ERROR_MAX, False)
+            np.testing.assert_array_equal(got["index"], idx, err_msg=f"k={k} var={var}")
+            np.testing.assert_array_equal(got["qc"], q[idx])
