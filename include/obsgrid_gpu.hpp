@@ -19,6 +19,7 @@
 #include <string>
 
 #include "obsgrid_gpu.h"
+#include "obsgrid_reports.h"
 
 namespace og {
 
@@ -43,6 +44,27 @@ public:
     og_ctx* handle() const { return h_; }
 
     void set_arithmetic(int mode) { check(og_set_arithmetic(h_, mode), "og_set_arithmetic"); }
+
+    // One slab over several GPUs: installs the all-reduce callback (obsgrid_gpu.h, og_set_exchange);
+    // every rank must then make the same calls on the same batches.  world <= 1: back to one GPU.
+    void set_exchange(int rank, int world, og_exchange_fn fn, void* user)
+    {
+        check(og_set_exchange(h_, rank, world, fn, user), "og_set_exchange");
+    }
+
+    // The report list of one analysis time -> the flat table proc_qc / proc_oa run on, and the flags
+    // back (obsgrid_reports.h: query_ob / store_ob / proc_ob_access / qc_consistency semantics).
+    static void reports_to_table(og_report* reports, int nrep, og_meas* meas, int nmeas, int date, int time,
+                                 int request_p_diff, og_time_desc& table, int* meas_index)
+    {
+        check(og_reports_to_table(reports, nrep, meas, nmeas, date, time, request_p_diff, &table, meas_index),
+              "og_reports_to_table");
+    }
+    static void table_to_reports(og_report* reports, int nrep, og_meas* meas, int nmeas, int date, int time,
+                                 const og_time_desc& table, const int* meas_index)
+    {
+        check(og_table_to_reports(reports, nrep, meas, nmeas, date, time, &table, meas_index), "og_table_to_reports");
+    }
 
     // SUBROUTINE cressman ( obs_value , obs , xob , yob , numobs , gridded , iew , jns , crsdot , name ,
     //   radius_influence , dxd , u_banana , v_banana , pressure , passes , smooth_type , lat_center ,
